@@ -1,0 +1,192 @@
+"""ctypes binding of libdcbf.so (include/dcbf.h).  The ONLY compute path of this package.
+
+There is deliberately no fallback: if the shared library is missing it is built with nvcc
+(``dpdk_dc_sand_b200.build``); if that fails, or a call returns a non-zero status, an exception
+is raised.  All pointers handed to the library are raw device (or, for the host plan, host)
+addresses; PyTorch is only the owner of the memory behind them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+OK = 0
+ERR_INVALID_ARG = -1
+ERR_UNSUPPORTED = -2
+ERR_CUDA = -3
+ERR_NO_DEVICE = -4
+ERR_TIMEOUT = -5
+
+FLAG_SIGNED_INPUT = 0x1
+FLAG_FP16_COEFF = 0x2
+FLAG_DEBUG_ROWWISE_EPILOGUE = 0x100
+
+_ROLE_NAMES = {1: "producer", 2: "mma", 3: "epilogue", 4: "convert", 5: "coeff"}
+
+# name -> (restype, argtypes); must list every symbol include/dcbf.h declares (tests check this).
+SIGNATURES = {
+    "dcbf_version": (C.c_int, []),
+    "dcbf_strerror": (C.c_char_p, [C.c_int]),
+    "dcbf_last_cuda_error": (C.c_char_p, []),
+    "dcbf_reorder": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "dcbf_coeffs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                              C.c_double, C.c_void_p]),
+    "dcbf_beamform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_uint, C.c_void_p]),
+    "dcbf_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                             C.c_int, C.c_double, C.c_uint, C.c_void_p]),
+    "dcbf_fused_status": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dcbf_fused_tiling": (None, [C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int)]),
+    "dcbf_host_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_double, C.c_uint, C.c_int, C.c_int]),
+    "dcbf_host_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcbf_host_plan_destroy": (C.c_int, [C.c_void_p]),
+    "dcbf_launch_count": (C.c_ulonglong, []),
+    "dcbf_fused_bytes": (C.c_ulonglong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class DcbfError(RuntimeError):
+    """A libdcbf call failed (CUDA error, unsupported shape, watchdog)."""
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load (building first if needed) libdcbf.so and attach prototypes.  Raises if impossible."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            path = _build.build()
+        lib = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def strerror(status: int) -> str:
+    return load().dcbf_strerror(status).decode()
+
+
+def check(status: int, what: str) -> None:
+    if status == OK:
+        return
+    lib = load()
+    msg = f"{what}: {lib.dcbf_strerror(status).decode()} ({status})"
+    if status == ERR_CUDA:
+        msg += f" [{lib.dcbf_last_cuda_error().decode()}]"
+    if status in (ERR_INVALID_ARG, ERR_UNSUPPORTED):
+        raise ValueError(msg)
+    raise DcbfError(msg)
+
+
+def _ptr(t) -> int:
+    """Device address of a torch tensor (must be contiguous)."""
+    if not t.is_contiguous():
+        raise ValueError("libdcbf needs contiguous buffers")
+    return t.data_ptr()
+
+
+def _stream_handle(stream) -> int:
+    if stream is None:
+        return 0
+    return int(getattr(stream, "cuda_stream", stream))
+
+
+def reorder(samples, reordered, n_batches, n_ants, n_chans, n_samples, stream=None) -> None:
+    check(load().dcbf_reorder(_ptr(samples), _ptr(reordered), n_batches, n_ants, n_chans, n_samples,
+                              _stream_handle(stream)), "dcbf_reorder")
+
+
+def coeffs(delay_vals, out, n_batches, n_pols, n_chans, n_chans_total, n_ants, n_beams, xeng_id, sample_period,
+           stream=None) -> None:
+    check(load().dcbf_coeffs(_ptr(delay_vals), _ptr(out), n_batches, n_pols, n_chans, n_chans_total, n_ants, n_beams,
+                             xeng_id, float(sample_period), _stream_handle(stream)), "dcbf_coeffs")
+
+
+def beamform(reordered, coeff, beams, n_batches, n_chans, n_samples, n_ants, n_beams, flags=0, stream=None) -> None:
+    check(load().dcbf_beamform(_ptr(reordered), _ptr(coeff), _ptr(beams), n_batches, n_chans, n_samples, n_ants,
+                               n_beams, flags, _stream_handle(stream)), "dcbf_beamform")
+
+
+def fused(samples, delay_vals, beams, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id,
+          sample_period, flags=0, stream=None) -> None:
+    check(load().dcbf_fused(_ptr(samples), _ptr(delay_vals), _ptr(beams), n_batches, n_ants, n_chans, n_chans_total,
+                            n_samples, n_beams, xeng_id, float(sample_period), flags, _stream_handle(stream)),
+          "dcbf_fused")
+
+
+def fused_status() -> None:
+    """Synchronise and raise if a fused kernel's pipeline watchdog fired."""
+    role, barrier, block = C.c_int(0), C.c_int(0), C.c_int(0)
+    st = load().dcbf_fused_status(C.byref(role), C.byref(barrier), C.byref(block))
+    if st == ERR_TIMEOUT:
+        raise DcbfError(f"dcbf_fused watchdog: role {_ROLE_NAMES.get(role.value, role.value)} stuck on barrier "
+                        f"{barrier.value} in block {block.value}")
+    check(st, "dcbf_fused_status")
+
+
+def fused_tiling(n_ants, n_beams, flags=0):
+    kb, nt, ntc = C.c_int(0), C.c_int(0), C.c_int(0)
+    load().dcbf_fused_tiling(n_ants, n_beams, flags, C.byref(kb), C.byref(nt), C.byref(ntc))
+    return kb.value, nt.value, ntc.value
+
+
+def fused_bytes(n_batches, n_ants, n_chans, n_samples, n_beams) -> int:
+    return int(load().dcbf_fused_bytes(n_batches, n_ants, n_chans, n_samples, n_beams))
+
+
+def launch_count() -> int:
+    return int(load().dcbf_launch_count())
+
+
+class HostPlan:
+    """dcbf_host_plan_*: fused path on HOST arrays (numpy / pinned), chunked + pipelined over PCIe."""
+
+    def __init__(self, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id, sample_period,
+                 flags=0, chunk_chans=0, n_slots=3):
+        self._h = C.c_void_p(None)
+        self.shape_in = (n_batches, n_ants, n_chans, n_samples, 2, 2)
+        self.shape_dv = (n_chans, n_beams, n_ants, 4)
+        self.shape_out = (n_batches, 2, n_chans, n_samples // 16, 16, 2 * n_beams)
+        check(load().dcbf_host_plan_create(C.byref(self._h), n_batches, n_ants, n_chans, n_chans_total, n_samples,
+                                           n_beams, xeng_id, float(sample_period), flags, chunk_chans, n_slots),
+              "dcbf_host_plan_create")
+
+    def run(self, samples, delay_vals, beams) -> None:
+        """numpy arrays (C-contiguous; pinned for overlap) with the reference shapes; blocks until done."""
+        import numpy as np
+
+        for arr, shape, dt in ((samples, self.shape_in, np.uint8), (delay_vals, self.shape_dv, np.float32),
+                               (beams, self.shape_out, np.float32)):
+            if tuple(arr.shape) != shape or arr.dtype != dt or not arr.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"expected C-contiguous {np.dtype(dt).name} array of shape {shape}, got "
+                                 f"{arr.dtype} {arr.shape}")
+        check(load().dcbf_host_plan_run(self._h, samples.ctypes.data, delay_vals.ctypes.data, beams.ctypes.data),
+              "dcbf_host_plan_run")
+
+    def close(self) -> None:
+        if self._h:
+            load().dcbf_host_plan_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

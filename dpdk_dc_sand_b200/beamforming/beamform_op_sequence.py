@@ -1,0 +1,115 @@
+"""Reorder + coefficient generation + beamform multiplication as one operation.
+
+API mirror of ``beamformer/beamforming/beamform_op_sequence.py`` (template :16-114, sequence :117-157): same
+constructor, same sub-operation attributes (``prebeamform_reorder``, ``beamform_coeff``, ``beamform_mult``),
+same compound buffer names (``bufin_reorder``, ``bufin_delay_vals``, ``bufout_mult``, ``bufint_data``,
+``bufint_coeff``).
+
+Where the reference launches three kernels that round-trip the reordered voltages and the coefficients
+through device memory, ``OpSequence._run`` launches ONE fused sm_100a kernel (``dcbf_fused``, csrc/fused.cu)
+that reads every voltage byte and every delay value once.  The two intermediates are therefore not needed:
+``ensure_all_bound()`` allocates only the three external buffers unless ``materialize_intermediates`` is set
+(or the caller bound them), in which case the stand-alone reorder / coefficient kernels fill them as well so
+that code inspecting ``bufint_*`` after a call still finds the reference's contents.
+"""
+from .. import _capi
+from ..katsdpsigproc import accel
+from .coeff_generator import CoeffGeneratorTemplate
+from .matrix_multiply import MatrixMultiplyTemplate
+from .prebeamform_reorder import PreBeamformReorderTemplate
+
+_INTERMEDIATES = ("bufint_data", "bufint_coeff")
+
+
+class OpSequenceTemplate:
+    """Same constructor as the reference (beamform_op_sequence.py:69-83)."""
+
+    def __init__(self, context, n_batches, n_pols, n_channels_per_stream, n_channels, n_blocks,
+                 n_samples_per_block, n_ants, n_beams, xeng_id, sample_period, n_samples_per_channel) -> None:
+        if n_pols != 2:
+            raise ValueError("n_pols must be 2 (the reference hard-codes it: prebeamform_reorder.py:54)")
+        self.context = context
+        self.preBeamformReorder_template = PreBeamformReorderTemplate(
+            context, n_ants, n_channels_per_stream, n_samples_per_channel, n_batches
+        )
+        self.beamform_coeff_template = CoeffGeneratorTemplate(
+            context, n_batches, n_pols, n_channels_per_stream, n_channels, n_blocks, n_samples_per_block, n_ants,
+            n_beams, xeng_id, sample_period,
+        )
+        self.beamform_mult_template = MatrixMultiplyTemplate(
+            context=context, n_ants=n_ants, n_channels_per_stream=n_channels_per_stream,
+            n_samples_per_channel=n_samples_per_channel, n_beams=n_beams, n_batches=n_batches,
+        )
+
+    def instantiate(self, queue) -> "OpSequence":
+        return OpSequence(self, queue)
+
+
+class OpSequence(accel.OperationSequence):
+    """Fused reorder -> steering coefficients -> beamform.
+
+    Attributes (all optional, set after ``instantiate``):
+        materialize_intermediates: also fill ``bufint_data`` / ``bufint_coeff`` (default False).
+        signed_input: bytes are int8 instead of the reference API's uint8 (default False).
+        fp16_coeff: single fp16 rounding of the coefficients instead of the fp16 hi+lo pair (default False).
+        fused: False runs the three stand-alone kernels like the reference (default True).
+    """
+
+    def __init__(self, template: OpSequenceTemplate, queue) -> None:
+        self.prebeamform_reorder = template.preBeamformReorder_template.instantiate(queue)
+        self.beamform_coeff = template.beamform_coeff_template.instantiate(queue)
+        self.beamform_mult = template.beamform_mult_template.instantiate(queue)
+
+        operations = [
+            ("prebeamform_reorder", self.prebeamform_reorder),
+            ("beamform_coeff", self.beamform_coeff),
+            ("beamform_mult", self.beamform_mult),
+        ]
+        compounds = {
+            "bufin_delay_vals": ["beamform_coeff:delay_vals"],
+            "bufint_coeff": ["beamform_coeff:outCoeffs", "beamform_mult:inCoeffs"],
+            "bufin_reorder": ["prebeamform_reorder:inSamples"],
+            "bufint_data": ["prebeamform_reorder:outReordered", "beamform_mult:inData"],
+            "bufout_mult": ["beamform_mult:outData"],
+        }
+        super().__init__(queue, operations, compounds)
+        self.template = template
+        self.materialize_intermediates = False
+        self.signed_input = False
+        self.fp16_coeff = False
+        self.fused = True
+
+    # -- binding policy ---------------------------------------------------------------------------
+    def _needs(self, name: str) -> bool:
+        return name not in _INTERMEDIATES or self.materialize_intermediates or not self.fused
+
+    def ensure_all_bound(self) -> None:
+        for name in self.slots:
+            if self._needs(name):
+                self.ensure_bound(name)
+
+    def check_all_bound(self) -> None:
+        for name, slot in self.slots.items():
+            if self._needs(name) and not slot.is_bound:
+                raise ValueError(f"slot {name} is not bound")
+
+    def flags(self) -> int:
+        return (_capi.FLAG_SIGNED_INPUT if self.signed_input else 0) | (_capi.FLAG_FP16_COEFF if self.fp16_coeff else 0)
+
+    # -- execution --------------------------------------------------------------------------------
+    def _run(self) -> None:
+        if not self.fused:
+            self.beamform_mult.signed_input = self.signed_input
+            super()._run()
+            return
+        r = self.template.preBeamformReorder_template
+        c = self.template.beamform_coeff_template
+        _capi.fused(
+            self.buffer("bufin_reorder").buffer, self.buffer("bufin_delay_vals").buffer,
+            self.buffer("bufout_mult").buffer, r.n_batches, r.n_ants, r.n_channels_per_stream, c.n_channels,
+            r.n_samples_per_channel, c.n_beams, c.xeng_id, c.sample_period, self.flags(), self.command_queue.stream,
+        )
+        if self.slots["bufint_data"].is_bound:
+            self.prebeamform_reorder()
+        if self.slots["bufint_coeff"].is_bound:
+            self.beamform_coeff()

@@ -1,0 +1,71 @@
+"""Steering-coefficient generation operation (stand-alone stage 2).
+
+API mirror of ``beamformer/beamforming/coeff_generator.py`` (template :106-181, operation :184-250).  The
+numba kernel ``run_coeff_gen`` (:12-103) is replaced by ``dcbf_coeffs`` (csrc/coeffs.cu): float64 phase in the
+reference's operation order, float64 sincos, float32 store; ``delay_vals[c][beam][ant]`` lands at rows
+``2*ant``, columns ``2*beam`` (the consistent indexing of ``unit_test/coeff_generator_cpu.py:125-186``; the
+reference GPU kernel's read index transposes ant/beam, which only uniform delays hide).  The launch does not
+host-synchronise (the reference calls ``cuda.synchronize()``, :250).
+"""
+import numpy as np
+
+from .. import _capi
+from ..katsdpsigproc import accel
+from ..katsdpsigproc.accel import IOSlot, Operation
+
+
+class CoeffGeneratorTemplate:
+    """Same constructor as the reference (coeff_generator.py:138-151)."""
+
+    def __init__(self, context, n_batches: int, n_pols: int, n_channels_per_stream: int, n_channels: int,
+                 n_blocks: int, n_samples_per_block: int, n_ants: int, n_beams: int, xeng_id: int,
+                 sample_period: float) -> None:
+        self.context = context
+        self.n_batches = n_batches
+        self.n_pols = n_pols
+        self.n_channels_per_stream = n_channels_per_stream
+        self.n_channels = n_channels
+        self.n_blocks = n_blocks
+        self.n_samples_per_block = n_samples_per_block
+        self.n_ants = n_ants
+        self.n_beams = n_beams
+        self.xeng_id = xeng_id
+        self.sample_period = sample_period
+
+        dim = accel.Dimension
+        self.delay_vals_data_dimensions = (
+            dim(self.n_channels_per_stream, exact=True),
+            dim(self.n_beams, exact=True),
+            dim(self.n_ants, exact=True),
+            dim(4, exact=True),
+        )
+        self.coeff_data_dimensions = (
+            dim(self.n_batches, exact=True),
+            dim(self.n_pols, exact=True),
+            dim(self.n_channels_per_stream, exact=True),
+            dim(self.n_ants * 2, exact=True),
+            dim(self.n_beams * 2, exact=True),
+        )
+
+    def instantiate(self, command_queue) -> "CoeffGenerator":
+        return CoeffGenerator(self, command_queue)
+
+
+class CoeffGenerator(Operation):
+    """.. rubric:: Slots
+
+    delay_vals: (n_channels_per_stream, n_beams, n_ants, 4), float32 -- {delay_s, delay_rate, phase_rad, phase_rate}
+    outCoeffs: (n_batches, n_pols, n_channels_per_stream, 2*n_ants, 2*n_beams), float32
+    """
+
+    def __init__(self, template: CoeffGeneratorTemplate, command_queue) -> None:
+        super().__init__(command_queue)
+        self.template = template
+        self.slots["delay_vals"] = IOSlot(dimensions=template.delay_vals_data_dimensions, dtype=np.float32)
+        self.slots["outCoeffs"] = IOSlot(dimensions=template.coeff_data_dimensions, dtype=np.float32)
+
+    def _run(self) -> None:
+        t = self.template
+        _capi.coeffs(self.buffer("delay_vals").buffer, self.buffer("outCoeffs").buffer, t.n_batches, t.n_pols,
+                     t.n_channels_per_stream, t.n_channels, t.n_ants, t.n_beams, t.xeng_id, t.sample_period,
+                     self.command_queue.stream)

@@ -1,0 +1,64 @@
+"""Builds libdcbf.so (the C-ABI CUDA library, sm_100a only) in-tree with nvcc.
+
+    python -m dpdk_dc_sand_b200.build [--force]
+
+The shared object lands in ``dpdk_dc_sand_b200/lib/libdcbf.so`` (git-ignored, travels with gpurun).
+nvcc cross-compiles for sm_100a without a GPU, so this also runs in the CPU-only authoring container.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libdcbf.so")
+SOURCES = ["api.cu", "reorder.cu", "coeffs.cu", "beamform.cu", "fused.cu", "host_pipeline.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    "-Xptxas", "-v",
+    "--shared", "-cudart", "shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libdcbf.so cannot be built (no CPU fallback exists)")
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "dcbf.h"), __file__]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu under csrc/ into one shared library; returns its path."""
+    if not force and not _stale():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+           *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB_PATH + ".tmp"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or proc.returncode:
+        sys.stderr.write(proc.stdout + proc.stderr)
+    if proc.returncode:
+        raise RuntimeError("nvcc failed building libdcbf.so")
+    with open(os.path.join(LIB_DIR, "ptxas.log"), "w") as fh:
+        fh.write(proc.stdout + proc.stderr)
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

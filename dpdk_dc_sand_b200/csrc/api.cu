@@ -1,0 +1,123 @@
+// extern "C" entry points of libdcbf.so (declared in include/dcbf.h): argument validation,
+// error bookkeeping and dispatch to the kernel launchers.  No kernels live here.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace dcbf {
+
+static thread_local char g_last_cuda_error[256] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+int record_cuda_error(cudaError_t err, const char* what) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s (%s)", what, cudaGetErrorName(err),
+             cudaGetErrorString(err));
+    return DCBF_ERR_CUDA;
+}
+
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static int check_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return DCBF_ERR_NO_DEVICE;
+    }
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return DCBF_ERR_NO_DEVICE;
+    }
+    // The library carries sm_100a SASS only: anything else cannot run it.
+    return major == 10 ? DCBF_OK : DCBF_ERR_NO_DEVICE;
+}
+
+static bool bad_t(int T) { return T <= 0 || (T % kSamplesPerBlock) != 0; }
+
+}  // namespace dcbf
+
+using namespace dcbf;
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int dcbf_version(void) { return DCBF_VERSION; }
+
+const char* dcbf_strerror(int status) {
+    switch (status) {
+        case DCBF_OK: return "ok";
+        case DCBF_ERR_INVALID_ARG: return "invalid argument (null/misaligned pointer, non-positive dimension or n_samples % 16 != 0)";
+        case DCBF_ERR_UNSUPPORTED: return "unsupported shape for this build";
+        case DCBF_ERR_CUDA: return "CUDA runtime error (see dcbf_last_cuda_error)";
+        case DCBF_ERR_NO_DEVICE: return "current device is not an sm_100 (B200) GPU";
+        case DCBF_ERR_TIMEOUT: return "in-kernel watchdog fired";
+        default: return "unknown dcbf status";
+    }
+}
+
+const char* dcbf_last_cuda_error(void) { return g_last_cuda_error; }
+
+unsigned long long dcbf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+unsigned long long dcbf_fused_bytes(int B, int A, int C, int T, int M) {
+    const unsigned long long in = 1ull * B * A * C * T * kPols * 2;
+    const unsigned long long dv = 1ull * C * M * A * 16;
+    const unsigned long long out = 1ull * B * kPols * C * T * M * 8;
+    return in + dv + out;
+}
+
+int dcbf_reorder(const uint8_t* samples, uint8_t* reordered, int B, int A, int C, int T, dcbf_stream_t stream) {
+    if (!samples || !reordered || B <= 0 || A <= 0 || C <= 0 || bad_t(T)) return DCBF_ERR_INVALID_ARG;
+    if (!aligned16(samples) || !aligned16(reordered)) return DCBF_ERR_INVALID_ARG;
+    if (int e = check_device()) return e;
+    return launch_reorder(samples, reordered, B, A, C, T, static_cast<cudaStream_t>(stream));
+}
+
+int dcbf_coeffs(const float* delay_vals, float* coeffs, int B, int P, int C, int N, int A, int M, int xeng_id,
+                double sample_period, dcbf_stream_t stream) {
+    if (!delay_vals || !coeffs || B <= 0 || P <= 0 || C <= 0 || N <= 0 || A <= 0 || M <= 0 || xeng_id < 0 ||
+        !(sample_period > 0.0))
+        return DCBF_ERR_INVALID_ARG;
+    if (!aligned16(delay_vals) || !aligned16(coeffs)) return DCBF_ERR_INVALID_ARG;
+    if (int e = check_device()) return e;
+    return launch_coeffs(delay_vals, coeffs, B, P, C, N, A, M, xeng_id, sample_period,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int dcbf_beamform(const uint8_t* reordered, const float* coeffs, float* beams, int B, int C, int T, int A, int M,
+                  unsigned flags, dcbf_stream_t stream) {
+    if (!reordered || !coeffs || !beams || B <= 0 || C <= 0 || A <= 0 || M <= 0 || bad_t(T))
+        return DCBF_ERR_INVALID_ARG;
+    if (!aligned16(reordered) || !aligned16(coeffs) || !aligned16(beams)) return DCBF_ERR_INVALID_ARG;
+    if (int e = check_device()) return e;
+    return launch_beamform(reordered, coeffs, beams, B, C, T, A, M, flags, static_cast<cudaStream_t>(stream));
+}
+
+int dcbf_fused(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T, int M,
+               int xeng_id, double sample_period, unsigned flags, dcbf_stream_t stream) {
+    if (!samples || !delay_vals || !beams || B <= 0 || A <= 0 || C <= 0 || N <= 0 || M <= 0 || xeng_id < 0 ||
+        bad_t(T) || !(sample_period > 0.0))
+        return DCBF_ERR_INVALID_ARG;
+    if (!aligned16(samples) || !aligned16(delay_vals) || !aligned16(beams)) return DCBF_ERR_INVALID_ARG;
+    if (int e = check_device()) return e;
+    return launch_fused(samples, delay_vals, beams, B, A, C, N, T, M, static_cast<long long>(C) * xeng_id, sample_period, flags,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int dcbf_fused_status(int* role, int* barrier, int* block) {
+    if (int e = check_device()) return e;
+    return fused_status(role, barrier, block);
+}
+
+void dcbf_fused_tiling(int A, int M, unsigned flags, int* kb_count, int* nt, int* nt_count) {
+    int a = 0, b = 0, c = 0;
+    if (A > 0 && M > 0) fused_tiling(A, M, flags, &a, &b, &c);
+    if (kb_count) *kb_count = a;
+    if (nt) *nt = b;
+    if (nt_count) *nt_count = c;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

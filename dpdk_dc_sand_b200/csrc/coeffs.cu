@@ -1,0 +1,100 @@
+// Stage 2 (stand-alone): steering-coefficient generation.
+//
+//   delay_vals [C][M][A][4] f32  ->  coeffs [B][P][C][2A][2M] f32
+//   block (ant a, beam m):  rows 2a,2a+1 / cols 2m,2m+1 = [[cos r, sin r], [-sin r, cos r]]
+//   r = delay*ch*(-pi)/(N*Ts) + phase - delay*(N/2)*(-pi)/(N*Ts),   ch = c + C*xeng_id
+//
+// Replaces kernel `run_coeff_gen` (reference: beamformer/beamforming/coeff_generator.py:12-103) and the
+// static (rate-free) case of the native precursor's calculate_beamweights_* kernels
+// (beamformer_coefficient_generator/BeamformerKernels.cu:7-189).  Indexing follows the reference's CPU
+// checker (beamformer/unit_test/coeff_generator_cpu.py:125-186): delay_vals is read at [c][beam][ant] and
+// written at rows 2*ant, cols 2*beam (the reference GPU kernel transposes ant/beam between its read and
+// its write; the tests never see it because they use uniform delays).
+//
+// Arithmetic: float64 with the reference's exact operation order (explicit _rn intrinsics, no FMA
+// contraction), float64 sincos, rounded once to float32 -- i.e. the same value the reference computes under
+// numba/numpy-1.x promotion rules, so the result is bit-identical to the float64 oracle except where
+// libm's and CUDA's double cos differ in the last ulp AND that ulp straddles a float32 rounding boundary.
+//
+// Memory: one CTA owns a [32 beams] x [32 ants] tile of one channel.  delay_vals is read with lanes along
+// `ant` (contiguous 16-byte structs -> fully coalesced), the (cos, sin) pairs are transposed through
+// shared memory, and the coefficient rows are written with lanes along `beam` (contiguous float2) for
+// every (batch, pol) replica.
+#include "common.cuh"
+
+namespace dcbf {
+
+namespace {
+
+constexpr int kTile = 32;
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads)
+coeffs_kernel(const float4* __restrict__ delay_vals, float* __restrict__ coeffs, int n_rep, int C, int A, int M,
+              int chan_offset, double half_n, double denom, int tiles_a, int tiles_m) {
+    __shared__ float2 cs[kTile][kTile + 1];  // [beam][ant] -> (cos, sin)
+
+    const long long blk = blockIdx.x;
+    const int ta = static_cast<int>(blk % tiles_a);
+    const int tm = static_cast<int>((blk / tiles_a) % tiles_m);
+    const int c = static_cast<int>(blk / (static_cast<long long>(tiles_a) * tiles_m));
+    const int a0 = ta * kTile, m0 = tm * kTile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const double ch = static_cast<double>(c + chan_offset);
+    const double neg_pi = -3.141592653589793;  // == -math.pi
+
+    // phase 1: lanes along ant
+    for (int mi = warp; mi < kTile; mi += kThreads / 32) {
+        const int m = m0 + mi, a = a0 + lane;
+        if (m < M && a < A) {
+            const float4 dv = __ldg(delay_vals + (static_cast<size_t>(c) * M + m) * A + a);
+            const double delay = static_cast<double>(dv.x);
+            const double phase = static_cast<double>(dv.z);
+            // ((delay*ch)*(-pi))/(N*Ts) + phase      coeff_generator_cpu.py:143-150
+            const double initial = __dadd_rn(__ddiv_rn(__dmul_rn(__dmul_rn(delay, ch), neg_pi), denom), phase);
+            // ((delay*(N/2))*(-pi))/(N*Ts)           coeff_generator_cpu.py:155-160
+            const double centre = __ddiv_rn(__dmul_rn(__dmul_rn(delay, half_n), neg_pi), denom);
+            const double rot = __dsub_rn(initial, centre);
+            double sn, cn;
+            sincos(rot, &sn, &cn);
+            cs[mi][lane] = make_float2(static_cast<float>(cn), static_cast<float>(sn));
+        }
+    }
+    __syncthreads();
+
+    // phase 2: lanes along beam; rows 2a (cos, sin) and 2a+1 (-sin, cos)
+    const int m = m0 + lane;
+    if (m >= M) return;
+    const size_t row_len = 2 * static_cast<size_t>(M);
+    for (int ai = warp; ai < kTile; ai += kThreads / 32) {
+        const int a = a0 + ai;
+        if (a >= A) break;
+        const float2 v = cs[lane][ai];
+        const float2 r0 = make_float2(v.x, v.y);
+        const float2 r1 = make_float2(-v.y, v.x);
+        for (int rep = 0; rep < n_rep; ++rep) {
+            float* base = coeffs + ((static_cast<size_t>(rep) * C + c) * (2 * static_cast<size_t>(A)) + 2 * a) * row_len;
+            reinterpret_cast<float2*>(base)[m] = r0;
+            reinterpret_cast<float2*>(base + row_len)[m] = r1;
+        }
+    }
+}
+
+}  // namespace
+
+int launch_coeffs(const float* delay_vals, float* coeffs, int B, int P, int C, int N, int A, int M, int xeng_id,
+                  double sample_period, cudaStream_t s) {
+    const int tiles_a = (A + kTile - 1) / kTile, tiles_m = (M + kTile - 1) / kTile;
+    const long long n_blocks = static_cast<long long>(C) * tiles_a * tiles_m;
+    if (n_blocks > 0x7fffffffLL) return DCBF_ERR_UNSUPPORTED;
+    const double denom = static_cast<double>(N) * sample_period;  // python: (n_channels * sample_period)
+    const double half_n = static_cast<double>(N) / 2.0;           // python: (n_channels / 2)
+    coeffs_kernel<<<static_cast<unsigned>(n_blocks), kThreads, 0, s>>>(
+        reinterpret_cast<const float4*>(delay_vals), coeffs, B * P, C, A, M, C * xeng_id, half_n, denom, tiles_a,
+        tiles_m);
+    DCBF_CHECK_LAUNCH("coeffs_kernel");
+    return DCBF_OK;
+}
+
+}  // namespace dcbf

@@ -1,0 +1,46 @@
+// Shared host/device helpers for libdcbf (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dcbf.h"
+
+namespace dcbf {
+
+constexpr int kPols = 2;            // reference: prebeamform_reorder.py:54 ("Hardcoded to 2")
+constexpr int kSamplesPerBlock = 16;  // reference: prebeamform_reorder.py:59
+
+// Records a CUDA error for dcbf_last_cuda_error() and maps it to DCBF_ERR_CUDA.
+int record_cuda_error(cudaError_t err, const char* what);
+void count_launch(unsigned n = 1);
+
+#define DCBF_CUDA_TRY(expr)                                              \
+    do {                                                                 \
+        cudaError_t _e = (expr);                                         \
+        if (_e != cudaSuccess) return ::dcbf::record_cuda_error(_e, #expr); \
+    } while (0)
+
+// Peek (not clear) launch errors right after a kernel launch.
+#define DCBF_CHECK_LAUNCH(name)                                         \
+    do {                                                                \
+        cudaError_t _e = cudaGetLastError();                            \
+        if (_e != cudaSuccess) return ::dcbf::record_cuda_error(_e, name); \
+        ::dcbf::count_launch();                                         \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Kernel launchers (one per translation unit).
+int launch_reorder(const uint8_t* samples, uint8_t* reordered, int B, int A, int C, int T, cudaStream_t s);
+int launch_coeffs(const float* delay_vals, float* coeffs, int B, int P, int C, int N, int A, int M, int xeng_id,
+                  double sample_period, cudaStream_t s);
+int launch_beamform(const uint8_t* reordered, const float* coeffs, float* beams, int B, int C, int T, int A, int M,
+                    unsigned flags, cudaStream_t s);
+// first_chan = absolute F-engine channel of local channel 0 (n_chans * xeng_id for a whole stream).
+int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T,
+                 int M, long long first_chan, double sample_period, unsigned flags, cudaStream_t s);
+int fused_status(int* role, int* barrier, int* block);
+void fused_tiling(int A, int M, unsigned flags, int* kb_count, int* nt, int* nt_count);
+
+}  // namespace dcbf

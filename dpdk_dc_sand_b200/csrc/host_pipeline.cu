@@ -1,0 +1,125 @@
+// Host-buffer entry point of the fused path: what a caller that owns HOST arrays (the reference's tests do:
+// `buf.set(queue, host)` ... `op()` ... `buf.get(queue, host)`, beamform_op_sequence_test.py:156-163) binds to.
+//
+// A plan owns `n_slots` device workspaces and streams.  The channel axis is cut into chunks; chunk i runs on
+// slot i % n_slots as  H2D(samples chunk, strided 2-D copy) -> H2D(delay_vals chunk) -> fused kernel ->
+// D2H(beams chunk, strided 2-D copy),  so the copy engines (one per direction) and the SMs overlap across
+// chunks.  Channels are independent, so chunking changes nothing in the result.
+#include <vector>
+
+#include "common.cuh"
+
+namespace dcbf {
+
+struct HostPlan {
+    int B, A, C, N, T, M, xeng_id;
+    double sample_period;
+    unsigned flags;
+    int chunk;  // channels per chunk
+    int device;
+    struct Slot {
+        cudaStream_t stream = nullptr;
+        uint8_t* samples = nullptr;
+        float* delay_vals = nullptr;
+        float* beams = nullptr;
+    };
+    std::vector<Slot> slots;
+};
+
+static int destroy_plan(HostPlan* p) {
+    if (!p) return DCBF_OK;
+    for (auto& s : p->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.samples);
+        cudaFree(s.delay_vals);
+        cudaFree(s.beams);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    delete p;
+    cudaGetLastError();
+    return DCBF_OK;
+}
+
+static int create_plan(HostPlan* p) {
+    const size_t in_b = static_cast<size_t>(p->B) * p->A * p->chunk * p->T * 4;
+    const size_t dv_b = static_cast<size_t>(p->chunk) * p->M * p->A * 16;
+    const size_t out_b = static_cast<size_t>(p->B) * kPols * p->chunk * p->T * p->M * 8;
+    for (auto& s : p->slots) {
+        DCBF_CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        DCBF_CUDA_TRY(cudaMalloc(&s.samples, in_b));
+        DCBF_CUDA_TRY(cudaMalloc(&s.delay_vals, dv_b));
+        DCBF_CUDA_TRY(cudaMalloc(&s.beams, out_b));
+    }
+    return DCBF_OK;
+}
+
+static int run_plan(HostPlan* p, const uint8_t* h_samples, const float* h_dv, float* h_beams) {
+    int dev = 0;
+    DCBF_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != p->device) return DCBF_ERR_INVALID_ARG;
+    const size_t samp_chan = static_cast<size_t>(p->T) * 4;          // bytes per (b, a, c)
+    const size_t beam_chan = static_cast<size_t>(p->T) * p->M * 8;   // bytes per (b, p, c)
+    int i = 0;
+    for (int c0 = 0; c0 < p->C; c0 += p->chunk, ++i) {
+        auto& s = p->slots[i % p->slots.size()];
+        const int cc = (p->C - c0 < p->chunk) ? p->C - c0 : p->chunk;
+        // samples[b][a][c0:c0+cc] : B*A rows of cc*T*4 bytes, pitch C*T*4 -> dense [B][A][cc][T][4]
+        DCBF_CUDA_TRY(cudaMemcpy2DAsync(s.samples, cc * samp_chan, h_samples + c0 * samp_chan, p->C * samp_chan,
+                                        cc * samp_chan, static_cast<size_t>(p->B) * p->A, cudaMemcpyHostToDevice,
+                                        s.stream));
+        DCBF_CUDA_TRY(cudaMemcpyAsync(s.delay_vals, h_dv + static_cast<size_t>(c0) * p->M * p->A * 4,
+                                      static_cast<size_t>(cc) * p->M * p->A * 16, cudaMemcpyHostToDevice, s.stream));
+        const long long first_chan = static_cast<long long>(p->C) * p->xeng_id + c0;
+        if (int e = launch_fused(s.samples, s.delay_vals, s.beams, p->B, p->A, cc, p->N, p->T, p->M, first_chan,
+                                 p->sample_period, p->flags, s.stream))
+            return e;
+        DCBF_CUDA_TRY(cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(h_beams) + c0 * beam_chan, p->C * beam_chan, s.beams,
+                                        cc * beam_chan, cc * beam_chan, static_cast<size_t>(p->B) * kPols,
+                                        cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto& s : p->slots) DCBF_CUDA_TRY(cudaStreamSynchronize(s.stream));
+    return DCBF_OK;
+}
+
+}  // namespace dcbf
+
+using namespace dcbf;
+
+extern "C" {
+
+__attribute__((visibility("default"))) int dcbf_host_plan_create(dcbf_host_plan_t* plan, int B, int A, int C, int N,
+                                                                 int T, int M, int xeng_id, double sample_period,
+                                                                 unsigned flags, int chunk_chans, int n_slots) {
+    if (!plan || B <= 0 || A <= 0 || C <= 0 || N <= 0 || M <= 0 || T <= 0 || (T % kSamplesPerBlock) || xeng_id < 0 ||
+        !(sample_period > 0.0))
+        return DCBF_ERR_INVALID_ARG;
+    if (chunk_chans <= 0 || chunk_chans > C) chunk_chans = C;
+    if (n_slots <= 0) n_slots = 3;
+    const int n_chunks = (C + chunk_chans - 1) / chunk_chans;
+    if (n_slots > n_chunks) n_slots = n_chunks;
+    auto* p = new HostPlan{B, A, C, N, T, M, xeng_id, sample_period, flags, chunk_chans, 0, {}};
+    if (cudaGetDevice(&p->device) != cudaSuccess) {
+        delete p;
+        cudaGetLastError();
+        return DCBF_ERR_NO_DEVICE;
+    }
+    p->slots.resize(n_slots);
+    if (int e = create_plan(p)) {
+        destroy_plan(p);
+        return e;
+    }
+    *plan = p;
+    return DCBF_OK;
+}
+
+__attribute__((visibility("default"))) int dcbf_host_plan_run(dcbf_host_plan_t plan, const uint8_t* samples,
+                                                              const float* delay_vals, float* beams) {
+    if (!plan || !samples || !delay_vals || !beams) return DCBF_ERR_INVALID_ARG;
+    return run_plan(static_cast<HostPlan*>(plan), samples, delay_vals, beams);
+}
+
+__attribute__((visibility("default"))) int dcbf_host_plan_destroy(dcbf_host_plan_t plan) {
+    return destroy_plan(static_cast<HostPlan*>(plan));
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+/*
+ * dcbf.h -- C ABI of libdcbf.so, the B200 (sm_100a) tied-array beamforming hot path.
+ *
+ * This is the drop-in boundary: plain C, device pointers + sizes, no torch / C++ types.
+ * Each entry point replaces one launch site of the reference (paths relative to the
+ * reference root, magnate3/dpdk_dc_sand):
+ *
+ *   dcbf_reorder   <- PreBeamformReorder._run          beamformer/beamforming/prebeamform_reorder.py:171-186
+ *                     (kernel prebeamform_reorder,     beamformer/beamforming/kernels/prebeamform_reorder_kernel.mako:37-92)
+ *   dcbf_coeffs    <- CoeffGenerator._run              beamformer/beamforming/coeff_generator.py:209-250
+ *                     (kernel run_coeff_gen,           beamformer/beamforming/coeff_generator.py:12-103;
+ *                      indexing follows the CPU oracle beamformer/unit_test/coeff_generator_cpu.py:120-186)
+ *   dcbf_beamform  <- ComplexMultKernel.complex_mult   beamformer/beamforming/complex_mult_kernel.py:106-162
+ *                     (kernel run_complex_mult,        beamformer/beamforming/complex_mult_kernel.py:11-100)
+ *   dcbf_fused     <- OpSequence.__call__              beamformer/beamforming/beamform_op_sequence.py:117-157
+ *                     (the three launches above fused; also supersedes the native precursor
+ *                      calculate_beamweights_and_beamform_single_channel,
+ *                      beamformer_coefficient_generator/BeamformerKernels.cu:192-367)
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers owned by the caller (16-byte aligned, as any
+ *     cudaMalloc / torch allocation is).  The library allocates nothing persistent.
+ *   - Work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream)
+ *     and is NOT synchronised (the reference calls cuda.synchronize() after every op;
+ *     callers that need that call cudaStreamSynchronize themselves).
+ *   - The device is the caller's current device (the reference hard-codes device 0).
+ *   - Return value: DCBF_OK (0) or a negative dcbf_status; dcbf_strerror() names it.
+ *   - Arrays are C-order with exactly the reference's shapes (no padding):
+ *       samples     uint8  [B][A][C][T][2 pols][2 re,im]
+ *       reordered   uint8  [B][2][C][T/16][16][A][2]
+ *       delay_vals  float  [C][M][A][4]  {delay_s, delay_rate, phase_rad, phase_rate}
+ *       coeffs      float  [B][P][C][2A][2M]   block (a,m) = [[cos, sin], [-sin, cos]]
+ *       beams       float  [B][2][C][T/16][16][2M]  (col 2m = Re, 2m+1 = Im of beam m)
+ *   - T must be a positive multiple of 16 (reference: prebeamform_reorder.py:59-65).
+ */
+#ifndef DCBF_H_
+#define DCBF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCBF_VERSION 1
+
+typedef void* dcbf_stream_t; /* cudaStream_t */
+
+typedef enum dcbf_status {
+    DCBF_OK = 0,
+    DCBF_ERR_INVALID_ARG = -1, /* null pointer, non-positive dimension, T % 16 != 0, misaligned pointer */
+    DCBF_ERR_UNSUPPORTED = -2, /* shape outside what the kernels were built for */
+    DCBF_ERR_CUDA = -3,        /* a CUDA runtime call failed; see dcbf_last_cuda_error() */
+    DCBF_ERR_NO_DEVICE = -4,   /* no sm_100 device is current */
+    DCBF_ERR_TIMEOUT = -5      /* in-kernel watchdog fired (pipeline dead-lock guard) */
+} dcbf_status;
+
+/* dcbf_fused / dcbf_beamform flags */
+#define DCBF_FLAG_SIGNED_INPUT 0x1u /* bytes are int8 (F-engine native); default: uint8 like the reference API */
+#define DCBF_FLAG_FP16_COEFF 0x2u   /* dcbf_fused: round the steering coefficients once to fp16 (error <= 2^-12 per
+                                       component) instead of the default fp16 hi+lo pair (~2^-24); halves tensor work */
+#define DCBF_FLAG_DEBUG_ROWWISE_EPILOGUE 0x100u /* dcbf_fused: row-per-thread TMEM read-out (cross-check only) */
+
+int dcbf_version(void);
+const char* dcbf_strerror(int status);
+/* Text of the last CUDA error seen by this library on the calling thread ("" if none). */
+const char* dcbf_last_cuda_error(void);
+
+/* Stage 1.  samples [B][A][C][T][2][2] u8 -> reordered [B][2][C][T/16][16][A][2] u8.  Bit-exact. */
+int dcbf_reorder(const uint8_t* samples, uint8_t* reordered, int n_batches, int n_ants, int n_chans,
+                 int n_samples, dcbf_stream_t stream);
+
+/* Stage 2.  delay_vals [C][M][A][4] f32 -> coeffs [B][P][C][2A][2M] f32.
+ * rot = delay*ch*(-pi)/(N*Ts) + phase - delay*(N/2)*(-pi)/(N*Ts), ch = c + C*xeng_id, evaluated in
+ * float64 with the reference's operation order, cos/sin in float64, stored as float32. */
+int dcbf_coeffs(const float* delay_vals, float* coeffs, int n_batches, int n_pols, int n_chans,
+                int n_chans_total, int n_ants, int n_beams, int xeng_id, double sample_period,
+                dcbf_stream_t stream);
+
+/* Stage 3.  out[b,p,c,t,n] = sum_j f32(reordered[b,p,c,t,j]) * coeffs[b,p,c,j,n], fp32 accumulate. */
+int dcbf_beamform(const uint8_t* reordered, const float* coeffs, float* beams, int n_batches, int n_chans,
+                  int n_samples, int n_ants, int n_beams, unsigned flags, dcbf_stream_t stream);
+
+/* Stages 1+2+3 in one pass: every voltage byte and every delay value is read from HBM once,
+ * neither `reordered` nor `coeffs` is materialised.  tcgen05 (fp16 operands, fp32 accumulate in TMEM).
+ * n_chans_total / xeng_id / sample_period as in dcbf_coeffs.  Does not synchronise. */
+int dcbf_fused(const uint8_t* samples, const float* delay_vals, float* beams, int n_batches, int n_ants,
+               int n_chans, int n_chans_total, int n_samples, int n_beams, int xeng_id, double sample_period,
+               unsigned flags, dcbf_stream_t stream);
+
+/* Blocks until prior work on the current device is done, then returns the status the last dcbf_fused kernels
+ * left behind: DCBF_OK, or DCBF_ERR_TIMEOUT if an in-kernel pipeline wait exceeded its 2 s guard (the kernel
+ * then exits early instead of hanging; *role / *barrier / *block say who waited on what).  Clears the status. */
+int dcbf_fused_status(int* role, int* barrier, int* block);
+
+/* The tiling dcbf_fused will use for (n_ants, n_beams, flags): k-blocks of 32 antennas, N tiles of *nt columns. */
+void dcbf_fused_tiling(int n_ants, int n_beams, unsigned flags, int* kb_count, int* nt, int* nt_count);
+
+/* ---- host-buffer entry point (what a caller holding HOST arrays binds to) --------------------------------
+ * Replaces the reference's set() / op() / get() round trip (beamformer/unit_test/beamform_op_sequence_test.py:156-163).
+ * A plan owns n_slots device workspaces + streams; dcbf_host_plan_run cuts the channel axis into chunks of
+ * chunk_chans channels and pipelines H2D -> dcbf_fused -> D2H across the slots, then blocks until `beams` is
+ * complete in host memory.  Host arrays have the full reference shapes; pin them (cudaHostRegister /
+ * torch pin_memory) for the copies to overlap.  chunk_chans <= 0: one chunk; n_slots <= 0: 3. */
+typedef void* dcbf_host_plan_t;
+int dcbf_host_plan_create(dcbf_host_plan_t* plan, int n_batches, int n_ants, int n_chans, int n_chans_total,
+                          int n_samples, int n_beams, int xeng_id, double sample_period, unsigned flags,
+                          int chunk_chans, int n_slots);
+int dcbf_host_plan_run(dcbf_host_plan_t plan, const uint8_t* samples, const float* delay_vals, float* beams);
+int dcbf_host_plan_destroy(dcbf_host_plan_t plan);
+
+/* Number of kernel launches this library has issued since load (all entry points); used by bench.py
+ * to report gpu_launches. */
+unsigned long long dcbf_launch_count(void);
+
+/* Algorithmic HBM bytes of one dcbf_fused call (in + delay_vals + out). */
+unsigned long long dcbf_fused_bytes(int n_batches, int n_ants, int n_chans, int n_samples, int n_beams);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCBF_H_ */
