@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the fused tied-array beamforming hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of reorder + steering coefficients + beamform (one `dcbf_fused` launch) over one heap
+batch of synthetic input resident in HBM.  Workload (default c3 = the configuration the BASELINE target is
+quoted on): MeerKAT 4k mode, 64 antennas x 2 pols x 4096 channels x 256 samples, 64 beams, per GPU.
+With N GPUs every rank processes its own 4096-channel stream (rank == xeng_id, n_channels = 4096*N):
+frequency-channel sharding, no data-path collective -> "scaling": "weak".
+
+One JSON line is printed by rank 0:
+  value          whole-job input GB/s (all ranks' voltage bytes / max-over-ranks device time), inputs in HBM
+  roofline       algorithmic bytes (in + delay_vals + out) per launch / mean launch time,
+                 against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  e2e            the same metric through the host-buffer C-ABI call (dcbf_host_plan_run): pinned host arrays,
+                 H2D + kernel + D2H inside the timed region
+  cpu_baseline   the oracle's vectorised numpy port of the same path on this box's host cores (bounded sample)
+`--impl reference` times that CPU port alone (the reference's own implementation is numba/python and cannot
+travel to the GPU box) and prints the same line shape with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (description, n_ants, n_chans per GPU, n_samples, n_beams, n_batches)
+    "c1": ("4 antennas x 2 pols x 64 channels x 256 samples, 4 beams (parity case)", 4, 64, 256, 4, 1),
+    "c2": ("MeerKAT 64 antennas x 2 pols x 1024 channels x 256 samples/heap, 16 beams", 64, 1024, 256, 16, 1),
+    "c3": ("MeerKAT 4k mode: 64 antennas x 2 pols x 4096 channels x 256 samples, 64 beams", 64, 4096, 256, 64, 1),
+}
+SAMPLE_PERIOD = 1 / 1712e6
+METRIC = "fused reorder+coeff+beamform input throughput"
+UNIT = "GB/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic(workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "fused_traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh).get(workload)
+    return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self) -> None:
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t_begin: float, t_end: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        rows = [r for r in self.rows if t_begin <= r[0] <= t_end + 0.1] or self.rows
+        for _, line in rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port) -- the only place bench.py touches oracle/
+# --------------------------------------------------------------------------------------------------------
+def cpu_port_rate(n_ants, n_beams, n_samples, n_chans_total, sample_chans, repeats, budget_s=25.0):
+    """Input GB/s of the oracle's numpy port on `sample_chans` channels of the workload."""
+    import numpy as np
+
+    from oracle import beamform_oracle as orc
+
+    x = orc.make_samples(1, n_ants, sample_chans, n_samples, seed=2021)
+    dv = orc.make_delay_vals_random(sample_chans, n_beams, n_ants, seed=2022)
+    orc.beamform_pipeline_fast(x[:, :, :4], dv[:4], n_chans_total, 0, SAMPLE_PERIOD)  # warm-up (BLAS init)
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        out = orc.beamform_pipeline_fast(x, dv, n_chans_total, 0, SAMPLE_PERIOD)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    del out
+    best = statistics.median(times)
+    try:
+        from threadpoolctl import threadpool_info
+
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    return x.nbytes / best / 1e9, int(np.int64(threads)), times
+
+
+def run_reference(args, wl) -> None:
+    desc, A, C, T, M, B = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = min(C, 256)
+    t0 = time.perf_counter()
+    # W warm-up + K timed steps, each step = one pass over the bounded sample
+    rate, threads, times = cpu_port_rate(A, M, T, C * args.gpus, sample, repeats=args.warmup + args.steps, budget_s=120.0)
+    timed = times[args.warmup:] or times
+    sec = statistics.mean(timed)
+    in_bytes = B * A * sample * T * 4
+    value = in_bytes / sec / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(timed), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "sample": f"{sample} of {C} channels per step",
+                   "n_ants": A, "n_beams": M, "n_samples": T},
+        "beam_gsamples_per_s": B * 2 * sample * T * M / sec / 1e9,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} of {C} channels ({in_bytes} input bytes) per step, numpy float32 "
+                                   f"transpose + float64 phase + BLAS matmul; host has {os.cpu_count()} logical cores"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------
+def run_ours(args, wl) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from dpdk_dc_sand_b200 import _capi
+
+    desc, A, C, T, M, B = wl
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_total = C * world
+    flags = _capi.FLAG_FP16_COEFF if args.fp16_coeff else 0
+
+    # synthetic inputs, generated on the device (seeded per rank); each rank owns channels [rank*C, (rank+1)*C)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2021 + rank)
+    samples = torch.randint(0, 256, (B, A, C, T, 2, 2), dtype=torch.uint8, device=dev, generator=gen)
+    dv = torch.zeros((C, M, A, 4), dtype=torch.float32, device=dev)
+    dv[..., 0] = (torch.rand((C, M, A), device=dev, generator=gen) * 32 - 16) * SAMPLE_PERIOD
+    dv[..., 2] = (torch.rand((C, M, A), device=dev, generator=gen) * 2 - 1) * 3.14159265
+    beams = torch.empty((B, 2, C, T // 16, 16, 2 * M), dtype=torch.float32, device=dev)
+    stream = torch.cuda.Stream()
+    alg_bytes = _capi.fused_bytes(B, A, C, T, M)
+    in_bytes = samples.numel()
+
+    def step():
+        _capi.fused(samples, dv, beams, B, A, C, n_total, T, M, rank, SAMPLE_PERIOD, flags, stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    _capi.fused_status()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.12)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches0 = _capi.launch_count()
+    barrier()
+    t_begin = time.time()
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for i in range(args.steps):
+            step()
+            ev[i + 1].record(stream)
+    stream.synchronize()
+    barrier()
+    t_end = time.time()
+    launches = _capi.launch_count() - launches0
+    clocks = sampler.stop(t_begin, t_end)
+    _capi.fused_status()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms_max = float(t.item())
+    else:
+        total_ms_max = total_ms
+    sec_per_step = total_ms_max / 1e3 / args.steps
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host arrays, H2D + kernel + D2H timed) ----
+    e2e = None
+    if not args.no_e2e:
+        h_in = torch.empty(samples.shape, dtype=torch.uint8, pin_memory=True)
+        h_dv = torch.empty(dv.shape, dtype=torch.float32, pin_memory=True)
+        h_out = torch.empty(beams.shape, dtype=torch.float32, pin_memory=True)
+        h_in.copy_(samples)
+        h_dv.copy_(dv)
+        torch.cuda.synchronize()
+        plan = _capi.HostPlan(B, A, C, n_total, T, M, rank, SAMPLE_PERIOD, flags, chunk_chans=max(1, C // 16), n_slots=3)
+        n_in, n_dv, n_out = h_in.numpy(), h_dv.numpy(), h_out.numpy()
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            plan.run(n_in, n_dv, n_out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            plan.run(n_in, n_dv, n_out)  # blocks until the beams are in host memory
+        torch.cuda.synchronize()
+        e2e_sec = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_sec], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_sec = float(t.item())
+        plan.close()
+        # the host-path result must be the device-path result (same kernel, chunked): cheap identity check
+        same = bool(torch.equal(h_out[:, :, : min(C, 8)], beams[:, :, : min(C, 8)].cpu()))
+        e2e = {"value": world * in_bytes / e2e_sec / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(in_bytes + dv.numel() * 4), "d2h_bytes_per_step": int(beams.numel() * 4),
+               "ms_per_step": e2e_sec * 1e3, "steps": e2e_steps, "api": "dcbf_host_plan_run (pinned host arrays)",
+               "matches_device_path": same}
+        del h_in, h_dv, h_out
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = _peaks()
+    mean_launch_s = statistics.mean(per_launch_ms) / 1e3
+    achieved = alg_bytes / mean_launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": _traffic(args.workload), "kernel": "fused_beamform_kernel",
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_us_mean": mean_launch_s * 1e6,
+                "launch_us_min": min(per_launch_ms) * 1e3, "peak_source": peak_src,
+                "tensor_tflops_real_expanded": B * 2 * C * T * 8 * A * M / mean_launch_s / 1e12}
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        sample = min(C, 256)
+        rate, threads, times = cpu_port_rate(A, M, T, n_total, sample, repeats=5, budget_s=20.0)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{sample} of {C} channels x {len(times)} repeats (median), oracle numpy port "
+                         f"(transpose + float64 phase + float32 BLAS matmul); host has {os.cpu_count()} logical cores"}
+    line = {
+        "metric": METRIC, "value": world * in_bytes / sec_per_step / 1e9, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": sec_per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands (u8 exact, coefficients fp16 " + ("single" if args.fp16_coeff else "hi+lo") + "), f32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc} per GPU", "n_ants": A, "n_chans_per_gpu": C,
+                   "n_chans_total": n_total, "n_samples": T, "n_beams": M, "n_batches": B,
+                   "parallelism": f"channel-sharded x{world} (rank == xeng_id), no collective",
+                   "l2": f"working set {alg_bytes / 2**20:.0f} MiB per step > 126 MB L2 (inputs larger than L2)",
+                   "tiling": dict(zip(("kb_count", "nt", "nt_count"), _capi.fused_tiling(A, M, flags)))},
+        "beam_gsamples_per_s": world * B * 2 * C * T * M / sec_per_step / 1e9,
+        "algorithmic_GBps": world * alg_bytes / sec_per_step / 1e9,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c3")
+    ap.add_argument("--fp16-coeff", action="store_true", help="single fp16 coefficient rounding (DCBF_FLAG_FP16_COEFF)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

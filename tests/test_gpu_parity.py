@@ -1,0 +1,342 @@
+"""Parity of the CUDA path (through the operator API -> ctypes -> libdcbf C ABI) against the oracle.
+
+Mirrors the reference's four GPU tests (beamformer/unit_test/*_test.py): same calling protocol, same
+synthetic inputs (rng seed 2021; uniform delay 5*Ts / phase pi/2), plus the cases those tests miss
+(non-uniform delays, M > 2, xeng_id > 0, signed input, ragged antenna counts, partial time tiles).
+Tolerances: reorder bit-exact; coefficients <= 1e-6 of a float64 evaluation (and exact float32 equality on the
+reference's own uniform inputs); beams max|err| <= 2^-10 * sum_a |x_a| per output sample, and the
+reference's rtol=atol=1e-4 on its own test inputs.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import beamform_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TS = orc.SAMPLE_PERIOD
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    import dpdk_dc_sand_b200
+
+    dpdk_dc_sand_b200.install_dropin()
+    from katsdpsigproc import accel
+
+    ctx = accel.create_some_context(device_filter=lambda d: d.is_cuda, interactive=False)
+    return ctx, ctx.create_command_queue()
+
+
+def _budget(x, signed=False):
+    return 2.0 ** -10 * orc.beamform_abs_bound(orc.reorder(x), signed_input=signed)[..., None]
+
+
+# reference grid: n_ants (test_parameters.py:19) with C = N // A // 4 (prebeamform_reorder_test.py:72), B = 3
+REF_ANTS = [4, 8, 16, 32, 64, 79, 80, 84, 130, 192, 256, 5, 23, 61, 19]
+
+
+@pytest.mark.parametrize("n_ants", REF_ANTS)
+def test_prebeamform_reorder(dropin, n_ants):
+    from beamforming.prebeamform_reorder import PreBeamformReorderTemplate
+
+    ctx, queue = dropin
+    n_batches, n_channels, n_samples = 3, 1024, 256
+    c = max(1, n_channels // n_ants // 4)
+    op = PreBeamformReorderTemplate(ctx, n_ants, c, n_samples, n_batches).instantiate(queue)
+    op.ensure_all_bound()
+    buf_in, buf_out = op.buffer("inSamples"), op.buffer("outReordered")
+    host_in = buf_in.empty_like()
+    rng = np.random.default_rng(seed=2021)
+    host_in[:] = rng.uniform(0, 255, host_in.shape).astype(np.uint8)  # prebeamform_reorder_test.py:100-106
+    buf_in.set(queue, host_in)
+    op()
+    got = buf_out.get(queue)
+    np.testing.assert_array_equal(got, orc.reorder(np.asarray(host_in)))
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 2, 16), (2, 7, 5, 48), (1, 64, 3, 512), (1, 300, 1, 32)])
+def test_prebeamform_reorder_ragged(dropin, shape):
+    from dpdk_dc_sand_b200 import _capi
+    import torch
+
+    b, a, c, t = shape
+    x = orc.make_samples(b, a, c, t, seed=5)
+    dx = torch.from_numpy(x).cuda()
+    out = torch.zeros((b, 2, c, t // 16, 16, a, 2), dtype=torch.uint8, device="cuda")
+    _capi.reorder(dx, out, b, a, c, t)
+    np.testing.assert_array_equal(out.cpu().numpy(), orc.reorder(x))
+
+
+@pytest.mark.parametrize("n_ants,n_channels", [(4, 1024), (64, 4096), (79, 32768), (23, 1024)])
+def test_coeff_generator_reference_inputs_exact(dropin, n_ants, n_channels):
+    """beamform_coeff_test.py: uniform delay 5*Ts, phase pi/2 -> exact float32 equality with the CPU values."""
+    from beamforming.coeff_generator import CoeffGeneratorTemplate
+
+    ctx, queue = dropin
+    b, p, m, xid = 3, 2, 2, 0
+    c = max(1, n_channels // n_ants // 4)
+    op = CoeffGeneratorTemplate(ctx, b, p, c, n_channels, 16, 16, n_ants, m, xid, TS).instantiate(queue)
+    op.ensure_all_bound()
+    dv = orc.make_delay_vals_uniform(c, m, n_ants)
+    op.buffer("delay_vals").set(queue, dv)
+    op()
+    got = op.buffer("outCoeffs").get(queue)
+    np.testing.assert_array_equal(got, orc.steering_coeffs(dv, b, p, c, n_channels, n_ants, m, xid, TS))
+
+
+@pytest.mark.parametrize("n_ants,n_beams,xid", [(5, 3, 1), (64, 16, 0), (80, 32, 7), (197, 9, 2)])
+def test_coeff_generator_random(dropin, n_ants, n_beams, xid):
+    from beamforming.coeff_generator import CoeffGeneratorTemplate
+
+    ctx, queue = dropin
+    b, p, c, n = 1, 2, 6, 4096
+    op = CoeffGeneratorTemplate(ctx, b, p, c, n, 16, 16, n_ants, n_beams, xid, TS).instantiate(queue)
+    op.ensure_all_bound()
+    dv = orc.make_delay_vals_random(c, n_beams, n_ants, seed=11)
+    op.buffer("delay_vals").set(queue, dv)
+    op()
+    got = op.buffer("outCoeffs").get(queue).astype(np.float64)
+    ref = orc.steering_coeffs(dv, b, p, c, n, n_ants, n_beams, xid, TS, out_dtype=np.float64)
+    assert np.abs(got - ref).max() <= 1e-6  # unit-magnitude phasors: absolute == relative to |coeff|
+    # block structure
+    np.testing.assert_array_equal(got[..., 1::2, 0::2], -got[..., 0::2, 1::2])
+    np.testing.assert_array_equal(got[..., 1::2, 1::2], got[..., 0::2, 0::2])
+
+
+@pytest.mark.parametrize("n_ants,n_beams,signed", [(4, 2, False), (64, 16, False), (23, 5, True), (130, 2, False)])
+def test_matrix_multiply(dropin, n_ants, n_beams, signed):
+    from beamforming.matrix_multiply import MatrixMultiplyTemplate
+
+    ctx, queue = dropin
+    b, c, t = 2, 3, 64
+    op = MatrixMultiplyTemplate(ctx, n_ants, c, t, n_beams, b).instantiate(queue)
+    op.signed_input = signed
+    op.ensure_all_bound()
+    x = orc.make_samples(b, n_ants, c, t, seed=3)
+    re = orc.reorder(x)
+    co = np.random.default_rng(4).standard_normal((b, 2, c, 2 * n_ants, 2 * n_beams)).astype(np.float32)
+    op.buffer("inData").set(queue, re)
+    op.buffer("inCoeffs").set(queue, co)
+    op()
+    got = op.buffer("outData").get(queue)
+    ref = orc.beamform(re, co, signed_input=signed)
+    scale = np.abs(orc.beamform(re, np.abs(co), signed_input=False))  # sum |x||w|
+    assert np.all(np.abs(got - ref) <= 1e-5 * scale + 1e-6)
+
+
+@pytest.mark.parametrize("n_ants", [4, 64, 79, 19])
+def test_beamform_coeff_plus_mult_reference_inputs(dropin, n_ants):
+    """beamform_mult_kernel_test.py: coefficient op + multiply op, uniform delays, rtol=atol=1e-4."""
+    from beamforming.coeff_generator import CoeffGeneratorTemplate
+    from beamforming.matrix_multiply import MatrixMultiplyTemplate
+
+    ctx, queue = dropin
+    b, t, m, n, xid = 3, 256, 2, 1024, 0
+    c = max(1, n // n_ants // 4)
+    cg = CoeffGeneratorTemplate(ctx, b, 2, c, n, t // 16, 16, n_ants, m, xid, TS).instantiate(queue)
+    mm = MatrixMultiplyTemplate(ctx, n_ants, c, t, m, b).instantiate(queue)
+    cg.ensure_all_bound()
+    mm.bind(inCoeffs=cg.buffer("outCoeffs"))
+    mm.ensure_all_bound()
+    rng = np.random.default_rng(seed=2021)
+    re = rng.uniform(0, 255, mm.buffer("inData").shape).astype(np.uint8)
+    dv = orc.make_delay_vals_uniform(c, m, n_ants)
+    cg.buffer("delay_vals").set(queue, dv)
+    mm.buffer("inData").set(queue, re)
+    cg()
+    mm()
+    got = mm.buffer("outData").get(queue)
+    co = orc.steering_coeffs(dv, b, 2, c, n, n_ants, m, xid, TS)
+    ref64 = orc.beamform(re, co)
+    ulp = 2.0 ** -23 * orc.beamform_abs_bound(re)[..., None]  # one float32 ulp of the accumulated magnitude
+    tol = 1e-4 + 1e-4 * np.abs(ref64) + ulp  # reference tolerance (beamform_mult_kernel_test.py:267) + accumulate ulp
+    assert np.all(np.abs(got - ref64) <= tol)
+    assert np.all(np.abs(got - orc.complex_mult_beam0(re, co)) <= tol + ulp * np.sqrt(2 * n_ants))
+
+
+@pytest.mark.parametrize("n_ants", REF_ANTS)
+def test_op_sequence_reference_inputs(dropin, n_ants):
+    """beamform_op_sequence_test.py protocol, inputs and tolerance (rtol=atol=1e-4), fused kernel."""
+    from beamforming.beamform_op_sequence import OpSequenceTemplate
+
+    ctx, queue = dropin
+    b, t, m, n, xid = 3, 256, 2, 1024, 0
+    c = max(1, n // n_ants // 4)
+    op = OpSequenceTemplate(ctx, b, 2, c, n, t // 16, 16, n_ants, m, xid, TS, t).instantiate(queue)
+    op.ensure_all_bound()
+    buf_in, buf_dv, buf_out = op.buffer("bufin_reorder"), op.buffer("bufin_delay_vals"), op.buffer("bufout_mult")
+    host_in = buf_in.empty_like()
+    rng = np.random.default_rng(seed=2021)
+    host_in[:] = rng.uniform(0, 255, host_in.shape).astype(np.uint8)
+    host_dv = buf_dv.empty_like()
+    host_dv[:] = orc.make_delay_vals_uniform(c, m, n_ants, samples_delay=5, phase=math.pi / 2)
+    buf_in.set(queue, host_in)
+    buf_dv.set(queue, host_dv)
+    op()
+    host_out = buf_out.empty_like()
+    buf_out.get(queue, host_out)
+    from dpdk_dc_sand_b200 import _capi
+
+    _capi.fused_status()
+    x, dv = np.asarray(host_in), np.asarray(host_dv)
+    co = orc.steering_coeffs(dv, b, 2, c, n, n_ants, m, xid, TS)
+    re = orc.reorder(x)
+    # The reference asserts rtol=atol=1e-4 between two float32 evaluations that share their summation order
+    # (beamform_op_sequence_test.py:198).  Against the float64 value of the same sum that tolerance needs one
+    # float32 ulp of the accumulated magnitude added (sum_a |x_a| ~ 1e3..3e4 here): 2^-23 * sum|x|.
+    ref64 = orc.beamform(re, co)
+    tol = 1e-4 + 1e-4 * np.abs(ref64) + 2.0 ** -23 * _budget(x) * 2.0 ** 10
+    assert np.all(np.abs(host_out - ref64) <= tol)
+    chk = orc.complex_mult_beam0(re, co)  # the reference's own float32 checker (beam-uniform coefficients here)
+    assert np.all(np.abs(host_out - chk) <= tol + 2.0 ** -23 * _budget(x) * 2.0 ** 10 * np.sqrt(2 * n_ants))
+    assert np.all(np.abs(host_out - orc.beamform_pipeline(x, dv, n, xid, TS)) <= _budget(x))
+
+
+FUSED_CASES = [
+    # B, A, C, T, M, N, xeng_id, signed, fp16_coeff
+    (1, 4, 64, 256, 4, 64, 0, False, False),      # BASELINE configs[0]
+    (1, 64, 24, 256, 16, 1024, 0, False, False),  # configs[1] geometry, a slice of channels
+    (1, 64, 10, 256, 64, 4096, 5, False, False),  # configs[2] geometry, xeng 5 of 8... (C=10 slice)
+    (1, 80, 6, 256, 32, 32768, 3, False, False),  # configs[3] geometry
+    (1, 197, 3, 256, 256, 4096, 1, False, False),  # configs[4] geometry (16 N tiles, 7 k-blocks)
+    (2, 5, 3, 32, 3, 256, 1, False, False),       # odd everything, partial time tile
+    (3, 23, 7, 48, 2, 1024, 0, True, False),      # signed input
+    (1, 64, 10, 256, 64, 4096, 0, False, True),   # single-fp16 coefficients (fast mode)
+    (1, 33, 200, 144, 9, 4096, 2, False, False),  # more channels than SMs, T = 128 + 16
+    (1, 256, 2, 256, 2, 1024, 0, False, False),   # 8 k-blocks
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=lambda c: "B{}A{}C{}T{}M{}N{}x{}s{:d}h{:d}".format(*c))
+def test_fused_random_delays(dropin, case):
+    from beamforming.beamform_op_sequence import OpSequenceTemplate
+    from dpdk_dc_sand_b200 import _capi
+
+    ctx, queue = dropin
+    b, a, c, t, m, n, xid, signed, fp16 = case
+    op = OpSequenceTemplate(ctx, b, 2, c, n, t // 16, 16, a, m, xid, TS, t).instantiate(queue)
+    op.signed_input, op.fp16_coeff = signed, fp16
+    op.ensure_all_bound()
+    assert not op.slots["bufint_coeff"].is_bound and not op.slots["bufint_data"].is_bound
+    x = orc.make_samples(b, a, c, t, seed=100 + a)
+    dv = orc.make_delay_vals_random(c, m, a, seed=200 + m)
+    op.buffer("bufin_reorder").set(queue, x)
+    op.buffer("bufin_delay_vals").set(queue, dv)
+    op.buffer("bufout_mult").zero(queue)
+    n0 = _capi.launch_count()
+    op()
+    got = op.buffer("bufout_mult").get(queue).astype(np.float64)
+    _capi.fused_status()
+    assert _capi.launch_count() - n0 == 1
+    ref = orc.beamform_pipeline(x, dv, n, xid, TS, signed_input=signed)
+    err = np.abs(got - ref)
+    assert not np.isnan(got).any()
+    assert np.all(err <= _budget(x, signed)), f"max err {err.max()} vs budget"
+    if not fp16:  # hi+lo coefficients: float32-grade result
+        assert np.all(err <= 2.0 ** -18 * _budget(x, signed) * 2 ** 10 + 1e-3)
+
+
+def test_fused_matches_three_kernel_chain_and_materialises_intermediates(dropin):
+    from beamforming.beamform_op_sequence import OpSequenceTemplate
+
+    ctx, queue = dropin
+    b, a, c, t, m, n, xid = 2, 19, 12, 256, 6, 1024, 1
+    x = orc.make_samples(b, a, c, t, seed=9)
+    dv = orc.make_delay_vals_random(c, m, a, seed=10)
+    outs = {}
+    for fused in (True, False):
+        op = OpSequenceTemplate(ctx, b, 2, c, n, t // 16, 16, a, m, xid, TS, t).instantiate(queue)
+        op.fused = fused
+        op.materialize_intermediates = True
+        op.ensure_all_bound()
+        op.buffer("bufin_reorder").set(queue, x)
+        op.buffer("bufin_delay_vals").set(queue, dv)
+        op()
+        outs[fused] = op.buffer("bufout_mult").get(queue)
+        np.testing.assert_array_equal(op.buffer("bufint_data").get(queue), orc.reorder(x))
+        co = op.buffer("bufint_coeff").get(queue).astype(np.float64)
+        ref_co = orc.steering_coeffs(dv, b, 2, c, n, a, m, xid, TS, out_dtype=np.float64)
+        assert np.abs(co - ref_co).max() <= 1e-6
+    np.testing.assert_allclose(outs[True], outs[False], rtol=0, atol=float(_budget(x).max()) * 2.0 ** -6)
+
+
+def test_fused_linearity_and_channel_independence_full_size(dropin):
+    """Size-independent properties at BASELINE configs[1] size (64 ants x 1024 chans x 256 x 16 beams).
+
+    (1) channel independence: the fused result of a channel-sharded call (xeng_id = 1, second half) equals the
+        corresponding half of the full call bit for bit;  (2) linearity in the voltages: beamform(x) for
+        x = hi*16 + lo equals 16*beamform(hi) + beamform(lo) to float32 rounding;  (3) a sampled slice agrees
+        with the oracle.
+    """
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m = 1, 64, 1024, 256, 16
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randint(0, 256, (b, a, c, t, 2, 2), dtype=torch.uint8, device="cuda", generator=g)
+    dv = torch.from_numpy(orc.make_delay_vals_random(c, m, a, seed=3)).cuda()
+    full = torch.empty((b, 2, c, t // 16, 16, 2 * m), dtype=torch.float32, device="cuda")
+    _capi.fused(x, dv, full, b, a, c, c, t, m, 0, TS)
+    half = torch.empty((b, 2, c // 2, t // 16, 16, 2 * m), dtype=torch.float32, device="cuda")
+    _capi.fused(x[:, :, c // 2:].contiguous(), dv[c // 2:].contiguous(), half, b, a, c // 2, c, t, m, 1, TS)
+    _capi.fused_status()
+    assert torch.equal(full[:, :, c // 2:], half)
+    hi, lo = x >> 4, x & 15
+    o_hi, o_lo = torch.empty_like(full), torch.empty_like(full)
+    _capi.fused(hi, dv, o_hi, b, a, c, c, t, m, 0, TS)
+    _capi.fused(lo, dv, o_lo, b, a, c, c, t, m, 0, TS)
+    _capi.fused_status()
+    assert (16 * o_hi + o_lo - full).abs().max().item() <= 0.05
+    sl = slice(500, 504)
+    xs, dvs = x[:, :, sl].cpu().numpy(), dv[sl].cpu().numpy()
+    # channels 500..503 of a 1024-channel stream: emulate by xeng geometry C=4, xeng_id=125
+    ref = orc.beamform_pipeline(xs, np.ascontiguousarray(dvs), c, 125, TS)
+    assert np.all(np.abs(full[:, :, sl].cpu().numpy() - ref) <= _budget(xs))
+
+
+def test_host_plan_matches_device_path(dropin):
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m, n, xid = 2, 20, 37, 64, 5, 256, 3
+    x = orc.make_samples(b, a, c, t, seed=21)
+    dv = orc.make_delay_vals_random(c, m, a, seed=22)
+    out = np.zeros((b, 2, c, t // 16, 16, 2 * m), np.float32)
+    plan = _capi.HostPlan(b, a, c, n, t, m, xid, TS, chunk_chans=8, n_slots=3)
+    plan.run(x, dv, out)
+    plan.close()
+    dev_out = torch.empty(out.shape, dtype=torch.float32, device="cuda")
+    _capi.fused(torch.from_numpy(x).cuda(), torch.from_numpy(dv).cuda(), dev_out, b, a, c, n, t, m, xid, TS)
+    _capi.fused_status()
+    np.testing.assert_array_equal(out, dev_out.cpu().numpy())
+    assert np.all(np.abs(out - orc.beamform_pipeline(x, dv, n, xid, TS)) <= _budget(x))
+
+
+def test_c_abi_error_codes(dropin):
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    x = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError):
+        _capi.reorder(x, x, 1, 1, 1, 24)  # T % 16 != 0
+    with pytest.raises(ValueError):
+        _capi.fused(x, x, x, 1, 0, 1, 1, 16, 1, 0, TS)  # n_ants = 0
+    lib = _capi.load()
+    assert lib.dcbf_reorder(None, None, 1, 1, 1, 16, None) == _capi.ERR_INVALID_ARG
+    assert b"invalid" in lib.dcbf_strerror(_capi.ERR_INVALID_ARG)
+
+
+def test_native_library_is_loaded():
+    """The round-end harness records which in-tree .so files the test process loaded."""
+    from dpdk_dc_sand_b200 import _capi
+
+    _capi.load()
+    with open("/proc/self/maps") as fh:
+        assert any("libdcbf.so" in line for line in fh)
+    assert os.path.basename(_capi.lib_path()) == "libdcbf.so"
