@@ -111,6 +111,8 @@ int dcbf_fused_status(int* role, int* barrier, int* block) {
     return fused_status(role, barrier, block);
 }
 
+void dcbf_debug_set_profile_buffer(unsigned long long* dev_ptr) { fused_set_profile_buffer(dev_ptr); }
+
 void dcbf_fused_tiling(int A, int M, unsigned flags, int* kb_count, int* nt, int* nt_count) {
     int a = 0, b = 0, c = 0;
     if (A > 0 && M > 0) fused_tiling(A, M, flags, &a, &b, &c);

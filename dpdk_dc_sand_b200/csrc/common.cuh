@@ -41,6 +41,7 @@ int launch_beamform(const uint8_t* reordered, const float* coeffs, float* beams,
 int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T,
                  int M, long long first_chan, double sample_period, unsigned flags, cudaStream_t s);
 int fused_status(int* role, int* barrier, int* block);
+void fused_set_profile_buffer(unsigned long long* dev_ptr);
 void fused_tiling(int A, int M, unsigned flags, int* kb_count, int* nt, int* nt_count);
 
 }  // namespace dcbf

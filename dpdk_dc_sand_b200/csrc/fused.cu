@@ -15,12 +15,12 @@
 //   W[2a+x][2m+y] = {{cos, sin}, {-sin, cos}}[x][y] of rot(c, m, a), carried as fp16 hi + fp16 lo
 //                  (two accumulating MMAs; coefficient error ~2^-24) or fp16 hi only (DCBF_FLAG_FP16_COEFF).
 //
-// One persistent CTA per SM walks channels c = blockIdx.x, +gridDim.x, ...  Warp roles (512 threads):
+// One persistent CTA per SM walks channels c = blockIdx.x, +gridDim.x, ...  Warp roles (640 threads):
 //   warp 0        producer  : 1-D TMA bulk copies  in[b][a][c][t0:t0+128] (512 B runs) -> raw ring, mbarrier tx
 //   warp 1        MMA       : one lane issues tcgen05.mma (M=128, N<=128, K=16), accumulators in TMEM
 //   warps 4-7     epilogue  : tcgen05.ld 16x256b -> full-sector st.global.v2 straight from registers
 //   warps 8-11    convert   : raw bytes -> fp16, pol de-interleave, a<->t transpose into the 128B-swizzled A tiles
-//   warps 12-15   coeffs    : delay_vals (coalesced float4) -> f64 phase -> sincospif -> swizzled B tiles
+//   warps 12-19   coeffs    : delay_vals (coalesced float4) -> f64 phase -> sincospif -> swizzled B tiles
 // Pipelines (mbarrier full/empty pairs): raw ring (TMA->convert), A ring (convert->MMA), B double buffer
 // (coeffs->MMA, one channel ahead), TMEM accumulator double buffer (MMA->epilogue).
 //
@@ -35,7 +35,8 @@ namespace dcbf {
 
 namespace {
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 640;
+constexpr int kCoeffWarp0 = 12, kCoeffWarps = 8;  // warps 12..19
 constexpr int kTileT = 128;    // samples per MMA tile (UMMA M)
 constexpr int kKbAnts = 32;    // antennas per k-block
 constexpr int kRawStages = 2;
@@ -50,7 +51,7 @@ constexpr int kTmemCols = 512;
 constexpr unsigned long long kWatchdogNs = 2000000000ull;  // 2 s without progress on one barrier = dead-lock
 
 constexpr int kSmemData = kAopStages * kAopStageBytes + kBopBufs * kBopBufBytes + kRawStages * kRawStageBytes;
-constexpr int kSmemBytes = 1024 /*alignment slack*/ + kSmemData + 256 /*barriers + control*/;
+constexpr int kSmemBytes = 1024 /*alignment slack*/ + kSmemData + 512 /*barriers + control*/;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 enum Role { kRoleProducer = 1, kRoleMma = 2, kRoleEpilogue = 3, kRoleConvert = 4, kRoleCoeff = 5 };
@@ -60,6 +61,7 @@ struct FusedParams {
     const float4* dv;
     float* out;
     int* status;  // [0]=error code, [1]=role, [2]=barrier id, [3]=blockIdx
+    unsigned long long* prof;  // optional [grid][6 roles][4]: ns blocked per barrier class, [..][3] = role span
     int B, A, C, T, M;
     int kb_count;   // ceil(A / 32)
     int nt;         // columns per N tile (multiple of 16, <= 128)
@@ -211,6 +213,7 @@ __device__ __forceinline__ uint32_t make_idesc_f16(int n) {
 struct Control {
     uint32_t tmem_base;
     volatile int abort;
+    unsigned long long wait_ns[6][4];  // [role][slot]: time lane 0 of a role's first warp spent blocked
 };
 
 __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Control* ctl, int* status, int role, int id) {
@@ -233,9 +236,15 @@ __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Contr
     return true;
 }
 // Warp-collective: every lane waits; the result is made warp-uniform.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, Control* ctl, int* status, int role, int id) {
+// `slot` >= 0 on exactly one lane of a role makes that lane account its blocked time (profiling aid; the
+// first try_wait may itself suspend the thread, so the whole call is timed).
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, Control* ctl, int* status, int role, int id,
+                                          int slot = -1) {
+    unsigned long long t0 = 0;
+    if (slot >= 0) t0 = global_ns();
     bool ok = mbar_try_wait(bar, parity) != 0;
     if (!ok) ok = mbar_wait_slow(bar, parity, ctl, status, role, id);
+    if (slot >= 0) ctl->wait_ns[role][slot] += global_ns() - t0;
     return __all_sync(0xffffffffu, ok);
 }
 
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
             mbar_init(bar(kAopEmpty + s), 1);
         }
         for (int s = 0; s < kBopBufs; ++s) {
-            mbar_init(bar(kBopFull + s), 4);
+            mbar_init(bar(kBopFull + s), kCoeffWarps);
             mbar_init(bar(kBopEmpty + s), 1);
         }
         for (int s = 0; s < kAccBufs; ++s) {
@@ -294,6 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
             mbar_init(bar(kAccEmpty + s), 4);
         }
         ctl->abort = 0;
+        for (int i = 0; i < 24; ++i) ctl->wait_ns[i >> 2][i & 3] = 0;
         fence_mbar_init();
         (void)kNumBars;
     }
@@ -313,6 +323,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
     const int N2 = 2 * M;
     const int nt = prm.nt, parts = prm.parts;
     const uint32_t bop_kb_bytes = static_cast<uint32_t>(parts * nt * 128);  // one k-block: [part][nt rows][128 B]
+    // profiling: lane 0 of each role's first warp accounts blocked time per barrier class (slot) and role span
+    const bool prof_lane = lane == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 8 || warp == kCoeffWarp0);
+    const int ps = prof_lane ? 0 : -100;
+    const int my_role = warp == 0 ? kRoleProducer : warp == 1 ? kRoleMma : warp < 8 ? kRoleEpilogue : warp < 12 ? kRoleConvert : kRoleCoeff;
+    const unsigned long long role_t0 = prof_lane ? global_ns() : 0ull;
 
     if (warp == 0) {
         // =================================== TMA producer ===================================
@@ -326,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                         const int rows = min(kTileT, T - t0);
                         for (int kb = 0; kb < prm.kb_count; ++kb, ++slab) {
                             const uint32_t rs = slab % kRawStages, ph = (slab / kRawStages) & 1u;
-                            ok = mbar_wait(bar(kRawEmpty + rs), ph ^ 1u, ctl, prm.status, kRoleProducer, kRawEmpty + rs);
+                            ok = mbar_wait(bar(kRawEmpty + rs), ph ^ 1u, ctl, prm.status, kRoleProducer, kRawEmpty + rs, ps + 0);
                             if (!ok) break;
                             const int a0 = kb * kKbAnts;
                             const int n_ants = min(kKbAnts, A - a0);
@@ -348,15 +363,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
         for (int c = blockIdx.x; c < C && ok; c += gridDim.x)
             for (int it = 0; it < prm.nt_count && ok; ++it, ++step) {
                 const uint32_t bb = step % kBopBufs;
-                ok = mbar_wait(bar(kBopFull + bb), (step / kBopBufs) & 1u, ctl, prm.status, kRoleMma, kBopFull + bb);
+                ok = mbar_wait(bar(kBopFull + bb), (step / kBopBufs) & 1u, ctl, prm.status, kRoleMma, kBopFull + bb, ps + 0);
                 for (int bh = 0; bh < B * prm.ht_count && ok; ++bh, ++unit) {
                     const uint32_t ab = unit % kAccBufs;
-                    ok = mbar_wait(bar(kAccEmpty + ab), ((unit / kAccBufs) & 1u) ^ 1u, ctl, prm.status, kRoleMma, kAccEmpty + ab);
+                    ok = mbar_wait(bar(kAccEmpty + ab), ((unit / kAccBufs) & 1u) ^ 1u, ctl, prm.status, kRoleMma, kAccEmpty + ab, ps + 1);
                     if (!ok) break;
                     tc_fence_after();
                     for (int kb = 0; kb < prm.kb_count; ++kb, ++slab) {
                         const uint32_t as = slab % kAopStages;
-                        ok = mbar_wait(bar(kAopFull + as), (slab / kAopStages) & 1u, ctl, prm.status, kRoleMma, kAopFull + as);
+                        ok = mbar_wait(bar(kAopFull + as), (slab / kAopStages) & 1u, ctl, prm.status, kRoleMma, kAopFull + as, ps + 2);
                         if (!ok) break;
                         tc_fence_after();
                         if (lane == 0) {
@@ -395,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 for (int b = 0; b < B && ok; ++b)
                     for (int h = 0; h < prm.ht_count && ok; ++h, ++unit) {
                         const uint32_t ab = unit % kAccBufs;
-                        ok = mbar_wait(bar(kAccFull + ab), (unit / kAccBufs) & 1u, ctl, prm.status, kRoleEpilogue, kAccFull + ab);
+                        ok = mbar_wait(bar(kAccFull + ab), (unit / kAccBufs) & 1u, ctl, prm.status, kRoleEpilogue, kAccFull + ab, ps + 0);
                         if (!ok) break;
                         tc_fence_after();
                         const int t0 = h * kTileT;
@@ -472,9 +487,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 for (int bh = 0; bh < B * prm.ht_count && ok; ++bh)
                     for (int kb = 0; kb < prm.kb_count; ++kb, ++slab) {
                         const uint32_t rs = slab % kRawStages, as = slab % kAopStages;
-                        ok = mbar_wait(bar(kRawFull + rs), (slab / kRawStages) & 1u, ctl, prm.status, kRoleConvert, kRawFull + rs);
+                        ok = mbar_wait(bar(kRawFull + rs), (slab / kRawStages) & 1u, ctl, prm.status, kRoleConvert, kRawFull + rs, ps + 0);
                         if (ok)
-                            ok = mbar_wait(bar(kAopEmpty + as), ((slab / kAopStages) & 1u) ^ 1u, ctl, prm.status, kRoleConvert, kAopEmpty + as);
+                            ok = mbar_wait(bar(kAopEmpty + as), ((slab / kAopStages) & 1u) ^ 1u, ctl, prm.status, kRoleConvert, kAopEmpty + as, ps + 1);
                         if (!ok) break;
                         const int n_ants = min(kKbAnts, A - kb * kKbAnts);
                         const int n_chunks = 2 * ((n_ants + 7) >> 3);  // 4-antenna chunks inside the padded K extent
@@ -502,15 +517,21 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                             mbar_arrive(bar(kRawEmpty + rs));
                         }
                     }
-    } else if (warp >= 12) {
+    } else if (warp >= kCoeffWarp0) {
         // =================================== steering coefficients ===================================
-        // lane <-> antenna (coalesced 16-byte delay_vals structs); a quad of lanes transposes its four
-        // (cos,-sin | sin,cos) x (hi,lo) words so that each lane owns one 16-byte swizzle chunk.
-        const int tid = threadIdx.x - 12 * 32;
+        // 32 lanes <-> 32 consecutive (beam, antenna) entries = 512 contiguous bytes of delay_vals per load.
+        // Lane L takes entry 4*(L%8) + L/8 of its group, so the four lanes {j, j+8, j+16, j+24} hold one
+        // 4-antenna chunk; they transpose their (row 2m | row 2m+1) x (hi | lo) words with two xor-shuffles and
+        // each ends up owning one 16-byte swizzle chunk.  A quarter-warp then stores 8 different chunks of the
+        // same B row: conflict-free STS.128.
+        const int wtid = (warp - kCoeffWarp0) * 32;
+        const int perm = 4 * (lane & 7) + (lane >> 3);
         const int a4 = (A + 3) & ~3;
         const int mt = nt >> 1;             // beams per N tile
         const int entries = mt * a4;        // (beam, antenna) pairs per N tile, quad-aligned
         const double kInvPi = 0.318309886183790671538;
+        constexpr int kBatch = 8;
+        constexpr int kStride = kCoeffWarps * 32;
         uint32_t step = 0;
         bool ok = true;
         for (int c = blockIdx.x; c < C && ok; c += gridDim.x) {
@@ -520,7 +541,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 const uint32_t bb = step % kBopBufs;
                 const int m0 = it * mt;
                 // warm L2 for the step after this one (same channel next N tile, or next channel's first)
-                if (tid == 0) {
+                if (warp == kCoeffWarp0 && lane == 0) {
                     int nc = c, nit = it + 1;
                     if (nit == prm.nt_count) {
                         nit = 0;
@@ -535,29 +556,33 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                             bulk_prefetch_l2(p + o, static_cast<uint32_t>(min(bytes - o, static_cast<size_t>(65536))));
                     }
                 }
-                ok = mbar_wait(bar(kBopEmpty + bb), ((step / kBopBufs) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + bb);
-                if (!ok) break;
+                bool waited = false;
                 const uint32_t buf = bop_base + bb * kBopBufBytes;
-                constexpr int kBatch = 4;
-                for (int e0 = (tid & ~31); e0 < entries; e0 += 128 * kBatch) {
-                    float4 v[kBatch];
+                for (int e0 = wtid; e0 < entries; e0 += kStride * kBatch) {
+                    float2 v[kBatch];  // (delay_s, phase_rad); the two rate fields are ignored like the reference does
 #pragma unroll
                     for (int u = 0; u < kBatch; ++u) {
-                        const int e = e0 + u * 128 + lane;
+                        const int e = e0 + u * kStride + perm;
                         const int ml = e / a4, a = e - ml * a4;
                         const bool valid = e < entries && a < A && m0 + ml < M;
-                        v[u] = valid ? ldg_nc_f4(prm.dv + (static_cast<size_t>(c) * M + (m0 + ml)) * A + a)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid) t4 = ldg_nc_f4(prm.dv + (static_cast<size_t>(c) * M + (m0 + ml)) * A + a);
+                        v[u] = make_float2(t4.x, t4.z);
+                    }
+                    if (!waited) {  // loads above are already in flight while we wait for the buffer
+                        ok = mbar_wait(bar(kBopEmpty + bb), ((step / kBopBufs) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + bb, ps + 0);
+                        waited = true;
+                        if (!ok) break;
                     }
 #pragma unroll
                     for (int u = 0; u < kBatch; ++u) {
-                        const int eb = e0 + u * 128;  // warp-uniform
+                        const int eb = e0 + u * kStride;  // warp-uniform
                         if (eb >= entries) break;
-                        const int e = eb + lane;
+                        const int e = eb + perm;
                         const int ml = e / a4, a = e - ml * a4;
                         const bool valid = e < entries && a < A && m0 + ml < M;
                         // rot/pi = delay * (ch - N/2) * (-1/(N Ts)) + phase/pi   (coeff_generator_cpu.py:143-165)
-                        const double x = fma(static_cast<double>(v[u].x), scale, static_cast<double>(v[u].z) * kInvPi);
+                        const double x = fma(static_cast<double>(v[u].x), scale, static_cast<double>(v[u].y) * kInvPi);
                         const float r = static_cast<float>(x - 2.0 * rint(0.5 * x));  // [-1, 1] half-turns
                         float sn, cs;
                         sincospif(r, &sn, &cs);
@@ -571,11 +596,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                         uint32_t w1 = pack_half2(cs - cs_h, -(sn - sn_h));
                         uint32_t w2 = pack_half2(sn_h, cs_h);
                         uint32_t w3 = pack_half2(sn - sn_h, cs - cs_h);
-                        // 4x4 transpose inside the quad: lane i ends with word i of antennas 4g..4g+3
+                        // 4x4 transpose across lanes {j, j+8, j+16, j+24}: lane with index i = lane/8 ends with
+                        // word i of the chunk's four antennas
                         {
-                            const bool odd = lane & 1;
+                            const bool odd = lane & 8;
                             const uint32_t s0 = odd ? w0 : w1, s1 = odd ? w2 : w3;
-                            const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                            const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 8), r1 = __shfl_xor_sync(0xffffffffu, s1, 8);
                             if (odd) {
                                 w0 = r0;
                                 w2 = r1;
@@ -583,9 +609,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                                 w1 = r0;
                                 w3 = r1;
                             }
-                            const bool up = lane & 2;
+                            const bool up = lane & 16;
                             const uint32_t s2 = up ? w0 : w2, s3 = up ? w1 : w3;
-                            const uint32_t r2 = __shfl_xor_sync(0xffffffffu, s2, 2), r3 = __shfl_xor_sync(0xffffffffu, s3, 2);
+                            const uint32_t r2 = __shfl_xor_sync(0xffffffffu, s2, 16), r3 = __shfl_xor_sync(0xffffffffu, s3, 16);
                             if (up) {
                                 w0 = r2;
                                 w1 = r3;
@@ -594,11 +620,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                                 w3 = r3;
                             }
                         }
-                        const int which = lane & 3;  // 0: row 2m hi, 1: row 2m lo, 2: row 2m+1 hi, 3: row 2m+1 lo
+                        const int which = lane >> 3;  // 0: row 2m hi, 1: row 2m lo, 2: row 2m+1 hi, 3: row 2m+1 lo
                         const int part = which & 1;
                         if (e < entries && part < parts) {
                             const int row = 2 * ml + (which >> 1);
-                            const int chunk = a >> 2;  // 4 antennas = 8 fp16 = 16 B (a is this lane's antenna; same quad)
+                            const int chunk = a >> 2;  // 4 antennas = 8 fp16 = 16 B (same for the four cooperating lanes)
                             const int kb = chunk >> 3, jj = chunk & 7;
                             const uint32_t dst = buf + kb * bop_kb_bytes + part * (nt * 128) + row * 128 +
                                                  static_cast<uint32_t>((jj ^ (row & 7)) << 4);
@@ -606,6 +632,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                         }
                     }
                 }
+                if (!ok) break;
+                if (!waited)  // this warp had no entries in this step; it still takes part in the hand-shake
+                    ok = mbar_wait(bar(kBopEmpty + bb), ((step / kBopBufs) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + bb, ps + 0);
+                if (!ok) break;
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(kBopFull + bb));
@@ -614,8 +644,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
     }
 
     // ---- teardown ----
+    if (prof_lane) ctl->wait_ns[my_role][3] = global_ns() - role_t0;
     tc_fence_before();
     __syncthreads();
+    if (prm.prof && threadIdx.x < 24) prm.prof[blockIdx.x * 24 + threadIdx.x] = ctl->wait_ns[threadIdx.x >> 2][threadIdx.x & 3];
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -623,6 +655,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
 }
 
 int* g_status_dev[64] = {};  // per-device 4-int status block, allocated on first use
+unsigned long long* g_prof_dev = nullptr;  // set by fused_set_profile_buffer (developer aid)
 
 }  // namespace
 
@@ -668,6 +701,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     p.chan_centre = static_cast<double>(first_chan) - static_cast<double>(N) / 2.0;
     p.turns_per_delay = -1.0 / (static_cast<double>(N) * sample_period);
     if (int e = get_status_block(&p.status)) return e;
+    p.prof = g_prof_dev;
 
     static int n_sms[64] = {};
     int dev = 0;
@@ -693,6 +727,8 @@ int fused_status(int* role, int* barrier, int* block) {
     if (block) *block = h[3];
     return h[0];
 }
+
+void fused_set_profile_buffer(unsigned long long* dev_ptr) { g_prof_dev = dev_ptr; }
 
 void fused_tiling(int A, int M, unsigned flags, int* kb_count, int* nt, int* nt_count) {
     pick_n_tiling(A, M, (flags & DCBF_FLAG_FP16_COEFF) ? 1 : 2, kb_count, nt, nt_count);

@@ -94,6 +94,11 @@ int dcbf_fused(const uint8_t* samples, const float* delay_vals, float* beams, in
  * then exits early instead of hanging; *role / *barrier / *block say who waited on what).  Clears the status. */
 int dcbf_fused_status(int* role, int* barrier, int* block);
 
+/* Developer aid: when non-NULL, every dcbf_fused CTA writes 24 uint64 to dev_ptr[blockIdx*24 + role*4 + slot]:
+ * nanoseconds each warp role spent blocked per barrier class (slot 0..2) and the role's span (slot 3).
+ * The buffer must hold 24 * (number of SMs) entries. */
+void dcbf_debug_set_profile_buffer(unsigned long long* dev_ptr);
+
 /* The tiling dcbf_fused will use for (n_ants, n_beams, flags): k-blocks of 32 antennas, N tiles of *nt columns. */
 void dcbf_fused_tiling(int n_ants, int n_beams, unsigned flags, int* kb_count, int* nt, int* nt_count);
 
