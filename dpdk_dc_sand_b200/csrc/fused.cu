@@ -99,6 +99,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok;
 }
+// Same probe with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~the hint
+// elapses, instead of returning to spin through the issue slots the working warps need.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok;
+}
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -179,6 +192,9 @@ __device__ __forceinline__ void st_global_v2(float* p, uint32_t a, uint32_t b) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
@@ -219,8 +235,8 @@ struct Control {
 __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Control* ctl, int* status, int role, int id) {
     const unsigned long long t0 = global_ns();
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 63u) == 0) {
+    while (!mbar_try_wait_hint(bar, parity, 100000u)) {
+        if ((++spins & 15u) == 0) {
             if (ctl->abort) return false;
             if (global_ns() - t0 > kWatchdogNs) {
                 ctl->abort = 1;
@@ -259,6 +275,30 @@ __device__ __forceinline__ uint32_t bytes_to_half2(uint32_t w, uint32_t sel, uin
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     const __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// sin(pi r), cos(pi r) for r in [-1, 1] (half-turns, already range-reduced in float64).  Quadrant split
+// q = rint(2r), t = r - q/2 in [-1/4, 1/4], odd/even Taylor polynomials in t (truncation < 2e-9 and 2e-10),
+// then the quadrant rotation.  Absolute error <= ~1.2e-7; no special cases (r is always finite here).
+__device__ __forceinline__ void sincospi_reduced(float r, float* sn, float* cs) {
+    const float z = fmaf(r, 2.0f, 12582912.0f);  // 1.5 * 2^23: the low mantissa bits now hold rint(2r)
+    const int q = __float_as_int(z);
+    const float t = fmaf(z - 12582912.0f, -0.5f, r);
+    const float s = t * t;
+    float ps = fmaf(s, 0.0821458866f, -0.599264529f);   // pi^9/9!, -pi^7/7!
+    ps = fmaf(ps, s, 2.55016404f);                       // pi^5/5!
+    ps = fmaf(ps, s, -5.16771278f);                      // -pi^3/3!
+    ps = fmaf(ps * s, t, t * 3.14159274f) ;              // t*pi + t*s*(...)
+    float pc = fmaf(s, -0.0258068914f, 0.235330630f);    // -pi^10/10!, pi^8/8!
+    pc = fmaf(pc, s, -1.33526277f);                      // -pi^6/6!
+    pc = fmaf(pc, s, 4.05871213f);                       // pi^4/4!
+    pc = fmaf(pc, s, -4.93480220f);                      // -pi^2/2!
+    pc = fmaf(pc, s, 1.0f);
+    const bool swap = q & 1;
+    const float a = swap ? pc : ps, b = swap ? ps : pc;
+    // q mod 4: 0 -> (s, c); 1 -> (c, -s); 2 -> (-s, -c); 3 -> (-c, s)
+    *sn = __int_as_float(__float_as_int(a) ^ ((q << 30) & 0x80000000));
+    *cs = __int_as_float(__float_as_int(b) ^ (((q + 1) << 30) & 0x80000000));
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -519,19 +559,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                     }
     } else if (warp >= kCoeffWarp0) {
         // =================================== steering coefficients ===================================
-        // 32 lanes <-> 32 consecutive (beam, antenna) entries = 512 contiguous bytes of delay_vals per load.
-        // Lane L takes entry 4*(L%8) + L/8 of its group, so the four lanes {j, j+8, j+16, j+24} hold one
-        // 4-antenna chunk; they transpose their (row 2m | row 2m+1) x (hi | lo) words with two xor-shuffles and
-        // each ends up owning one 16-byte swizzle chunk.  A quarter-warp then stores 8 different chunks of the
-        // same B row: conflict-free STS.128.
-        const int wtid = (warp - kCoeffWarp0) * 32;
-        const int perm = 4 * (lane & 7) + (lane >> 3);
-        const int a4 = (A + 3) & ~3;
-        const int mt = nt >> 1;             // beams per N tile
-        const int entries = mt * a4;        // (beam, antenna) pairs per N tile, quad-aligned
-        const double kInvPi = 0.318309886183790671538;
+        // delay_vals[c][m0 .. m0+mt) is one contiguous run of (beam, antenna) entries: the 256 threads walk it
+        // with lane <-> consecutive entry, so every warp load is 512 contiguous bytes.  Each entry becomes four
+        // 32-bit words (row 2m | row 2m+1) x (fp16 hi | fp16 lo residual); consecutive antennas are consecutive
+        // words of one 128-byte B row, so each of the four STS.32 of a warp touches 32 different banks.
+        const int ctid = threadIdx.x - kCoeffWarp0 * 32;
+        const int mt = nt >> 1;  // beams per N tile
         constexpr int kBatch = 8;
         constexpr int kStride = kCoeffWarps * 32;
+        const int dm = kStride / A, da = kStride - dm * A;  // (beam, antenna) advance per kStride entries
+        const int ml_first = ctid / A, a_first = ctid - ml_first * A;
+        const uint32_t part_bytes = static_cast<uint32_t>(nt * 128);
+        const double kInvPi = 0.318309886183790671538;
         uint32_t step = 0;
         bool ok = true;
         for (int c = blockIdx.x; c < C && ok; c += gridDim.x) {
@@ -540,6 +579,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
             for (int it = 0; it < prm.nt_count && ok; ++it, ++step) {
                 const uint32_t bb = step % kBopBufs;
                 const int m0 = it * mt;
+                const int entries = min(mt, M - m0) * A;
+                const float4* src = prm.dv + (static_cast<size_t>(c) * M + m0) * A;
                 // warm L2 for the step after this one (same channel next N tile, or next channel's first)
                 if (warp == kCoeffWarp0 && lane == 0) {
                     int nc = c, nit = it + 1;
@@ -558,77 +599,52 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 }
                 bool waited = false;
                 const uint32_t buf = bop_base + bb * kBopBufBytes;
-                for (int e0 = wtid; e0 < entries; e0 += kStride * kBatch) {
+                int ml = ml_first, a = a_first;
+                for (int e0 = ctid; e0 < entries + ctid; e0 += kStride * kBatch) {  // e0 - ctid is warp-uniform
                     float2 v[kBatch];  // (delay_s, phase_rad); the two rate fields are ignored like the reference does
 #pragma unroll
                     for (int u = 0; u < kBatch; ++u) {
-                        const int e = e0 + u * kStride + perm;
-                        const int ml = e / a4, a = e - ml * a4;
-                        const bool valid = e < entries && a < A && m0 + ml < M;
+                        const int e = e0 + u * kStride;
                         float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid) t4 = ldg_nc_f4(prm.dv + (static_cast<size_t>(c) * M + (m0 + ml)) * A + a);
+                        if (e < entries) t4 = ldg_nc_f4(src + e);
                         v[u] = make_float2(t4.x, t4.z);
                     }
-                    if (!waited) {  // loads above are already in flight while we wait for the buffer
+                    if (!waited) {  // the loads above are already in flight while we wait for the buffer
                         ok = mbar_wait(bar(kBopEmpty + bb), ((step / kBopBufs) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + bb, ps + 0);
                         waited = true;
                         if (!ok) break;
                     }
 #pragma unroll
                     for (int u = 0; u < kBatch; ++u) {
-                        const int eb = e0 + u * kStride;  // warp-uniform
-                        if (eb >= entries) break;
-                        const int e = eb + perm;
-                        const int ml = e / a4, a = e - ml * a4;
-                        const bool valid = e < entries && a < A && m0 + ml < M;
-                        // rot/pi = delay * (ch - N/2) * (-1/(N Ts)) + phase/pi   (coeff_generator_cpu.py:143-165)
-                        const double x = fma(static_cast<double>(v[u].x), scale, static_cast<double>(v[u].y) * kInvPi);
-                        const float r = static_cast<float>(x - 2.0 * rint(0.5 * x));  // [-1, 1] half-turns
-                        float sn, cs;
-                        sincospif(r, &sn, &cs);
-                        if (!valid) {
-                            sn = 0.f;
-                            cs = 0.f;
-                        }
-                        const float cs_h = __half2float(__float2half_rn(cs)), sn_h = __half2float(__float2half_rn(sn));
-                        // B^T rows: n = 2m -> (k=2a: cos, k=2a+1: -sin);  n = 2m+1 -> (sin, cos)
-                        uint32_t w0 = pack_half2(cs_h, -sn_h);
-                        uint32_t w1 = pack_half2(cs - cs_h, -(sn - sn_h));
-                        uint32_t w2 = pack_half2(sn_h, cs_h);
-                        uint32_t w3 = pack_half2(sn - sn_h, cs - cs_h);
-                        // 4x4 transpose across lanes {j, j+8, j+16, j+24}: lane with index i = lane/8 ends with
-                        // word i of the chunk's four antennas
-                        {
-                            const bool odd = lane & 8;
-                            const uint32_t s0 = odd ? w0 : w1, s1 = odd ? w2 : w3;
-                            const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 8), r1 = __shfl_xor_sync(0xffffffffu, s1, 8);
-                            if (odd) {
-                                w0 = r0;
-                                w2 = r1;
-                            } else {
-                                w1 = r0;
-                                w3 = r1;
-                            }
-                            const bool up = lane & 16;
-                            const uint32_t s2 = up ? w0 : w2, s3 = up ? w1 : w3;
-                            const uint32_t r2 = __shfl_xor_sync(0xffffffffu, s2, 16), r3 = __shfl_xor_sync(0xffffffffu, s3, 16);
-                            if (up) {
-                                w0 = r2;
-                                w1 = r3;
-                            } else {
-                                w2 = r2;
-                                w3 = r3;
+                        const int e = e0 + u * kStride;
+                        if (e < entries) {
+                            // rot/pi = delay * (ch - N/2) * (-1/(N Ts)) + phase/pi   (coeff_generator_cpu.py:143-165)
+                            const double x = fma(static_cast<double>(v[u].x), scale, static_cast<double>(v[u].y) * kInvPi);
+                            const float r = static_cast<float>(x - 2.0 * rint(0.5 * x));  // [-1, 1] half-turns
+                            float sn, cs;
+                            sincospi_reduced(r, &sn, &cs);
+                            // fp16 hi + fp16 residual of (cos, sin)
+                            const uint32_t hi = pack_half2(cs, sn);
+                            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+                            const uint32_t lo = pack_half2(cs - hf.x, sn - hf.y);
+                            // B^T rows: n = 2m -> (k=2a: cos, k=2a+1: -sin);  n = 2m+1 -> (sin, cos)
+                            const int row = 2 * ml;
+                            const int al = a & (kKbAnts - 1);
+                            const uint32_t d0 = buf + static_cast<uint32_t>(a >> 5) * bop_kb_bytes + static_cast<uint32_t>(row) * 128u +
+                                                (static_cast<uint32_t>(((al >> 2) ^ (row & 7)) << 4) | static_cast<uint32_t>((al & 3) << 2));
+                            const uint32_t d1 = (d0 + 128u) ^ 16u;  // row + 1: swizzle phase (row & 7) | 1
+                            st_shared_u32(d0, hi ^ 0x80000000u);
+                            st_shared_u32(d1, __byte_perm(hi, 0u, 0x1032u));
+                            if (parts > 1) {
+                                st_shared_u32(d0 + part_bytes, lo ^ 0x80000000u);
+                                st_shared_u32(d1 + part_bytes, __byte_perm(lo, 0u, 0x1032u));
                             }
                         }
-                        const int which = lane >> 3;  // 0: row 2m hi, 1: row 2m lo, 2: row 2m+1 hi, 3: row 2m+1 lo
-                        const int part = which & 1;
-                        if (e < entries && part < parts) {
-                            const int row = 2 * ml + (which >> 1);
-                            const int chunk = a >> 2;  // 4 antennas = 8 fp16 = 16 B (same for the four cooperating lanes)
-                            const int kb = chunk >> 3, jj = chunk & 7;
-                            const uint32_t dst = buf + kb * bop_kb_bytes + part * (nt * 128) + row * 128 +
-                                                 static_cast<uint32_t>((jj ^ (row & 7)) << 4);
-                            st_shared_v4(dst, w0, w1, w2, w3);
+                        ml += dm;
+                        a += da;
+                        if (a >= A) {
+                            a -= A;
+                            ++ml;
                         }
                     }
                 }
