@@ -1,0 +1,101 @@
+"""Frequency-channel sharding of the beamforming path across the GPUs of one box.
+
+The path shards with NO data-path collective: every output ``(b, p, c, ...)`` depends only on channel ``c``
+of the voltages and ``delay_vals[c]``.  This is the reference's own X-engine decomposition -- each engine owns
+``n_channels_per_stream = n_channels // n_engines`` contiguous channels and evaluates the steering phase at the
+absolute channel ``c + n_channels_per_stream * xeng_id`` (reference: beamformer/beamforming/coeff_generator.py:53,
+beamformer/unit_test/coeff_generator_cpu.py:138-141; ``n_channels_per_stream = n_channels // n_ants // 4`` in the
+tests, e.g. beamformer/unit_test/prebeamform_reorder_test.py:72).  Here rank ``r`` of ``world`` *is* X-engine
+``xeng_id = r``.
+
+One process per GPU (``torch.distributed``; NCCL over NVLink on the GPUs, gloo in the CPU tests).  The only
+collective is the OPTIONAL gather of the beam outputs along the channel axis to one rank (``gather_beams``);
+nothing in the compute path waits on another rank.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+
+@dataclass(frozen=True)
+class ChannelShard:
+    """What rank ``rank`` of ``world`` owns: channels ``[first_channel, first_channel + n_channels_per_stream)``."""
+
+    rank: int
+    world: int
+    n_channels: int             # total F-engine channels N (the `n_channels` ctor argument of the operators)
+    n_channels_per_stream: int  # C: channels this rank processes
+
+    @property
+    def xeng_id(self) -> int:
+        return self.rank
+
+    @property
+    def first_channel(self) -> int:
+        return self.rank * self.n_channels_per_stream
+
+    @property
+    def channels(self) -> slice:
+        return slice(self.first_channel, self.first_channel + self.n_channels_per_stream)
+
+
+def plan(n_channels: int, world: Optional[int] = None, rank: Optional[int] = None) -> ChannelShard:
+    """Shard ``n_channels`` over ``world`` ranks (defaults: WORLD_SIZE / RANK from the torchrun environment)."""
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else int(world)
+    rank = int(os.environ.get("RANK", "0")) if rank is None else int(rank)
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    if n_channels <= 0 or n_channels % world:
+        # the reference's `n_channels // n_engines` silently drops the remainder; refuse instead
+        raise ValueError(f"n_channels ({n_channels}) must be a positive multiple of the number of ranks ({world})")
+    return ChannelShard(rank, world, n_channels, n_channels // world)
+
+
+def local_samples(samples, shard: ChannelShard):
+    """``(B, A, N, T, P, 2)`` full-band voltages -> this rank's contiguous ``(B, A, C, T, P, 2)`` block.
+
+    Works on numpy arrays and torch tensors.  (In production each X-engine receives only its own channels;
+    this helper exists for tests and for feeding synthetic full-band data.)"""
+    part = samples[:, :, shard.channels]
+    return part.contiguous() if hasattr(part, "contiguous") else part.copy()
+
+
+def local_delay_vals(delay_vals, shard: ChannelShard):
+    """``(N, M, A, 4)`` full-band delay models -> this rank's ``(C, M, A, 4)`` block."""
+    part = delay_vals[shard.channels]
+    return part.contiguous() if hasattr(part, "contiguous") else part.copy()
+
+
+def make_op_sequence(context, queue, shard: ChannelShard, n_batches: int, n_ants: int, n_beams: int,
+                     n_samples_per_channel: int, sample_period: float):
+    """The rank-local fused operation: the reference's OpSequenceTemplate with ``xeng_id = rank``."""
+    from .beamforming.beamform_op_sequence import OpSequenceTemplate
+
+    tmpl = OpSequenceTemplate(context, n_batches, 2, shard.n_channels_per_stream, shard.n_channels,
+                              n_samples_per_channel // 16, 16, n_ants, n_beams, shard.xeng_id, sample_period,
+                              n_samples_per_channel)
+    return tmpl.instantiate(queue)
+
+
+def gather_beams(local_beams, shard: ChannelShard, dst: int = 0, group=None):
+    """Optional: collect every rank's ``(B, P, C, K, S, 2M)`` beams on ``dst`` as ``(B, P, N, K, S, 2M)``.
+
+    ``local_beams`` is a torch tensor (CUDA with the nccl backend, CPU with gloo).  Returns the full-band
+    tensor on ``dst`` and ``None`` elsewhere.  This is the only collective of the package and it is outside
+    the timed compute path."""
+    import torch
+    import torch.distributed as dist
+
+    if shard.world == 1:
+        return local_beams
+    if tuple(local_beams.shape)[2] != shard.n_channels_per_stream:
+        raise ValueError("local_beams axis 2 must be this rank's n_channels_per_stream")
+    local_beams = local_beams.contiguous()
+    # grouped send/recv under the hood (ncclSend/ncclRecv over NVLink/NVSwitch with the nccl backend)
+    parts = [torch.empty_like(local_beams) for _ in range(shard.world)] if dist.get_rank(group) == dst else None
+    dist.gather(local_beams, parts, dst=dst, group=group)
+    if parts is None:
+        return None
+    return torch.cat(parts, dim=2)
