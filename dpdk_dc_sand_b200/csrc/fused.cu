@@ -16,17 +16,20 @@
 //                  (two accumulating MMAs; coefficient error ~2^-24) or fp16 hi only (DCBF_FLAG_FP16_COEFF).
 //
 // One persistent CTA per SM walks channels c = blockIdx.x, +gridDim.x, ...  Warp roles (576 threads):
-//   warps 0-7     coeffs    : delay_vals (coalesced float4) -> f64 phase -> sincospi -> swizzled B tiles
-//   warps 8-11    convert   : raw bytes -> fp16, pol de-interleave, a<->t transpose into the 128B-swizzled A tiles
-//   warps 12-15   epilogue  : tcgen05.ld 16x256b -> full-sector st.global.v2 straight from registers
-//   warp 16       producer  : 1-D TMA bulk copies  in[b][a][c][t0:t0+128] (512 B runs) -> raw ring, mbarrier tx
+//   warps 0-7     coeffs    : delay_vals (coalesced float4, one batch prefetched in registers) -> f64 phase
+//                             -> sincospi -> fp16 hi/lo -> 128B-swizzled B tiles, one channel ahead
+//   warps 8-11    convert   : raw bytes -> fp16, pol de-interleave, a<->t transpose into 64B-swizzled A tiles
+//   warps 12-15   epilogue  : tcgen05.ld 32x32b -> 128B-swizzled staging tile -> TMA tensor store (32x32 boxes)
+//                             (odd beam counts / ragged N tiles: 16x256b -> st.global.v2 from registers)
+//   warp 16       producer  : one tensor-map TMA box [16 ant][128 samples][4 B] per slab -> raw ring
 //   warp 17       MMA       : one lane issues tcgen05.mma (M=128, N<=128, K=16), accumulators in TMEM
 // Pipelines (mbarrier full/empty pairs): raw ring (TMA->convert), A ring (convert->MMA), B double buffer
-// (coeffs->MMA, one channel ahead), TMEM accumulator double buffer (MMA->epilogue).
+// (coeffs->MMA), TMEM accumulator double buffer (MMA->epilogue), per-warp staging pairs (bulk groups).
 //
-// Tiling: time tiles of 128 samples (UMMA M), k-blocks of 32 antennas (64 fp16 = one 128-byte swizzle row),
-// N tiles of <=128 columns (64 beams) chosen so that one B tile set (all k-blocks, hi+lo) fits 64 KiB.  With
-// more than one N tile the voltages of a channel are re-read (they then come from L2).
+// Tiling: time tiles of 128 samples (UMMA M), slabs of 16 antennas (K = 32 = two MMA K-steps), B k-blocks of
+// 32 antennas (one 128-byte swizzle row), N tiles of <=128 columns chosen so that one B tile set (all k-blocks,
+// hi+lo) fits 64 KiB.  With more than one N tile the voltages of a channel are re-read (from L2).
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -46,39 +49,42 @@ constexpr int kProducerWarp = 16;
 constexpr int kMmaWarp = 17;
 constexpr int kThreads = 18 * 32;
 constexpr int kTileT = 128;    // samples per MMA tile (UMMA M)
-constexpr int kKbAnts = 32;    // antennas per k-block
-constexpr int kRawStages = 2;
+constexpr int kSlabAnts = 16;  // antennas per raw slab / A stage
+constexpr int kKbAnts = 32;    // antennas per B k-block (128-byte swizzle row of fp16)
+constexpr int kRawStages = 4;
 constexpr int kAopStages = 2;
 constexpr int kBopBufs = 2;
 constexpr int kAccBufs = 2;
-constexpr int kRawStageBytes = kKbAnts * kTileT * 4;  // 16 KiB: [ant][t][pol][re,im]
-constexpr int kAopTileBytes = kTileT * 128;           // 16 KiB: [t][64 fp16], 128B swizzle
-constexpr int kAopStageBytes = 2 * kAopTileBytes;     // pol 0 + pol 1
+constexpr int kRawStageBytes = kSlabAnts * kTileT * 4;  // 8 KiB: [ant][t][pol][re,im]
+constexpr int kAopTileBytes = kTileT * 64;              // 8 KiB: [t][32 fp16], 64B swizzle
+constexpr int kAopStageBytes = 2 * kAopTileBytes;       // pol 0 + pol 1
 constexpr int kBopBufBytes = 64 * 1024;
+constexpr int kOutBoxBytes = 32 * 128;                  // 32 rows x 32 fp32 columns, 128B swizzle
+constexpr int kOutStageBytes = 4 * 2 * kOutBoxBytes;    // 4 epilogue warps x 2 boxes
 constexpr int kTmemCols = 512;
 constexpr unsigned long long kWatchdogNs = 2000000000ull;  // 2 s without progress on one barrier = dead-lock
 
-constexpr int kSmemData = kAopStages * kAopStageBytes + kBopBufs * kBopBufBytes + kRawStages * kRawStageBytes;
+constexpr int kSmemData = kAopStages * kAopStageBytes + kBopBufs * kBopBufBytes + kRawStages * kRawStageBytes + kOutStageBytes;
 constexpr int kSmemBytes = 1024 /*alignment slack*/ + kSmemData + 512 /*barriers + control*/;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 enum Role { kRoleProducer = 1, kRoleMma = 2, kRoleEpilogue = 3, kRoleConvert = 4, kRoleCoeff = 5 };
 
 struct FusedParams {
-    const uint8_t* in;
     const float4* dv;
     float* out;
     int* status;  // [0]=error code, [1]=role, [2]=barrier id, [3]=blockIdx
     unsigned long long* prof;  // optional [grid][6 roles][4]: ns blocked per barrier class, [..][3] = role span
     int B, A, C, T, M;
-    int kb_count;   // ceil(A / 32)
-    int nt;         // columns per N tile (multiple of 16, <= 128)
-    int nt_count;   // number of N tiles
-    int ht_count;   // ceil(T / 128)
-    int parts;      // 2 = fp16 hi+lo coefficients, 1 = fp16 hi only
+    int slab_count;  // ceil(A / 16)
+    int kb_count;    // ceil(A / 32)
+    int nt;          // columns per N tile (multiple of 16, <= 128)
+    int nt_count;    // number of N tiles
+    int ht_count;    // ceil(T / 128)
+    int parts;       // 2 = fp16 hi+lo coefficients, 1 = fp16 hi only
     int signed_in;
-    int rowwise_epilogue;  // debug: 32x32b row-per-thread epilogue
-    double chan_centre;    // absolute index of local channel 0, minus N/2
+    int tma_store;   // 1: epilogue through shared memory + TMA tensor stores; 0: st.global from registers
+    double chan_centre;      // absolute index of local channel 0, minus N/2
     double turns_per_delay;  // -1 / (N * Ts): half-turns of phase per (second of delay x channel offset)
 };
 
@@ -117,11 +123,28 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// 1-D TMA: global -> shared, completion counted in bytes on an mbarrier.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
+// Tensor-map TMA: one [16 ant] x [128 sample] box of 4-byte words, global -> shared, bytes counted on an mbarrier.
+// Out-of-range antennas / samples are zero-filled by the hardware and still count towards the box's bytes.
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// Tensor-map TMA store: one [32 row] x [32 column] fp32 box, shared -> global; rows/columns outside the tensor are clipped.
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
@@ -170,13 +193,12 @@ __device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)
         : "r"(taddr)
         : "memory");
 }
-// 32 lanes x 16 columns: thread = row, r[j] = column j.
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+// 32 lanes x 32 columns: thread = row (TMEM lane), r[j] = column j.
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
 }
@@ -203,14 +225,14 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
     return v;
 }
 
-// Shared-memory matrix descriptor: K-major, 128-byte swizzle, rows 128 B apart, 8-row atoms 1024 B apart.
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-    uint64_t d = static_cast<uint64_t>((smem_addr >> 4) & 0x3fffu);
-    d |= 1ull << 16;             // leading byte offset (unused for swizzled K-major), canonical value 1
-    d |= (1024ull >> 4) << 32;   // stride byte offset between 8-row atoms
-    d |= 1ull << 46;             // descriptor version (Blackwell)
-    d |= 2ull << 61;             // SWIZZLE_128B
-    return d;
+// Shared-memory matrix descriptors, K-major.  Low word: start address >> 4 (14 bits) | leading-byte-offset field
+// (unused for swizzled K-major, canonical value 1).  High word: stride between 8-row atoms >> 4, descriptor
+// version 1 (Blackwell), swizzle mode.  A K=16 step advances the start address by 32 B (+2 in the low word).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3fffu) | (1u << 16); }
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // B tiles: 128 B rows, 128B swizzle
+constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);    // A tiles: 64 B rows, 64B swizzle
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
+    return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 // Instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M = 128.
 __device__ __forceinline__ uint32_t make_idesc_f16(int n) {
@@ -312,14 +334,17 @@ __device__ __forceinline__ void sincospi_reduced(float r, float* sn, float* cs) 
 // ------------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const FusedParams prm) {
+__global__ void __launch_bounds__(kThreads, 1)
+fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_constant__ CUtensorMap tm_in,
+                      const __grid_constant__ CUtensorMap tm_out) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-    const uint32_t aop_base = smem_base;                                    // [stage][pol][128 x 128 B]
-    const uint32_t bop_base = aop_base + kAopStages * kAopStageBytes;       // [buf][kb][part][nt x 128 B]
-    const uint32_t raw_base = bop_base + kBopBufs * kBopBufBytes;           // [stage][ant][t][4 B]
+    const uint32_t bop_base = smem_base;                                    // [buf][kb][part][nt x 128 B]
+    const uint32_t ost_base = bop_base + kBopBufs * kBopBufBytes;           // [warp][2][32 x 128 B]
+    const uint32_t aop_base = ost_base + kOutStageBytes;                    // [stage][pol][128 x 64 B]
+    const uint32_t raw_base = aop_base + kAopStages * kAopStageBytes;       // [stage][ant][t][4 B]
     const uint32_t bar_base = raw_base + kRawStages * kRawStageBytes;       // 8-byte mbarriers
     Control* ctl = reinterpret_cast<Control*>(smem_gen + kSmemData + 192);
 
@@ -357,11 +382,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
     }
     // B tiles start as zeros: padding rows (k >= 2A, n >= 2M) are never written afterwards.
     {
-        uint4* z = reinterpret_cast<uint4*>(smem_gen + kAopStages * kAopStageBytes);
+        uint4* z = reinterpret_cast<uint4*>(smem_gen);
         for (int i = threadIdx.x; i < kBopBufs * kBopBufBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async_smem();
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
+    if (warp == kProducerWarp && lane == 0) prefetch_tensormap(&tm_in);
+    if (warp == kEpilogueWarp0 && lane == 0) prefetch_tensormap(&tm_out);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -370,11 +397,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
     const int A = prm.A, C = prm.C, T = prm.T, M = prm.M, B = prm.B;
     const int N2 = 2 * M;
     const int nt = prm.nt, parts = prm.parts;
-    const uint32_t bop_kb_bytes = static_cast<uint32_t>(parts * nt * 128);  // one k-block: [part][nt rows][128 B]
+    const uint32_t part_bytes = static_cast<uint32_t>(nt * 128);            // one part of a k-block: [nt rows][128 B]
+    const uint32_t bop_kb_bytes = static_cast<uint32_t>(parts) * part_bytes;  // one k-block: [part][nt rows][128 B]
     // profiling: lane 0 of each role's first warp accounts blocked time per barrier class (slot) and role span
-    const bool prof_lane = lane == 0 && (warp == kProducerWarp || warp == kMmaWarp || warp == kEpilogueWarp0 || warp == kConvertWarp0 || warp == kCoeffWarp0);
+    const bool prof_lane = lane == 0 && (warp == kProducerWarp || warp == kMmaWarp || warp == kEpilogueWarp0 ||
+                                         warp == kConvertWarp0 || warp == kCoeffWarp0);
     const int ps = prof_lane ? 0 : -100;
-    const int my_role = warp == kProducerWarp ? kRoleProducer : warp == kMmaWarp ? kRoleMma : warp >= kEpilogueWarp0 ? kRoleEpilogue : warp >= kConvertWarp0 ? kRoleConvert : kRoleCoeff;
+    const int my_role = warp == kProducerWarp ? kRoleProducer : warp == kMmaWarp ? kRoleMma
+                        : warp >= kEpilogueWarp0 ? kRoleEpilogue : warp >= kConvertWarp0 ? kRoleConvert : kRoleCoeff;
     const unsigned long long role_t0 = prof_lane ? global_ns() : 0ull;
 
     if (warp == kProducerWarp) {
@@ -384,28 +414,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
         for (int c = blockIdx.x; c < C && ok; c += gridDim.x)
             for (int it = 0; it < prm.nt_count && ok; ++it)
                 for (int b = 0; b < B && ok; ++b)
-                    for (int h = 0; h < prm.ht_count && ok; ++h) {
-                        const int t0 = h * kTileT;
-                        const int rows = min(kTileT, T - t0);
-                        for (int kb = 0; kb < prm.kb_count; ++kb, ++slab) {
+                    for (int h = 0; h < prm.ht_count && ok; ++h)
+                        for (int s = 0; s < prm.slab_count; ++s, ++slab) {
                             const uint32_t rs = slab % kRawStages, ph = (slab / kRawStages) & 1u;
                             ok = mbar_wait(bar(kRawEmpty + rs), ph ^ 1u, ctl, prm.status, kRoleProducer, kRawEmpty + rs, ps + 0);
                             if (!ok) break;
-                            const int a0 = kb * kKbAnts;
-                            const int n_ants = min(kKbAnts, A - a0);
-                            if (lane == 0)
-                                mbar_arrive_expect_tx(bar(kRawFull + rs), static_cast<uint32_t>(n_ants * rows * 4));
-                            __syncwarp();
-                            if (lane < n_ants) {
-                                const size_t row = ((static_cast<size_t>(b) * A + (a0 + lane)) * C + c) * static_cast<size_t>(T) + t0;
-                                bulk_g2s(raw_base + rs * kRawStageBytes + lane * (kTileT * 4), prm.in + row * 4,
-                                         static_cast<uint32_t>(rows * 4), bar(kRawFull + rs));
+                            if (lane == 0) {
+                                mbar_arrive_expect_tx(bar(kRawFull + rs), kRawStageBytes);
+                                tma_load_4d(raw_base + rs * kRawStageBytes, &tm_in, bar(kRawFull + rs), h * kTileT, c,
+                                            s * kSlabAnts, b);
                             }
+                            __syncwarp();
                         }
-                    }
     } else if (warp == kMmaWarp) {
         // =================================== MMA issuer ===================================
         const uint32_t idesc = make_idesc_f16(nt);
+        const uint32_t a_lo0 = desc_lo(aop_base), b_lo0 = desc_lo(bop_base);
+        const uint32_t part_lo = part_bytes >> 4, kb_lo = bop_kb_bytes >> 4;
         uint32_t slab = 0, unit = 0, step = 0;
         bool ok = true;
         for (int c = blockIdx.x; c < C && ok; c += gridDim.x)
@@ -417,23 +442,31 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                     ok = mbar_wait(bar(kAccEmpty + ab), ((unit / kAccBufs) & 1u) ^ 1u, ctl, prm.status, kRoleMma, kAccEmpty + ab, ps + 1);
                     if (!ok) break;
                     tc_fence_after();
-                    for (int kb = 0; kb < prm.kb_count; ++kb, ++slab) {
+                    const uint32_t d_tmem0 = tmem_base + ab * kPols * static_cast<uint32_t>(nt);
+                    for (int s = 0; s < prm.slab_count; ++s, ++slab) {
                         const uint32_t as = slab % kAopStages;
                         ok = mbar_wait(bar(kAopFull + as), (slab / kAopStages) & 1u, ctl, prm.status, kRoleMma, kAopFull + as, ps + 2);
                         if (!ok) break;
                         tc_fence_after();
                         if (lane == 0) {
-                            const int n_ants = min(kKbAnts, A - kb * kKbAnts);
-                            const int k16_steps = (n_ants + 7) >> 3;  // 8 antennas = 16 k per MMA
+                            const int n_ants = min(kSlabAnts, A - s * kSlabAnts);
+                            const int k_steps = (n_ants + 7) >> 3;  // 8 antennas = 16 k per MMA
+                            const uint32_t a_lo = a_lo0 + as * (kAopStageBytes >> 4);
+                            // B: k-block s/2, 64-byte half s%2 of its 128-byte rows
+                            const uint32_t b_lo = b_lo0 + bb * (kBopBufBytes >> 4) + static_cast<uint32_t>(s >> 1) * kb_lo + static_cast<uint32_t>(s & 1) * 4u;
+#pragma unroll
                             for (int p = 0; p < kPols; ++p) {
-                                const uint32_t d_tmem = tmem_base + (ab * kPols + p) * static_cast<uint32_t>(nt);
-                                const uint64_t a_desc = make_kmajor_sw128_desc(aop_base + as * kAopStageBytes + p * kAopTileBytes);
-                                for (int part = 0; part < parts; ++part) {
-                                    const uint64_t b_desc = make_kmajor_sw128_desc(
-                                        bop_base + bb * kBopBufBytes + kb * bop_kb_bytes + part * (nt * 128));
-                                    for (int k = 0; k < k16_steps; ++k) {
-                                        // +32 B per K=16 step inside the 128-byte swizzle row (encoded >> 4)
-                                        umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | part | k) != 0);
+                                const uint32_t d_tmem = d_tmem0 + p * static_cast<uint32_t>(nt);
+#pragma unroll
+                                for (int part = 0; part < 2; ++part) {
+                                    if (part < parts) {
+#pragma unroll
+                                        for (int k = 0; k < 2; ++k) {
+                                            if (k < k_steps)
+                                                umma_f16(d_tmem, make_desc(a_lo + p * (kAopTileBytes >> 4) + 2u * k, kDescHiSw64),
+                                                         make_desc(b_lo + part * part_lo + 2u * k, kDescHiSw128), idesc,
+                                                         (s | part | k) != 0);
+                                        }
                                     }
                                 }
                             }
@@ -450,7 +483,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
     } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + 4) {
         // =================================== epilogue ===================================
         const int q = warp & 3;  // TMEM lane quarter this warp may read
-        uint32_t unit = 0;
+        const uint32_t ost = ost_base + static_cast<uint32_t>(q) * (2 * kOutBoxBytes);
+        uint32_t unit = 0, box = 0;
         bool ok = true;
         for (int c = blockIdx.x; c < C && ok; c += gridDim.x)
             for (int it = 0; it < prm.nt_count && ok; ++it) {
@@ -462,10 +496,34 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                         if (!ok) break;
                         tc_fence_after();
                         const int t0 = h * kTileT;
-                        for (int p = 0; p < kPols; ++p) {
-                            const uint32_t col0 = (ab * kPols + p) * static_cast<uint32_t>(nt);
-                            float* tile_out = prm.out + (((static_cast<size_t>(b) * kPols + p) * C + c) * static_cast<size_t>(T) + t0) * N2 + n0;
-                            if (!prm.rowwise_epilogue) {
+                        if (prm.tma_store) {
+                            const int row0 = t0 + 32 * q;  // this warp's 32 rows of the tile
+                            for (int p = 0; p < kPols; ++p) {
+                                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kPols + p) * static_cast<uint32_t>(nt);
+                                const int plane = (b * kPols + p) * C + c;
+                                for (int cb = 0; cb < nt && row0 < T && n0 + cb < N2; cb += 32, ++box) {
+                                    uint32_t r[32];
+                                    tmem_ld_32x32b_x32(taddr + cb, r);
+                                    const uint32_t sb = ost + (box & 1u) * kOutBoxBytes;
+                                    if (lane == 0) bulk_wait_group_read<1>();  // the store that last read this box is done
+                                    __syncwarp();
+                                    tmem_wait_ld();
+                                    const uint32_t dst = sb + lane * 128;
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j)
+                                        st_shared_v4(dst + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                                    fence_proxy_async_smem();
+                                    __syncwarp();
+                                    if (lane == 0) {
+                                        tma_store_3d(&tm_out, sb, n0 + cb, row0, plane);
+                                        bulk_commit_group();
+                                    }
+                                }
+                            }
+                        } else {
+                            for (int p = 0; p < kPols; ++p) {
+                                const uint32_t col0 = (ab * kPols + p) * static_cast<uint32_t>(nt);
+                                float* tile_out = prm.out + (((static_cast<size_t>(b) * kPols + p) * C + c) * static_cast<size_t>(T) + t0) * N2 + n0;
 #pragma unroll 1
                                 for (int half = 0; half < 2; ++half) {
                                     const int r_lo = 32 * q + 16 * half + (lane >> 2);
@@ -501,20 +559,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                                         }
                                     }
                                 }
-                            } else {
-                                const int row = 32 * q + lane;
-                                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + col0;
-                                float* rowp = tile_out + static_cast<size_t>(row) * N2;
-                                for (int cb = 0; cb < nt; cb += 16) {
-                                    uint32_t r[16];
-                                    tmem_ld_32x32b_x16(taddr + cb, r);
-                                    tmem_wait_ld();
-                                    if (t0 + row < T) {
-#pragma unroll
-                                        for (int j = 0; j < 16; j += 2)
-                                            if (n0 + cb + j < N2) st_global_v2(rowp + cb + j, r[j], r[j + 1]);
-                                    }
-                                }
                             }
                         }
                         tc_fence_before();
@@ -522,36 +566,36 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                         if (lane == 0) mbar_arrive(bar(kAccEmpty + ab));
                     }
             }
+        if (lane == 0) bulk_wait_group_all();  // staging memory and the stores themselves are done before exit
     } else if (warp >= kConvertWarp0 && warp < kConvertWarp0 + 4) {
         // =================================== convert ===================================
-        // thread = one sample row t; per 4-antenna chunk: 4 conflict-free LDS.32, 8 PRMT+HSUB2, 2 STS.128
+        // thread = one sample row t; per 4-antenna chunk: 4 conflict-free LDS.32, 8 PRMT + 8 HSUB2, 2 STS.128
+        // (quarter-warps write 8 distinct 16-byte chunks of the 64B-swizzled rows: conflict-free)
         const int t = threadIdx.x - kConvertWarp0 * 32;
         const uint32_t bias = prm.signed_in ? 0x64806480u : 0x64006400u;  // 1152 | 1024 as fp16 pairs
         const uint32_t flip = prm.signed_in ? 0x80808080u : 0u;
+        const uint32_t sw = static_cast<uint32_t>((t >> 1) & 3);
         uint32_t slab = 0;
         bool ok = true;
         for (int c = blockIdx.x; c < C && ok; c += gridDim.x)
             for (int it = 0; it < prm.nt_count && ok; ++it)
                 for (int bh = 0; bh < B * prm.ht_count && ok; ++bh)
-                    for (int kb = 0; kb < prm.kb_count; ++kb, ++slab) {
+                    for (int s = 0; s < prm.slab_count; ++s, ++slab) {
                         const uint32_t rs = slab % kRawStages, as = slab % kAopStages;
                         ok = mbar_wait(bar(kRawFull + rs), (slab / kRawStages) & 1u, ctl, prm.status, kRoleConvert, kRawFull + rs, ps + 0);
                         if (ok)
                             ok = mbar_wait(bar(kAopEmpty + as), ((slab / kAopStages) & 1u) ^ 1u, ctl, prm.status, kRoleConvert, kAopEmpty + as, ps + 1);
                         if (!ok) break;
-                        const int n_ants = min(kKbAnts, A - kb * kKbAnts);
-                        const int n_chunks = 2 * ((n_ants + 7) >> 3);  // 4-antenna chunks inside the padded K extent
+                        // antennas beyond A were zero-filled by the TMA box: byte 0 -> value 0 (u8), and
+                        // 0 ^ 0x80 - 128 -> 0 (i8), so the K padding of the operand needs no special case
                         const uint32_t src = raw_base + rs * kRawStageBytes + t * 4;
-                        const uint32_t dst0 = aop_base + as * kAopStageBytes + t * 128;
-                        for (int j = 0; j < n_chunks; ++j) {
+                        const uint32_t dst0 = aop_base + as * kAopStageBytes + t * 64;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
                             uint32_t w[4];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int a = 4 * j + i;
-                                w[i] = (a < n_ants) ? (ld_shared_u32(src + a * (kTileT * 4)) ^ flip) : flip;
-                            }
-                            const uint32_t off = static_cast<uint32_t>((j ^ (t & 7)) << 4);
-                            // padding antennas: byte 0 (u8) / 0x80^0x80 -> value 0 after the bias subtraction
+                            for (int i = 0; i < 4; ++i) w[i] = ld_shared_u32(src + (4 * j + i) * (kTileT * 4)) ^ flip;
+                            const uint32_t off = (static_cast<uint32_t>(j) ^ sw) << 4;
                             st_shared_v4(dst0 + off, bytes_to_half2(w[0], 0x4140u, bias), bytes_to_half2(w[1], 0x4140u, bias),
                                          bytes_to_half2(w[2], 0x4140u, bias), bytes_to_half2(w[3], 0x4140u, bias));
                             st_shared_v4(dst0 + kAopTileBytes + off, bytes_to_half2(w[0], 0x4342u, bias),
@@ -571,14 +615,47 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
         // with lane <-> consecutive entry, so every warp load is 512 contiguous bytes.  Each entry becomes four
         // 32-bit words (row 2m | row 2m+1) x (fp16 hi | fp16 lo residual); consecutive antennas are consecutive
         // words of one 128-byte B row, so each of the four STS.32 of a warp touches 32 different banks.
+        // The loads of the NEXT batch (possibly the next channel's) are issued before the current batch is
+        // evaluated, so HBM latency is covered by arithmetic rather than exposed once per batch.
         const int ctid = threadIdx.x - kCoeffWarp0 * 32;
         const int mt = nt >> 1;  // beams per N tile
         constexpr int kBatch = 8;
         constexpr int kStride = kCoeffWarps * 32;
         const int dm = kStride / A, da = kStride - dm * A;  // (beam, antenna) advance per kStride entries
         const int ml_first = ctid / A, a_first = ctid - ml_first * A;
-        const uint32_t part_bytes = static_cast<uint32_t>(nt * 128);
         const double kInvPi = 0.318309886183790671538;
+
+        // cursor of the batch whose loads are in flight
+        int nc = blockIdx.x, nit = 0, ne0 = ctid;
+        int n_entries = nc < C ? min(mt, M) * A : 0;
+        const float4* n_src = prm.dv + static_cast<size_t>(nc < C ? nc : 0) * M * A;
+        float2 nxt[kBatch];  // (delay_s, phase_rad); the two rate fields are ignored like the reference does
+        auto issue_loads = [&]() {
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int e = ne0 + u * kStride;
+                float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (nc < C && e < n_entries) t4 = ldg_nc_f4(n_src + e);
+                nxt[u] = make_float2(t4.x, t4.z);
+            }
+        };
+        auto advance_cursor = [&]() {
+            ne0 += kStride * kBatch;
+            if (ne0 - ctid >= n_entries) {  // next N tile, or next channel's first
+                ne0 = ctid;
+                if (++nit == prm.nt_count) {
+                    nit = 0;
+                    nc += gridDim.x;
+                }
+                if (nc < C) {
+                    const int m0 = nit * mt;
+                    n_entries = min(mt, M - m0) * A;
+                    n_src = prm.dv + (static_cast<size_t>(nc) * M + m0) * A;
+                }
+            }
+        };
+        issue_loads();
+
         uint32_t step = 0;
         bool ok = true;
         for (int c = blockIdx.x; c < C && ok; c += gridDim.x) {
@@ -588,19 +665,17 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 const uint32_t bb = step % kBopBufs;
                 const int m0 = it * mt;
                 const int entries = min(mt, M - m0) * A;
-                const float4* src = prm.dv + (static_cast<size_t>(c) * M + m0) * A;
-                // warm L2 for the step after this one (same channel next N tile, or next channel's first)
+                // warm L2 two steps ahead of the register prefetch
                 if (warp == kCoeffWarp0 && lane == 0) {
-                    int nc = c, nit = it + 1;
-                    if (nit == prm.nt_count) {
-                        nit = 0;
-                        nc = c + gridDim.x;
+                    int pc = c, pit = it + 1;
+                    if (pit == prm.nt_count) {
+                        pit = 0;
+                        pc = c + gridDim.x;
                     }
-                    if (nc < C) {
-                        const int nm0 = nit * mt;
-                        const int nm = min(mt, M - nm0);
-                        const size_t bytes = static_cast<size_t>(nm) * A * 16;
-                        const char* p = reinterpret_cast<const char*>(prm.dv + (static_cast<size_t>(nc) * M + nm0) * A);
+                    if (pc < C) {
+                        const int pm0 = pit * mt;
+                        const size_t bytes = static_cast<size_t>(min(mt, M - pm0)) * A * 16;
+                        const char* p = reinterpret_cast<const char*>(prm.dv + (static_cast<size_t>(pc) * M + pm0) * A);
                         for (size_t o = 0; o < bytes; o += 65536)
                             bulk_prefetch_l2(p + o, static_cast<uint32_t>(min(bytes - o, static_cast<size_t>(65536))));
                     }
@@ -608,16 +683,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_beamform_kernel(const Fused
                 bool waited = false;
                 const uint32_t buf = bop_base + bb * kBopBufBytes;
                 int ml = ml_first, a = a_first;
-                for (int e0 = ctid; e0 < entries + ctid; e0 += kStride * kBatch) {  // e0 - ctid is warp-uniform
-                    float2 v[kBatch];  // (delay_s, phase_rad); the two rate fields are ignored like the reference does
+                for (int e0 = ctid; e0 - ctid < entries; e0 += kStride * kBatch) {  // e0 - ctid is warp-uniform
+                    float2 v[kBatch];
 #pragma unroll
-                    for (int u = 0; u < kBatch; ++u) {
-                        const int e = e0 + u * kStride;
-                        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (e < entries) t4 = ldg_nc_f4(src + e);
-                        v[u] = make_float2(t4.x, t4.z);
-                    }
-                    if (!waited) {  // the loads above are already in flight while we wait for the buffer
+                    for (int u = 0; u < kBatch; ++u) v[u] = nxt[u];
+                    advance_cursor();
+                    issue_loads();
+                    if (!waited) {
                         ok = mbar_wait(bar(kBopEmpty + bb), ((step / kBopBufs) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + bb, ps + 0);
                         waited = true;
                         if (!ok) break;
@@ -684,15 +756,27 @@ unsigned long long* g_prof_dev = nullptr;  // set by fused_set_profile_buffer (d
 }  // namespace
 
 // Picks the N tiling: nt columns per tile (multiple of 16, <= 128) such that kb_count * parts * nt * 128 B <= 64 KiB.
+// With more than one N tile nt is a multiple of 32 when the budget allows, so that the 32-column TMA store boxes
+// never straddle two tiles.
 static void pick_n_tiling(int A, int M, int parts, int* kb_count, int* nt, int* nt_count) {
     const int kbc = (A + kKbAnts - 1) / kKbAnts;
     const int n_pad = ((2 * M + 15) / 16) * 16;
     int nt_max = (kBopBufBytes / (kbc * parts * 128)) & ~15;
     if (nt_max > 128) nt_max = 128;
-    const int count = nt_max > 0 ? (n_pad + nt_max - 1) / nt_max : 0;
     *kb_count = kbc;
-    *nt_count = count;
-    *nt = count > 0 ? ((((n_pad + count - 1) / count) + 15) / 16) * 16 : 0;
+    if (nt_max <= 0) {
+        *nt = 0;
+        *nt_count = 0;
+    } else if (n_pad <= nt_max) {
+        *nt = n_pad;
+        *nt_count = 1;
+    } else {
+        const int gran = (nt_max & ~31) >= 32 ? 32 : 16;
+        const int cap = gran == 32 ? (nt_max & ~31) : nt_max;
+        const int count = (n_pad + cap - 1) / cap;
+        *nt_count = count;
+        *nt = ((((n_pad + count - 1) / count) + gran - 1) / gran) * gran;
+    }
 }
 
 static int get_status_block(int** out) {
@@ -709,23 +793,74 @@ static int get_status_block(int** out) {
     return DCBF_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn* out) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        DCBF_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p) return record_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled lookup");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    *out = fn;
+    return DCBF_OK;
+}
+
 int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T,
                  int M, long long first_chan, double sample_period, unsigned flags, cudaStream_t s) {
     FusedParams p{};
-    p.in = samples;
     p.dv = reinterpret_cast<const float4*>(delay_vals);
     p.out = beams;
     p.B = B, p.A = A, p.C = C, p.T = T, p.M = M;
     p.parts = (flags & DCBF_FLAG_FP16_COEFF) ? 1 : 2;
     p.signed_in = (flags & DCBF_FLAG_SIGNED_INPUT) ? 1 : 0;
-    p.rowwise_epilogue = (flags & DCBF_FLAG_DEBUG_ROWWISE_EPILOGUE) ? 1 : 0;
     pick_n_tiling(A, M, p.parts, &p.kb_count, &p.nt, &p.nt_count);
     if (p.nt < 16) return DCBF_ERR_UNSUPPORTED;  // more than 128 k-blocks (4096 antennas)
+    p.slab_count = (A + kSlabAnts - 1) / kSlabAnts;
     p.ht_count = (T + kTileT - 1) / kTileT;
     p.chan_centre = static_cast<double>(first_chan) - static_cast<double>(N) / 2.0;
     p.turns_per_delay = -1.0 / (static_cast<double>(N) * sample_period);
+    // TMA stores need a 16-byte row pitch (even beam count) and 32-column boxes that stay inside their N tile
+    p.tma_store = !(flags & DCBF_FLAG_DEBUG_DIRECT_EPILOGUE) && (M % 2 == 0) && (p.nt_count == 1 || p.nt % 32 == 0);
+    if (static_cast<long long>(B) * kPols * C > 0x7fffffffLL) return DCBF_ERR_UNSUPPORTED;
     if (int e = get_status_block(&p.status)) return e;
     p.prof = g_prof_dev;
+
+    EncodeTiledFn encode = nullptr;
+    if (int e = get_encode_fn(&encode)) return e;
+    alignas(64) CUtensorMap tm_in, tm_out;
+    {
+        // samples as 4-byte words {p0.re, p0.im, p1.re, p1.im}: [B][A][C][T], box [1][16][1][128]
+        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(A),
+                                    static_cast<cuuint64_t>(B)};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(T) * 4, static_cast<cuuint64_t>(C) * T * 4,
+                                       static_cast<cuuint64_t>(A) * C * T * 4};
+        const cuuint32_t box[4] = {kTileT, 1, kSlabAnts, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult r = encode(&tm_in, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<uint8_t*>(samples), dims, strides, box,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return record_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(samples)");
+    }
+    if (p.tma_store) {
+        // beams as [B*2*C][T][2M] fp32, box [1][32][32], 128B swizzle
+        const cuuint64_t dims[3] = {static_cast<cuuint64_t>(2 * M), static_cast<cuuint64_t>(T),
+                                    static_cast<cuuint64_t>(B) * kPols * C};
+        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(2 * M) * 4, static_cast<cuuint64_t>(T) * 2 * M * 4};
+        const cuuint32_t box[3] = {32, 32, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = encode(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, beams, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return record_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(beams)");
+    } else {
+        tm_out = tm_in;  // never dereferenced
+    }
 
     static int n_sms[64] = {};
     int dev = 0;
@@ -735,7 +870,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
         DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     }
     const int grid = C < n_sms[dev] ? C : n_sms[dev];
-    fused_beamform_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
+    fused_beamform_kernel<<<grid, kThreads, kSmemBytes, s>>>(p, tm_in, tm_out);
     DCBF_CHECK_LAUNCH("fused_beamform_kernel");
     return DCBF_OK;
 }

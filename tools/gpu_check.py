@@ -86,7 +86,7 @@ if __name__ == "__main__":
     ]
     for c in cases:
         ok &= run_case(*c, tag="16x256b")
-    ok &= run_case(1, 64, 4, 256, 64, 4096, 0, flags=_capi.FLAG_DEBUG_ROWWISE_EPILOGUE, tag="rowwise")
+    ok &= run_case(1, 64, 4, 256, 64, 4096, 0, flags=_capi.FLAG_DEBUG_DIRECT_EPILOGUE, tag="direct")
     ok &= run_case(1, 64, 4, 256, 64, 4096, 0, flags=_capi.FLAG_FP16_COEFF, tag="fp16")
     ok &= run_case(1, 64, 4, 256, 64, 4096, 0, flags=_capi.FLAG_SIGNED_INPUT, tag="signed")
     ok &= run_case(1, 4, 8, 256, 4, 64, 0, uniform=True, tag="uniform")
