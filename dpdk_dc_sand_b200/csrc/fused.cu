@@ -30,6 +30,8 @@
 // 32 antennas (one 128-byte swizzle row), N tiles of <=128 columns chosen so that one B tile set (all k-blocks,
 // hi+lo) fits 64 KiB.  With more than one N tile the voltages of a channel are re-read (from L2).
 #include <cuda.h>
+
+#include <atomic>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -74,6 +76,7 @@ struct FusedParams {
     const float4* dv;
     float* out;
     int* status;  // [0]=error code, [1]=role, [2]=barrier id, [3]=blockIdx
+    int* sched;   // [0]=next channel counter (beyond the first gridDim.x), [1]=finished CTAs; self-resetting
     unsigned long long* prof;  // optional [grid][6 roles][4]: ns blocked per barrier class, [..][3] = role span
     int B, A, C, T, M;
     int slab_count;  // ceil(A / 16)
@@ -112,6 +115,17 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "r"(bar), "r"(parity)
         : "memory");
     return ok;
+}
+// True on exactly one lane of a converged warp.  ptxas knows the guarded region is single-threaded, so
+// warp-uniform operands of tcgen05 / TMA instructions go straight to uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
@@ -247,7 +261,22 @@ struct Control {
     uint32_t tmem_base;
     volatile int abort;
     unsigned long long wait_ns[6][4];  // [role][slot]: time lane 0 of a role's first warp spent blocked
+    volatile int chan_pub;             // number of entries of this CTA's channel sequence published so far
+    volatile int chan_ring[8];         // channel sequence, entry k at [k % 8]; kChanSentinel ends it
 };
+constexpr int kChanSentinel = 0x7fffffff;
+
+// k-th channel this CTA works on.  Channels are handed out dynamically (first one = blockIdx.x, the rest from
+// a global counter) by one lane of the coefficient role, which is the first to need them; everybody else
+// reads the sequence from shared memory.  Balances the finish times of the 148 persistent CTAs to within one
+// channel instead of the fixed 27-or-28 split, and absorbs per-SM speed differences.
+__device__ __forceinline__ int sched_get(Control* ctl, uint32_t k) {
+    while (ctl->chan_pub <= static_cast<int>(k)) {
+        if (ctl->abort) return kChanSentinel;
+        __nanosleep(32);
+    }
+    return ctl->chan_ring[k & 7];
+}
 
 __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Control* ctl, int* status, int role, int id) {
     const unsigned long long t0 = global_ns();
@@ -282,15 +311,36 @@ __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Contr
     }
 }
 // Warp-collective: every lane waits; the result is made warp-uniform.
-// `slot` >= 0 on exactly one lane of a role makes that lane account its blocked time (profiling aid; the
+// kProf builds only: `slot` >= 0 on exactly one lane of a role makes that lane account its blocked time (the
 // first try_wait may itself suspend the thread, so the whole call is timed).
+template <bool kProf>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, Control* ctl, int* status, int role, int id,
                                           int slot = -1) {
     unsigned long long t0 = 0;
-    if (slot >= 0) t0 = global_ns();
+    if (kProf && slot >= 0) t0 = global_ns();
     bool ok = mbar_try_wait(bar, parity) != 0;
     if (!ok) ok = mbar_wait_slow(bar, parity, ctl, status, role, id);
-    if (slot >= 0) ctl->wait_ns[role][slot] += global_ns() - t0;
+    if (kProf && slot >= 0) ctl->wait_ns[role][slot] += global_ns() - t0;
+    return __all_sync(0xffffffffu, ok);
+}
+// Two barriers at once: both probes are in flight together (a probe of an already-completed phase still
+// costs ~90 cycles), the slow path is only entered for the one that is really pending.
+template <bool kProf>
+__device__ __forceinline__ bool mbar_wait2(uint32_t bar_a, uint32_t parity_a, int id_a, uint32_t bar_b, uint32_t parity_b,
+                                           int id_b, Control* ctl, int* status, int role, int slot = -1) {
+    unsigned long long t0 = 0;
+    if (kProf && slot >= 0) t0 = global_ns();
+    const bool ok_a = mbar_try_wait(bar_a, parity_a) != 0;
+    const bool ok_b = mbar_try_wait(bar_b, parity_b) != 0;
+    bool ok = true;
+    if (!ok_a) ok = mbar_wait_slow(bar_a, parity_a, ctl, status, role, id_a);
+    if (kProf && slot >= 0) {
+        const unsigned long long t1 = global_ns();
+        ctl->wait_ns[role][slot] += t1 - t0;
+        t0 = t1;
+    }
+    if (ok && !ok_b) ok = mbar_wait_slow(bar_b, parity_b, ctl, status, role, id_b);
+    if (kProf && slot >= 0) ctl->wait_ns[role][slot + 1] += global_ns() - t0;
     return __all_sync(0xffffffffu, ok);
 }
 
@@ -307,18 +357,18 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// sin(pi r), cos(pi r) for r in [-1, 1] (half-turns, already range-reduced in float64).  Quadrant split
-// q = rint(2r), t = r - q/2 in [-1/4, 1/4], odd/even Taylor polynomials in t (truncation < 2e-9 and 2e-10),
-// then the quadrant rotation.  Absolute error <= ~1.2e-7; no special cases (r is always finite here).
-__device__ __forceinline__ void sincospi_reduced(float r, float* sn, float* cs) {
+// sin(pi (r + small)), cos(pi (r + small)) for |r| < 2^20 half-turns and a tiny correction `small`.  Quadrant
+// split q = rint(2r), t = r - q/2 (exact) + small in [-1/4, 1/4], odd/even Taylor polynomials in t (truncation
+// < 2e-9 and 2e-10), then the quadrant rotation.  Absolute error <= ~1e-7; no special cases (r is finite here).
+__device__ __forceinline__ void sincospi_reduced(float r, float small, float* sn, float* cs) {
     const float z = fmaf(r, 2.0f, 12582912.0f);  // 1.5 * 2^23: the low mantissa bits now hold rint(2r)
     const int q = __float_as_int(z);
-    const float t = fmaf(z - 12582912.0f, -0.5f, r);
+    const float t = fmaf(z - 12582912.0f, -0.5f, r) + small;
     const float s = t * t;
     float ps = fmaf(s, 0.0821458866f, -0.599264529f);   // pi^9/9!, -pi^7/7!
     ps = fmaf(ps, s, 2.55016404f);                       // pi^5/5!
     ps = fmaf(ps, s, -5.16771278f);                      // -pi^3/3!
-    ps = fmaf(ps * s, t, t * 3.14159274f) ;              // t*pi + t*s*(...)
+    ps = fmaf(ps * s, t, t * 3.14159274f);               // t*pi + t*s*(...)
     float pc = fmaf(s, -0.0258068914f, 0.235330630f);    // -pi^10/10!, pi^8/8!
     pc = fmaf(pc, s, -1.33526277f);                      // -pi^6/6!
     pc = fmaf(pc, s, 4.05871213f);                       // pi^4/4!
@@ -331,13 +381,53 @@ __device__ __forceinline__ void sincospi_reduced(float r, float* sn, float* cs) 
     *cs = __int_as_float(__float_as_int(b) ^ (((q + 1) << 30) & 0x80000000));
 }
 
+constexpr double kInvPi = 0.318309886183790671538;
+constexpr float kInvPiHi = static_cast<float>(kInvPi);
+constexpr float kInvPiLo = static_cast<float>(kInvPi - static_cast<double>(kInvPiHi));
+
+// Steering phase in half-turns, reduced mod 2:  rot/pi = delay * scale + phase/pi   with
+// scale = (ch - N/2) * (-1/(N Ts))   (reference: beamformer/unit_test/coeff_generator_cpu.py:143-165).
+// Evaluated to float64 accuracy WITHOUT float64 instructions: scale = s_hi + s_lo and 1/pi are split into float
+// pairs, products carry their exact FMA residuals, the big term is reduced mod 2 exactly, and the rounding of
+// the final sum is captured by a two-sum.  Result: r (|r| <= 2) plus a correction `small` for sincospi_reduced.
+// Delays beyond ~1e6 half-turns of phase (milliseconds; nothing physical) take the float64 path.
+__device__ __forceinline__ void steer_phase(float delay, float phase, float s_hi, float s_lo, double scale, float* r,
+                                            float* small) {
+    const float p = delay * s_hi;
+    const float u = phase * kInvPiHi;
+    if (fabsf(p) < 1048576.0f && fabsf(u) < 1048576.0f) {
+        float e = fmaf(delay, s_hi, -p);       // exact residual of p
+        e = fmaf(delay, s_lo, e);
+        e += fmaf(phase, kInvPiHi, -u);        // exact residual of u
+        e = fmaf(phase, kInvPiLo, e);
+        const float qf = fmaf(p, 0.5f, 12582912.0f) - 12582912.0f;  // rint(p / 2)
+        const float r0 = fmaf(qf, -2.0f, p);                         // p mod 2 in [-1, 1], exact
+        const float s1 = r0 + u;
+        const float bb = s1 - r0;
+        const float err = (r0 - (s1 - bb)) + (u - bb);               // rounding error of s1 (two-sum)
+        *r = s1;
+        *small = e + err;
+    } else {
+        const double x = fma(static_cast<double>(delay), scale, static_cast<double>(phase) * kInvPi);
+        const double xr = x - 2.0 * rint(0.5 * x);
+        *r = static_cast<float>(xr);
+        *small = static_cast<float>(xr - static_cast<double>(*r));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------------
+template <bool kProf>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_constant__ CUtensorMap tm_in,
                       const __grid_constant__ CUtensorMap tm_out) {
     extern __shared__ uint8_t smem_raw[];
+    const unsigned long long t_entry = kProf ? global_ns() : 0ull;
+    // Programmatic dependent launch: with DCBF_FLAG_STREAMING the NEXT fused launch on the stream may start
+    // filling SMs as soon as this launch's CTAs leave them (there is no griddepcontrol.wait anywhere: such
+    // launches promise to be independent).  Without the launch attribute this is a no-op.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
@@ -376,6 +466,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             mbar_init(bar(kAccEmpty + s), 4);
         }
         ctl->abort = 0;
+        ctl->chan_pub = 0;
         for (int i = 0; i < 24; ++i) ctl->wait_ns[i >> 2][i & 3] = 0;
         fence_mbar_init();
         (void)kNumBars;
@@ -400,26 +491,27 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     const uint32_t part_bytes = static_cast<uint32_t>(nt * 128);            // one part of a k-block: [nt rows][128 B]
     const uint32_t bop_kb_bytes = static_cast<uint32_t>(parts) * part_bytes;  // one k-block: [part][nt rows][128 B]
     // profiling: lane 0 of each role's first warp accounts blocked time per barrier class (slot) and role span
-    const bool prof_lane = lane == 0 && (warp == kProducerWarp || warp == kMmaWarp || warp == kEpilogueWarp0 ||
+    const bool prof_lane = kProf && lane == 0 && (warp == kProducerWarp || warp == kMmaWarp || warp == kEpilogueWarp0 ||
                                          warp == kConvertWarp0 || warp == kCoeffWarp0);
     const int ps = prof_lane ? 0 : -100;
     const int my_role = warp == kProducerWarp ? kRoleProducer : warp == kMmaWarp ? kRoleMma
                         : warp >= kEpilogueWarp0 ? kRoleEpilogue : warp >= kConvertWarp0 ? kRoleConvert : kRoleCoeff;
     const unsigned long long role_t0 = prof_lane ? global_ns() : 0ull;
+    const unsigned long long role_t0_cta = (kProf && threadIdx.x < 24) ? global_ns() : 0ull;
 
     if (warp == kProducerWarp) {
         // =================================== TMA producer ===================================
         uint32_t slab = 0;
         bool ok = true;
-        for (int c = blockIdx.x; c < C && ok; c += gridDim.x)
+        for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k)
             for (int it = 0; it < prm.nt_count && ok; ++it)
                 for (int b = 0; b < B && ok; ++b)
                     for (int h = 0; h < prm.ht_count && ok; ++h)
                         for (int s = 0; s < prm.slab_count; ++s, ++slab) {
                             const uint32_t rs = slab % kRawStages, ph = (slab / kRawStages) & 1u;
-                            ok = mbar_wait(bar(kRawEmpty + rs), ph ^ 1u, ctl, prm.status, kRoleProducer, kRawEmpty + rs, ps + 0);
+                            ok = mbar_wait<kProf>(bar(kRawEmpty + rs), ph ^ 1u, ctl, prm.status, kRoleProducer, kRawEmpty + rs, ps + 0);
                             if (!ok) break;
-                            if (lane == 0) {
+                            if (elect_one()) {
                                 mbar_arrive_expect_tx(bar(kRawFull + rs), kRawStageBytes);
                                 tma_load_4d(raw_base + rs * kRawStageBytes, &tm_in, bar(kRawFull + rs), h * kTileT, c,
                                             s * kSlabAnts, b);
@@ -433,27 +525,27 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         const uint32_t part_lo = part_bytes >> 4, kb_lo = bop_kb_bytes >> 4;
         uint32_t slab = 0, unit = 0, step = 0;
         bool ok = true;
-        for (int c = blockIdx.x; c < C && ok; c += gridDim.x)
+        for (uint32_t k = 0; ok && sched_get(ctl, k) < C; ++k)
             for (int it = 0; it < prm.nt_count && ok; ++it, ++step) {
                 const uint32_t bb = step % kBopBufs;
-                ok = mbar_wait(bar(kBopFull + bb), (step / kBopBufs) & 1u, ctl, prm.status, kRoleMma, kBopFull + bb, ps + 0);
+                ok = mbar_wait<kProf>(bar(kBopFull + bb), (step / kBopBufs) & 1u, ctl, prm.status, kRoleMma, kBopFull + bb, ps + 0);
                 for (int bh = 0; bh < B * prm.ht_count && ok; ++bh, ++unit) {
                     const uint32_t ab = unit % kAccBufs;
-                    ok = mbar_wait(bar(kAccEmpty + ab), ((unit / kAccBufs) & 1u) ^ 1u, ctl, prm.status, kRoleMma, kAccEmpty + ab, ps + 1);
+                    ok = mbar_wait<kProf>(bar(kAccEmpty + ab), ((unit / kAccBufs) & 1u) ^ 1u, ctl, prm.status, kRoleMma, kAccEmpty + ab, ps + 1);
                     if (!ok) break;
                     tc_fence_after();
                     const uint32_t d_tmem0 = tmem_base + ab * kPols * static_cast<uint32_t>(nt);
                     for (int s = 0; s < prm.slab_count; ++s, ++slab) {
                         const uint32_t as = slab % kAopStages;
-                        ok = mbar_wait(bar(kAopFull + as), (slab / kAopStages) & 1u, ctl, prm.status, kRoleMma, kAopFull + as, ps + 2);
+                        ok = mbar_wait<kProf>(bar(kAopFull + as), (slab / kAopStages) & 1u, ctl, prm.status, kRoleMma, kAopFull + as, ps + 2);
                         if (!ok) break;
                         tc_fence_after();
-                        if (lane == 0) {
-                            const int n_ants = min(kSlabAnts, A - s * kSlabAnts);
-                            const int k_steps = (n_ants + 7) >> 3;  // 8 antennas = 16 k per MMA
-                            const uint32_t a_lo = a_lo0 + as * (kAopStageBytes >> 4);
-                            // B: k-block s/2, 64-byte half s%2 of its 128-byte rows
-                            const uint32_t b_lo = b_lo0 + bb * (kBopBufBytes >> 4) + static_cast<uint32_t>(s >> 1) * kb_lo + static_cast<uint32_t>(s & 1) * 4u;
+                        const int n_ants = min(kSlabAnts, A - s * kSlabAnts);
+                        const int k_steps = (n_ants + 7) >> 3;  // 8 antennas = 16 k per MMA
+                        const uint32_t a_lo = a_lo0 + as * (kAopStageBytes >> 4);
+                        // B: k-block s/2, 64-byte half s%2 of its 128-byte rows
+                        const uint32_t b_lo = b_lo0 + bb * (kBopBufBytes >> 4) + static_cast<uint32_t>(s >> 1) * kb_lo + static_cast<uint32_t>(s & 1) * 4u;
+                        if (elect_one()) {
 #pragma unroll
                             for (int p = 0; p < kPols; ++p) {
                                 const uint32_t d_tmem = d_tmem0 + p * static_cast<uint32_t>(nt);
@@ -474,10 +566,10 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         }
                         __syncwarp();
                     }
-                    if (ok && lane == 0) umma_commit(bar(kAccFull + ab));
+                    if (ok && elect_one()) umma_commit(bar(kAccFull + ab));
                     __syncwarp();
                 }
-                if (ok && lane == 0) umma_commit(bar(kBopEmpty + bb));
+                if (ok && elect_one()) umma_commit(bar(kBopEmpty + bb));
                 __syncwarp();
             }
     } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + 4) {
@@ -486,13 +578,13 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         const uint32_t ost = ost_base + static_cast<uint32_t>(q) * (2 * kOutBoxBytes);
         uint32_t unit = 0, box = 0;
         bool ok = true;
-        for (int c = blockIdx.x; c < C && ok; c += gridDim.x)
+        for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k)
             for (int it = 0; it < prm.nt_count && ok; ++it) {
                 const int n0 = it * nt;
                 for (int b = 0; b < B && ok; ++b)
                     for (int h = 0; h < prm.ht_count && ok; ++h, ++unit) {
                         const uint32_t ab = unit % kAccBufs;
-                        ok = mbar_wait(bar(kAccFull + ab), (unit / kAccBufs) & 1u, ctl, prm.status, kRoleEpilogue, kAccFull + ab, ps + 0);
+                        ok = mbar_wait<kProf>(bar(kAccFull + ab), (unit / kAccBufs) & 1u, ctl, prm.status, kRoleEpilogue, kAccFull + ab, ps + 0);
                         if (!ok) break;
                         tc_fence_after();
                         const int t0 = h * kTileT;
@@ -505,7 +597,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                     uint32_t r[32];
                                     tmem_ld_32x32b_x32(taddr + cb, r);
                                     const uint32_t sb = ost + (box & 1u) * kOutBoxBytes;
-                                    if (lane == 0) bulk_wait_group_read<1>();  // the store that last read this box is done
+                                    bulk_wait_group_read<1>();  // (issuing lane) the store that last read this box is done
                                     __syncwarp();
                                     tmem_wait_ld();
                                     const uint32_t dst = sb + lane * 128;
@@ -514,7 +606,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                         st_shared_v4(dst + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                                     fence_proxy_async_smem();
                                     __syncwarp();
-                                    if (lane == 0) {
+                                    if (elect_one()) {
                                         tma_store_3d(&tm_out, sb, n0 + cb, row0, plane);
                                         bulk_commit_group();
                                     }
@@ -566,7 +658,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         if (lane == 0) mbar_arrive(bar(kAccEmpty + ab));
                     }
             }
-        if (lane == 0) bulk_wait_group_all();  // staging memory and the stores themselves are done before exit
+        bulk_wait_group_all();  // (issuing lane) staging memory and the stores themselves are done before exit
     } else if (warp >= kConvertWarp0 && warp < kConvertWarp0 + 4) {
         // =================================== convert ===================================
         // thread = one sample row t; per 4-antenna chunk: 4 conflict-free LDS.32, 8 PRMT + 8 HSUB2, 2 STS.128
@@ -577,14 +669,13 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         const uint32_t sw = static_cast<uint32_t>((t >> 1) & 3);
         uint32_t slab = 0;
         bool ok = true;
-        for (int c = blockIdx.x; c < C && ok; c += gridDim.x)
+        for (uint32_t k = 0; ok && sched_get(ctl, k) < C; ++k)
             for (int it = 0; it < prm.nt_count && ok; ++it)
                 for (int bh = 0; bh < B * prm.ht_count && ok; ++bh)
                     for (int s = 0; s < prm.slab_count; ++s, ++slab) {
                         const uint32_t rs = slab % kRawStages, as = slab % kAopStages;
-                        ok = mbar_wait(bar(kRawFull + rs), (slab / kRawStages) & 1u, ctl, prm.status, kRoleConvert, kRawFull + rs, ps + 0);
-                        if (ok)
-                            ok = mbar_wait(bar(kAopEmpty + as), ((slab / kAopStages) & 1u) ^ 1u, ctl, prm.status, kRoleConvert, kAopEmpty + as, ps + 1);
+                        ok = mbar_wait2<kProf>(bar(kRawFull + rs), (slab / kRawStages) & 1u, kRawFull + rs, bar(kAopEmpty + as),
+                                               ((slab / kAopStages) & 1u) ^ 1u, kAopEmpty + as, ctl, prm.status, kRoleConvert, ps + 0);
                         if (!ok) break;
                         // antennas beyond A were zero-filled by the TMA box: byte 0 -> value 0 (u8), and
                         // 0 ^ 0x80 - 128 -> 0 (i8), so the K padding of the operand needs no special case
@@ -623,10 +714,54 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         constexpr int kStride = kCoeffWarps * 32;
         const int dm = kStride / A, da = kStride - dm * A;  // (beam, antenna) advance per kStride entries
         const int ml_first = ctid / A, a_first = ctid - ml_first * A;
-        const double kInvPi = 0.318309886183790671538;
+        // common shape (A = 64, 32, ...): a thread keeps its antenna and moves 4k beams per step, so its B
+        // address only advances by a constant
+        const bool fast_addr = da == 0 && (dm & 3) == 0;
+
+        // channel scheduler (lane 0 of the first coefficient warp): keeps the sequence published one entry
+        // beyond the load cursor; the atomic is issued a batch before its result is stored so its latency
+        // is never waited for
+        const bool is_sched = warp == kCoeffWarp0 && lane == 0;
+        int sch_n = 0, sch_raw = 0;  // sch_raw: counter value still in flight (not touched until it is published)
+        bool sch_end = false, sch_pending = false;
+        auto warm_l2 = [&](int ch, int m0) {  // delay_vals of one (channel, N tile) step -> L2
+            const size_t bytes = static_cast<size_t>(min(mt, M - m0)) * A * 16;
+            const char* p = reinterpret_cast<const char*>(prm.dv + (static_cast<size_t>(ch) * M + m0) * A);
+            for (size_t o = 0; o < bytes; o += 65536)
+                bulk_prefetch_l2(p + o, static_cast<uint32_t>(min(bytes - o, static_cast<size_t>(65536))));
+        };
+        auto sch_publish = [&](int id) {
+            if (id >= C) {
+                id = kChanSentinel;
+                sch_end = true;
+            } else if (sch_n > 0) {
+                warm_l2(id, 0);  // about one channel before the register loads get there
+            }
+            ctl->chan_ring[sch_n & 7] = id;
+            __threadfence_block();
+            ctl->chan_pub = ++sch_n;
+        };
+        auto sch_request = [&]() {
+            if (!sch_end && !sch_pending) {
+                sch_raw = atomicAdd(prm.sched, 1);
+                sch_pending = true;
+            }
+        };
+        auto sch_flush = [&]() {
+            if (sch_pending) {
+                sch_publish(static_cast<int>(gridDim.x) + sch_raw);
+                sch_pending = false;
+            }
+        };
+        if (is_sched) {
+            sch_publish(static_cast<int>(blockIdx.x));
+            sch_request();
+        }
+        __syncwarp();
 
         // cursor of the batch whose loads are in flight
-        int nc = blockIdx.x, nit = 0, ne0 = ctid;
+        uint32_t nk = 0;
+        int nc = sched_get(ctl, 0), nit = 0, ne0 = ctid;
         int n_entries = nc < C ? min(mt, M) * A : 0;
         const float4* n_src = prm.dv + static_cast<size_t>(nc < C ? nc : 0) * M * A;
         float2 nxt[kBatch];  // (delay_s, phase_rad); the two rate fields are ignored like the reference does
@@ -640,17 +775,30 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             }
         };
         auto advance_cursor = [&]() {
+            if (is_sched) {  // publish what has come back, ask for the entry after the cursor's next channel
+                sch_flush();
+                if (sch_n <= static_cast<int>(nk) + 1) sch_request();
+            }
+            if (nc >= C) return;
             ne0 += kStride * kBatch;
-            if (ne0 - ctid >= n_entries) {  // next N tile, or next channel's first
+            if (ne0 - ctid >= n_entries) {  // next N tile, or the next channel's first
                 ne0 = ctid;
                 if (++nit == prm.nt_count) {
                     nit = 0;
-                    nc += gridDim.x;
+                    ++nk;
+                    if (is_sched && sch_n <= static_cast<int>(nk)) {  // not published yet: do it now (rare)
+                        sch_request();
+                        sch_flush();
+                    }
+                    __syncwarp();
+                    nc = sched_get(ctl, nk);
                 }
                 if (nc < C) {
                     const int m0 = nit * mt;
                     n_entries = min(mt, M - m0) * A;
                     n_src = prm.dv + (static_cast<size_t>(nc) * M + m0) * A;
+                    // the channel's first N tile was warmed when the channel was published; warm the next one
+                    if (is_sched && nit + 1 < prm.nt_count) warm_l2(nc, (nit + 1) * mt);
                 }
             }
         };
@@ -658,31 +806,41 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
 
         uint32_t step = 0;
         bool ok = true;
-        for (int c = blockIdx.x; c < C && ok; c += gridDim.x) {
-            const double chan = static_cast<double>(c) + prm.chan_centre;
-            const double scale = chan * prm.turns_per_delay;  // half-turns per second of delay
+        for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k) {
+            const double scale = (static_cast<double>(c) + prm.chan_centre) * prm.turns_per_delay;  // half-turns per second of delay
+            const float s_hi = static_cast<float>(scale), s_lo = static_cast<float>(scale - static_cast<double>(s_hi));
+            // one (beam, antenna) entry -> four 32-bit words of the B tile at d0 (row 2m) and d1 (row 2m+1)
+            auto emit = [&](float2 dv2, uint32_t d0) {
+                float r, small, sn, cs;
+                steer_phase(dv2.x, dv2.y, s_hi, s_lo, scale, &r, &small);
+                sincospi_reduced(r, small, &sn, &cs);
+                // fp16 hi + fp16 residual of (cos, sin)
+                const uint32_t hi = pack_half2(cs, sn);
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+                const uint32_t lo = pack_half2(cs - hf.x, sn - hf.y);
+                // B^T rows: n = 2m -> (k=2a: cos, k=2a+1: -sin);  n = 2m+1 -> (sin, cos)
+                const uint32_t d1 = (d0 + 128u) ^ 16u;  // row + 1: swizzle phase (row & 7) | 1
+                st_shared_u32(d0, hi ^ 0x80000000u);
+                st_shared_u32(d1, __byte_perm(hi, 0u, 0x1032u));
+                if (parts > 1) {
+                    st_shared_u32(d0 + part_bytes, lo ^ 0x80000000u);
+                    st_shared_u32(d1 + part_bytes, __byte_perm(lo, 0u, 0x1032u));
+                }
+            };
+            auto b_addr = [&](uint32_t buf, int ml, int a) {
+                const int row = 2 * ml, al = a & (kKbAnts - 1);
+                return buf + static_cast<uint32_t>(a >> 5) * bop_kb_bytes + static_cast<uint32_t>(row) * 128u +
+                       (static_cast<uint32_t>(((al >> 2) ^ (row & 7)) << 4) | static_cast<uint32_t>((al & 3) << 2));
+            };
             for (int it = 0; it < prm.nt_count && ok; ++it, ++step) {
                 const uint32_t bb = step % kBopBufs;
                 const int m0 = it * mt;
                 const int entries = min(mt, M - m0) * A;
-                // warm L2 two steps ahead of the register prefetch
-                if (warp == kCoeffWarp0 && lane == 0) {
-                    int pc = c, pit = it + 1;
-                    if (pit == prm.nt_count) {
-                        pit = 0;
-                        pc = c + gridDim.x;
-                    }
-                    if (pc < C) {
-                        const int pm0 = pit * mt;
-                        const size_t bytes = static_cast<size_t>(min(mt, M - pm0)) * A * 16;
-                        const char* p = reinterpret_cast<const char*>(prm.dv + (static_cast<size_t>(pc) * M + pm0) * A);
-                        for (size_t o = 0; o < bytes; o += 65536)
-                            bulk_prefetch_l2(p + o, static_cast<uint32_t>(min(bytes - o, static_cast<size_t>(65536))));
-                    }
-                }
                 bool waited = false;
                 const uint32_t buf = bop_base + bb * kBopBufBytes;
                 int ml = ml_first, a = a_first;
+                uint32_t d_fast = b_addr(buf, ml_first, a_first);
+                const uint32_t d_step = static_cast<uint32_t>(dm) * 256u;  // dm beams = 2 dm rows of 128 B
                 for (int e0 = ctid; e0 - ctid < entries; e0 += kStride * kBatch) {  // e0 - ctid is warp-uniform
                     float2 v[kBatch];
 #pragma unroll
@@ -690,47 +848,31 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     advance_cursor();
                     issue_loads();
                     if (!waited) {
-                        ok = mbar_wait(bar(kBopEmpty + bb), ((step / kBopBufs) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + bb, ps + 0);
+                        ok = mbar_wait<kProf>(bar(kBopEmpty + bb), ((step / kBopBufs) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + bb, ps + 0);
                         waited = true;
                         if (!ok) break;
                     }
+                    if (fast_addr) {
 #pragma unroll
-                    for (int u = 0; u < kBatch; ++u) {
-                        const int e = e0 + u * kStride;
-                        if (e < entries) {
-                            // rot/pi = delay * (ch - N/2) * (-1/(N Ts)) + phase/pi   (coeff_generator_cpu.py:143-165)
-                            const double x = fma(static_cast<double>(v[u].x), scale, static_cast<double>(v[u].y) * kInvPi);
-                            const float r = static_cast<float>(x - 2.0 * rint(0.5 * x));  // [-1, 1] half-turns
-                            float sn, cs;
-                            sincospi_reduced(r, &sn, &cs);
-                            // fp16 hi + fp16 residual of (cos, sin)
-                            const uint32_t hi = pack_half2(cs, sn);
-                            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-                            const uint32_t lo = pack_half2(cs - hf.x, sn - hf.y);
-                            // B^T rows: n = 2m -> (k=2a: cos, k=2a+1: -sin);  n = 2m+1 -> (sin, cos)
-                            const int row = 2 * ml;
-                            const int al = a & (kKbAnts - 1);
-                            const uint32_t d0 = buf + static_cast<uint32_t>(a >> 5) * bop_kb_bytes + static_cast<uint32_t>(row) * 128u +
-                                                (static_cast<uint32_t>(((al >> 2) ^ (row & 7)) << 4) | static_cast<uint32_t>((al & 3) << 2));
-                            const uint32_t d1 = (d0 + 128u) ^ 16u;  // row + 1: swizzle phase (row & 7) | 1
-                            st_shared_u32(d0, hi ^ 0x80000000u);
-                            st_shared_u32(d1, __byte_perm(hi, 0u, 0x1032u));
-                            if (parts > 1) {
-                                st_shared_u32(d0 + part_bytes, lo ^ 0x80000000u);
-                                st_shared_u32(d1 + part_bytes, __byte_perm(lo, 0u, 0x1032u));
+                        for (int u = 0; u < kBatch; ++u)
+                            if (e0 + u * kStride < entries) emit(v[u], d_fast + static_cast<uint32_t>(u) * d_step);
+                        d_fast += kBatch * d_step;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < kBatch; ++u) {
+                            if (e0 + u * kStride < entries) emit(v[u], b_addr(buf, ml, a));
+                            ml += dm;
+                            a += da;
+                            if (a >= A) {
+                                a -= A;
+                                ++ml;
                             }
-                        }
-                        ml += dm;
-                        a += da;
-                        if (a >= A) {
-                            a -= A;
-                            ++ml;
                         }
                     }
                 }
                 if (!ok) break;
                 if (!waited)  // this warp had no entries in this step; it still takes part in the hand-shake
-                    ok = mbar_wait(bar(kBopEmpty + bb), ((step / kBopBufs) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + bb, ps + 0);
+                    ok = mbar_wait<kProf>(bar(kBopEmpty + bb), ((step / kBopBufs) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + bb, ps + 0);
                 if (!ok) break;
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -743,14 +885,29 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     if (prof_lane) ctl->wait_ns[my_role][3] = global_ns() - role_t0;
     tc_fence_before();
     __syncthreads();
-    if (prm.prof && threadIdx.x < 24) prm.prof[blockIdx.x * 24 + threadIdx.x] = ctl->wait_ns[threadIdx.x >> 2][threadIdx.x & 3];
+    if (threadIdx.x == 0) {  // last CTA out re-arms the channel counter for the next launch that uses this slot
+        __threadfence();
+        if (atomicAdd(prm.sched + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+            atomicExch(prm.sched, 0);
+            atomicExch(prm.sched + 1, 0);
+        }
+    }
+    if (kProf && prm.prof && threadIdx.x < 24) {
+        unsigned long long v = ctl->wait_ns[threadIdx.x >> 2][threadIdx.x & 3];
+        // role index 0 is unused: absolute times of CTA entry, first role start (thread 0's view) and exit
+        if (threadIdx.x == 0) v = t_entry;
+        if (threadIdx.x == 1) v = role_t0_cta;
+        if (threadIdx.x == 2) v = global_ns();
+        prm.prof[blockIdx.x * 24 + threadIdx.x] = v;
+    }
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
-int* g_status_dev[64] = {};  // per-device 4-int status block, allocated on first use
+constexpr int kSchedSlots = 64;  // concurrent launches per device that can share the pool without interfering
+int* g_status_dev[64] = {};  // per-device: 4-int status block + kSchedSlots x {next, done} channel counters
 unsigned long long* g_prof_dev = nullptr;  // set by fused_set_profile_buffer (developer aid)
 
 }  // namespace
@@ -785,8 +942,8 @@ static int get_status_block(int** out) {
     if (dev < 0 || dev >= 64) return DCBF_ERR_UNSUPPORTED;
     if (!g_status_dev[dev]) {
         int* p = nullptr;
-        DCBF_CUDA_TRY(cudaMalloc(&p, 4 * sizeof(int)));
-        DCBF_CUDA_TRY(cudaMemset(p, 0, 4 * sizeof(int)));
+        DCBF_CUDA_TRY(cudaMalloc(&p, (4 + 2 * kSchedSlots) * sizeof(int)));
+        DCBF_CUDA_TRY(cudaMemset(p, 0, (4 + 2 * kSchedSlots) * sizeof(int)));
         g_status_dev[dev] = p;
     }
     *out = g_status_dev[dev];
@@ -829,6 +986,8 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     p.tma_store = !(flags & DCBF_FLAG_DEBUG_DIRECT_EPILOGUE) && (M % 2 == 0) && (p.nt_count == 1 || p.nt % 32 == 0);
     if (static_cast<long long>(B) * kPols * C > 0x7fffffffLL) return DCBF_ERR_UNSUPPORTED;
     if (int e = get_status_block(&p.status)) return e;
+    static std::atomic<unsigned> ticket{0};
+    p.sched = p.status + 4 + 2 * (ticket.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
     p.prof = g_prof_dev;
 
     EncodeTiledFn encode = nullptr;
@@ -867,10 +1026,24 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     DCBF_CUDA_TRY(cudaGetDevice(&dev));
     if (!n_sms[dev]) {
         DCBF_CUDA_TRY(cudaDeviceGetAttribute(&n_sms[dev], cudaDevAttrMultiProcessorCount, dev));
-        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     }
     const int grid = C < n_sms[dev] ? C : n_sms[dev];
-    fused_beamform_kernel<<<grid, kThreads, kSmemBytes, s>>>(p, tm_in, tm_out);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (flags & DCBF_FLAG_STREAMING) ? 1 : 0;
+    if (p.prof)
+        DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, fused_beamform_kernel<true>, p, tm_in, tm_out));
+    else
+        DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, fused_beamform_kernel<false>, p, tm_in, tm_out));
     DCBF_CHECK_LAUNCH("fused_beamform_kernel");
     return DCBF_OK;
 }
@@ -880,7 +1053,7 @@ int fused_status(int* role, int* barrier, int* block) {
     if (int e = get_status_block(&blk)) return e;
     int h[4] = {};
     DCBF_CUDA_TRY(cudaMemcpy(h, blk, sizeof(h), cudaMemcpyDeviceToHost));  // synchronises with prior work
-    if (h[0] != 0) DCBF_CUDA_TRY(cudaMemset(blk, 0, sizeof(h)));
+    if (h[0] != 0) DCBF_CUDA_TRY(cudaMemset(blk, 0, (4 + 2 * kSchedSlots) * sizeof(int)));  // also re-arms the counters
     if (role) *role = h[1];
     if (barrier) *barrier = h[2];
     if (block) *block = h[3];

@@ -60,6 +60,11 @@ typedef enum dcbf_status {
 #define DCBF_FLAG_SIGNED_INPUT 0x1u /* bytes are int8 (F-engine native); default: uint8 like the reference API */
 #define DCBF_FLAG_FP16_COEFF 0x2u   /* dcbf_fused: round the steering coefficients once to fp16 (error <= 2^-12 per
                                        component) instead of the default fp16 hi+lo pair (~2^-24); halves tensor work */
+#define DCBF_FLAG_STREAMING 0x4u    /* dcbf_fused: this call is independent of the kernel queued just before it on the
+                                       stream (it reads nothing that kernel writes and writes nothing that kernel
+                                       reads or writes, e.g. consecutive heaps into alternating output buffers), so its
+                                       CTAs may start on SMs that kernel has already left (programmatic dependent
+                                       launch).  Copies and events keep their normal stream ordering. */
 #define DCBF_FLAG_DEBUG_DIRECT_EPILOGUE 0x100u /* dcbf_fused: st.global from registers instead of TMA stores (cross-check) */
 
 int dcbf_version(void);

@@ -239,6 +239,26 @@ def test_fused_random_delays(dropin, case):
         assert np.all(err <= 2.0 ** -18 * _budget(x, signed) * 2 ** 10 + 1e-3)
 
 
+@pytest.mark.parametrize("max_delay_samples", [1e5, 2e7], ids=["58us", "12ms_float64_path"])
+def test_fused_large_delays(dropin, max_delay_samples):
+    """Geometric-scale delays (tens of microseconds: ~1e4..1e5 half-turns of phase at the band edge) and an
+    absurd 12 ms that forces the kernel's float64 phase path: the float-pair phase arithmetic must still
+    agree with the float64 oracle to float32-grade accuracy."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m, n, xid = 1, 64, 6, 128, 8, 4096, 7  # band edge: channels 3584..3589 of 4096
+    x = orc.make_samples(b, a, c, t, seed=31)
+    dv = orc.make_delay_vals_random(c, m, a, seed=32, max_delay_samples=max_delay_samples)
+    out = torch.empty((b, 2, c, t // 16, 16, 2 * m), dtype=torch.float32, device="cuda")
+    _capi.fused(torch.from_numpy(x).cuda(), torch.from_numpy(dv).cuda(), out, b, a, c, n, t, m, xid, TS)
+    _capi.fused_status()
+    ref = orc.beamform_pipeline(x, dv, n, xid, TS)
+    err = np.abs(out.cpu().numpy().astype(np.float64) - ref)
+    assert np.all(err <= 2.0 ** -8 * _budget(x) + 1e-3), f"max err {err.max()}"  # 2^-18 * sum|x|
+
+
 def test_fused_matches_three_kernel_chain_and_materialises_intermediates(dropin):
     from beamforming.beamform_op_sequence import OpSequenceTemplate
 

@@ -37,6 +37,11 @@ def main():
     p = prof.cpu().numpy().reshape(n_sm, 6, 4).astype(np.float64) / 1e3  # us
     print(f"A={A} C={C} T={T} M={M} B={B} flags={flags:#x}: kernel {e0.elapsed_time(e1)*1e3:.1f} us; "
           f"per-role blocked time, mean over {n_sm} CTAs (us)")
+    t_in, t_role, t_out = p[:, 0, 0], p[:, 0, 1], p[:, 0, 2]
+    base = t_in.min()
+    print(f"  CTA entry skew {t_in.max() - base:6.1f} us | prologue (entry->roles) mean {(t_role - t_in).mean():5.1f} max "
+          f"{(t_role - t_in).max():5.1f} | last role start {t_role.max() - base:6.1f} | first exit {t_out.min() - base:6.1f} "
+          f"last exit {t_out.max() - base:6.1f} us after first entry")
     for r, name in ROLES.items():
         span = p[:, r, 3]
         parts = ", ".join(f"{SLOTS[r][k]}={p[:, r, k].mean():7.1f}" for k in range(3) if SLOTS[r][k] != "-")
