@@ -197,6 +197,7 @@ def run_ours(args, wl) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("DCBF_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     n_total = C * world
     flags = _capi.FLAG_FP16_COEFF if args.fp16_coeff else 0

@@ -35,10 +35,14 @@ SIGNATURES = {
     "dcbf_reorder": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dcbf_coeffs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.c_double, C.c_void_p]),
+    "dcbf_coeffs_tv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_double, C.POINTER(C.c_double), C.c_void_p]),
     "dcbf_beamform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_uint, C.c_void_p]),
     "dcbf_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                              C.c_int, C.c_double, C.c_uint, C.c_void_p]),
+    "dcbf_fused_tv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_int, C.c_double, C.POINTER(C.c_double), C.c_uint, C.c_void_p]),
     "dcbf_fused_status": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dcbf_debug_set_profile_buffer": (None, [C.c_void_p]),
     "dcbf_fused_tiling": (None, [C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -115,8 +119,19 @@ def reorder(samples, reordered, n_batches, n_ants, n_chans, n_samples, stream=No
                               _stream_handle(stream)), "dcbf_reorder")
 
 
+def _dt_array(batch_dt, n_batches):
+    if len(batch_dt) != n_batches:
+        raise ValueError("batch_dt needs one entry (seconds) per batch")
+    return (C.c_double * n_batches)(*[float(t) for t in batch_dt])
+
+
 def coeffs(delay_vals, out, n_batches, n_pols, n_chans, n_chans_total, n_ants, n_beams, xeng_id, sample_period,
-           stream=None) -> None:
+           stream=None, batch_dt=None) -> None:
+    if batch_dt is not None:
+        check(load().dcbf_coeffs_tv(_ptr(delay_vals), _ptr(out), n_batches, n_pols, n_chans, n_chans_total, n_ants,
+                                    n_beams, xeng_id, float(sample_period), _dt_array(batch_dt, n_batches),
+                                    _stream_handle(stream)), "dcbf_coeffs_tv")
+        return
     check(load().dcbf_coeffs(_ptr(delay_vals), _ptr(out), n_batches, n_pols, n_chans, n_chans_total, n_ants, n_beams,
                              xeng_id, float(sample_period), _stream_handle(stream)), "dcbf_coeffs")
 
@@ -127,7 +142,12 @@ def beamform(reordered, coeff, beams, n_batches, n_chans, n_samples, n_ants, n_b
 
 
 def fused(samples, delay_vals, beams, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id,
-          sample_period, flags=0, stream=None) -> None:
+          sample_period, flags=0, stream=None, batch_dt=None) -> None:
+    if batch_dt is not None:
+        check(load().dcbf_fused_tv(_ptr(samples), _ptr(delay_vals), _ptr(beams), n_batches, n_ants, n_chans,
+                                   n_chans_total, n_samples, n_beams, xeng_id, float(sample_period),
+                                   _dt_array(batch_dt, n_batches), flags, _stream_handle(stream)), "dcbf_fused_tv")
+        return
     check(load().dcbf_fused(_ptr(samples), _ptr(delay_vals), _ptr(beams), n_batches, n_ants, n_chans, n_chans_total,
                             n_samples, n_beams, xeng_id, float(sample_period), flags, _stream_handle(stream)),
           "dcbf_fused")

@@ -53,6 +53,7 @@ class OpSequence(accel.OperationSequence):
         signed_input: bytes are int8 instead of the reference API's uint8 (default False).
         fp16_coeff: single fp16 rounding of the coefficients instead of the fp16 hi+lo pair (default False).
         fused: False runs the three stand-alone kernels like the reference (default True).
+        batch_times: per-batch time offsets (s) for time-varying steering, see CoeffGenerator (default None).
     """
 
     def __init__(self, template: OpSequenceTemplate, queue) -> None:
@@ -78,6 +79,7 @@ class OpSequence(accel.OperationSequence):
         self.signed_input = False
         self.fp16_coeff = False
         self.fused = True
+        self.batch_times = None
 
     # -- binding policy ---------------------------------------------------------------------------
     def _needs(self, name: str) -> bool:
@@ -98,6 +100,7 @@ class OpSequence(accel.OperationSequence):
 
     # -- execution --------------------------------------------------------------------------------
     def _run(self) -> None:
+        self.beamform_coeff.batch_times = self.batch_times
         if not self.fused:
             self.beamform_mult.signed_input = self.signed_input
             super()._run()
@@ -108,6 +111,7 @@ class OpSequence(accel.OperationSequence):
             self.buffer("bufin_reorder").buffer, self.buffer("bufin_delay_vals").buffer,
             self.buffer("bufout_mult").buffer, r.n_batches, r.n_ants, r.n_channels_per_stream, c.n_channels,
             r.n_samples_per_channel, c.n_beams, c.xeng_id, c.sample_period, self.flags(), self.command_queue.stream,
+            batch_dt=self.batch_times,
         )
         if self.slots["bufint_data"].is_bound:
             self.prebeamform_reorder()

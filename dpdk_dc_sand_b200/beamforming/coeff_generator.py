@@ -56,11 +56,17 @@ class CoeffGenerator(Operation):
 
     delay_vals: (n_channels_per_stream, n_beams, n_ants, 4), float32 -- {delay_s, delay_rate, phase_rad, phase_rate}
     outCoeffs: (n_batches, n_pols, n_channels_per_stream, 2*n_ants, 2*n_beams), float32
+
+    ``batch_times`` (attribute, default None = the reference behaviour: rates ignored): one time offset in seconds
+    per batch, measured from the delay model's reference time; batch b is then steered with
+    ``delay + delay_rate*t_b`` and ``phase + phase_rate*t_b`` (the native precursor's time-varying form,
+    beamformer_coefficient_generator/BeamformerKernels.cu:25-35).
     """
 
     def __init__(self, template: CoeffGeneratorTemplate, command_queue) -> None:
         super().__init__(command_queue)
         self.template = template
+        self.batch_times = None
         self.slots["delay_vals"] = IOSlot(dimensions=template.delay_vals_data_dimensions, dtype=np.float32)
         self.slots["outCoeffs"] = IOSlot(dimensions=template.coeff_data_dimensions, dtype=np.float32)
 
@@ -68,4 +74,4 @@ class CoeffGenerator(Operation):
         t = self.template
         _capi.coeffs(self.buffer("delay_vals").buffer, self.buffer("outCoeffs").buffer, t.n_batches, t.n_pols,
                      t.n_channels_per_stream, t.n_channels, t.n_ants, t.n_beams, t.xeng_id, t.sample_period,
-                     self.command_queue.stream)
+                     self.command_queue.stream, batch_dt=self.batch_times)

@@ -82,7 +82,19 @@ int dcbf_coeffs(const float* delay_vals, float* coeffs, int B, int P, int C, int
         return DCBF_ERR_INVALID_ARG;
     if (!aligned16(delay_vals) || !aligned16(coeffs)) return DCBF_ERR_INVALID_ARG;
     if (int e = check_device()) return e;
-    return launch_coeffs(delay_vals, coeffs, B, P, C, N, A, M, xeng_id, sample_period,
+    return launch_coeffs(delay_vals, coeffs, B, P, C, N, A, M, xeng_id, sample_period, nullptr,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int dcbf_coeffs_tv(const float* delay_vals, float* coeffs, int B, int P, int C, int N, int A, int M, int xeng_id,
+                   double sample_period, const double* batch_dt_s, dcbf_stream_t stream) {
+    if (!delay_vals || !coeffs || !batch_dt_s || B <= 0 || P <= 0 || C <= 0 || N <= 0 || A <= 0 || M <= 0 ||
+        xeng_id < 0 || !(sample_period > 0.0))
+        return DCBF_ERR_INVALID_ARG;
+    if (!aligned16(delay_vals) || !aligned16(coeffs)) return DCBF_ERR_INVALID_ARG;
+    if (B > DCBF_MAX_TV_BATCHES) return DCBF_ERR_UNSUPPORTED;
+    if (int e = check_device()) return e;
+    return launch_coeffs(delay_vals, coeffs, B, P, C, N, A, M, xeng_id, sample_period, batch_dt_s,
                          static_cast<cudaStream_t>(stream));
 }
 
@@ -102,8 +114,21 @@ int dcbf_fused(const uint8_t* samples, const float* delay_vals, float* beams, in
         return DCBF_ERR_INVALID_ARG;
     if (!aligned16(samples) || !aligned16(delay_vals) || !aligned16(beams)) return DCBF_ERR_INVALID_ARG;
     if (int e = check_device()) return e;
-    return launch_fused(samples, delay_vals, beams, B, A, C, N, T, M, static_cast<long long>(C) * xeng_id, sample_period, flags,
-                        static_cast<cudaStream_t>(stream));
+    return launch_fused(samples, delay_vals, beams, B, A, C, N, T, M, static_cast<long long>(C) * xeng_id, sample_period,
+                        nullptr, flags, static_cast<cudaStream_t>(stream));
+}
+
+int dcbf_fused_tv(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T,
+                  int M, int xeng_id, double sample_period, const double* batch_dt_s, unsigned flags,
+                  dcbf_stream_t stream) {
+    if (!samples || !delay_vals || !beams || !batch_dt_s || B <= 0 || A <= 0 || C <= 0 || N <= 0 || M <= 0 ||
+        xeng_id < 0 || bad_t(T) || !(sample_period > 0.0))
+        return DCBF_ERR_INVALID_ARG;
+    if (!aligned16(samples) || !aligned16(delay_vals) || !aligned16(beams)) return DCBF_ERR_INVALID_ARG;
+    if (B > DCBF_MAX_TV_BATCHES) return DCBF_ERR_UNSUPPORTED;
+    if (int e = check_device()) return e;
+    return launch_fused(samples, delay_vals, beams, B, A, C, N, T, M, static_cast<long long>(C) * xeng_id, sample_period,
+                        batch_dt_s, flags, static_cast<cudaStream_t>(stream));
 }
 
 int dcbf_fused_status(int* role, int* barrier, int* block) {

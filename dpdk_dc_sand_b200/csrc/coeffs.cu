@@ -29,9 +29,17 @@ namespace {
 constexpr int kTile = 32;
 constexpr int kThreads = 256;
 
+// Per-batch time offsets of the time-varying form (dcbf_coeffs_tv): delay -> delay + delay_rate*dt,
+// phase -> phase + phase_rate*dt, after beamformer_coefficient_generator/BeamformerKernels.cu:25-35.
+struct BatchTimes {
+    int n;  // 0: static steering (the reference Python path ignores the rate fields)
+    double dt[DCBF_MAX_TV_BATCHES];
+};
+
 __global__ void __launch_bounds__(kThreads)
-coeffs_kernel(const float4* __restrict__ delay_vals, float* __restrict__ coeffs, int n_rep, int C, int A, int M,
-              int chan_offset, double half_n, double denom, int tiles_a, int tiles_m) {
+coeffs_kernel(const float4* __restrict__ delay_vals, float* __restrict__ coeffs, int n_batches, int n_pols, int C, int A,
+              int M, int chan_offset, double half_n, double denom, int tiles_a, int tiles_m,
+              const __grid_constant__ BatchTimes times) {
     __shared__ float2 cs[kTile][kTile + 1];  // [beam][ant] -> (cos, sin)
 
     const long long blk = blockIdx.x;
@@ -44,55 +52,71 @@ coeffs_kernel(const float4* __restrict__ delay_vals, float* __restrict__ coeffs,
     const double ch = static_cast<double>(c + chan_offset);
     const double neg_pi = -3.141592653589793;  // == -math.pi
 
-    // phase 1: lanes along ant
-    for (int mi = warp; mi < kTile; mi += kThreads / 32) {
-        const int m = m0 + mi, a = a0 + lane;
-        if (m < M && a < A) {
-            const float4 dv = __ldg(delay_vals + (static_cast<size_t>(c) * M + m) * A + a);
-            const double delay = static_cast<double>(dv.x);
-            const double phase = static_cast<double>(dv.z);
-            // ((delay*ch)*(-pi))/(N*Ts) + phase      coeff_generator_cpu.py:143-150
-            const double initial = __dadd_rn(__ddiv_rn(__dmul_rn(__dmul_rn(delay, ch), neg_pi), denom), phase);
-            // ((delay*(N/2))*(-pi))/(N*Ts)           coeff_generator_cpu.py:155-160
-            const double centre = __ddiv_rn(__dmul_rn(__dmul_rn(delay, half_n), neg_pi), denom);
-            const double rot = __dsub_rn(initial, centre);
-            double sn, cn;
-            sincos(rot, &sn, &cn);
-            cs[mi][lane] = make_float2(static_cast<float>(cn), static_cast<float>(sn));
-        }
-    }
-    __syncthreads();
-
-    // phase 2: lanes along beam; rows 2a (cos, sin) and 2a+1 (-sin, cos)
-    const int m = m0 + lane;
-    if (m >= M) return;
     const size_t row_len = 2 * static_cast<size_t>(M);
-    for (int ai = warp; ai < kTile; ai += kThreads / 32) {
-        const int a = a0 + ai;
-        if (a >= A) break;
-        const float2 v = cs[lane][ai];
-        const float2 r0 = make_float2(v.x, v.y);
-        const float2 r1 = make_float2(-v.y, v.x);
-        for (int rep = 0; rep < n_rep; ++rep) {
-            float* base = coeffs + ((static_cast<size_t>(rep) * C + c) * (2 * static_cast<size_t>(A)) + 2 * a) * row_len;
-            reinterpret_cast<float2*>(base)[m] = r0;
-            reinterpret_cast<float2*>(base + row_len)[m] = r1;
+    const int n_groups = times.n > 0 ? n_batches : 1;          // distinct coefficient sets
+    const int reps = times.n > 0 ? n_pols : n_batches * n_pols;  // (batch, pol) replicas per set
+    for (int g = 0; g < n_groups; ++g) {
+        // phase 1: lanes along ant
+        for (int mi = warp; mi < kTile; mi += kThreads / 32) {
+            const int m = m0 + mi, a = a0 + lane;
+            if (m < M && a < A) {
+                const float4 dv = __ldg(delay_vals + (static_cast<size_t>(c) * M + m) * A + a);
+                double delay = static_cast<double>(dv.x);
+                double phase = static_cast<double>(dv.z);
+                if (times.n > 0) {
+                    delay = __dadd_rn(delay, __dmul_rn(static_cast<double>(dv.y), times.dt[g]));
+                    phase = __dadd_rn(phase, __dmul_rn(static_cast<double>(dv.w), times.dt[g]));
+                }
+                // ((delay*ch)*(-pi))/(N*Ts) + phase      coeff_generator_cpu.py:143-150
+                const double initial = __dadd_rn(__ddiv_rn(__dmul_rn(__dmul_rn(delay, ch), neg_pi), denom), phase);
+                // ((delay*(N/2))*(-pi))/(N*Ts)           coeff_generator_cpu.py:155-160
+                const double centre = __ddiv_rn(__dmul_rn(__dmul_rn(delay, half_n), neg_pi), denom);
+                const double rot = __dsub_rn(initial, centre);
+                double sn, cn;
+                sincos(rot, &sn, &cn);
+                cs[mi][lane] = make_float2(static_cast<float>(cn), static_cast<float>(sn));
+            }
         }
+        __syncthreads();
+
+        // phase 2: lanes along beam; rows 2a (cos, sin) and 2a+1 (-sin, cos)
+        const int m = m0 + lane;
+        if (m < M) {
+            for (int ai = warp; ai < kTile; ai += kThreads / 32) {
+                const int a = a0 + ai;
+                if (a >= A) break;
+                const float2 v = cs[lane][ai];
+                const float2 r0 = make_float2(v.x, v.y);
+                const float2 r1 = make_float2(-v.y, v.x);
+                for (int rep = 0; rep < reps; ++rep) {
+                    float* base = coeffs + ((static_cast<size_t>(g * reps + rep) * C + c) * (2 * static_cast<size_t>(A)) + 2 * a) * row_len;
+                    reinterpret_cast<float2*>(base)[m] = r0;
+                    reinterpret_cast<float2*>(base + row_len)[m] = r1;
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
 }  // namespace
 
 int launch_coeffs(const float* delay_vals, float* coeffs, int B, int P, int C, int N, int A, int M, int xeng_id,
-                  double sample_period, cudaStream_t s) {
+                  double sample_period, const double* batch_dt_s, cudaStream_t s) {
+    BatchTimes times{};
+    if (batch_dt_s) {
+        if (B > DCBF_MAX_TV_BATCHES) return DCBF_ERR_UNSUPPORTED;
+        times.n = B;
+        for (int b = 0; b < B; ++b) times.dt[b] = batch_dt_s[b];
+    }
     const int tiles_a = (A + kTile - 1) / kTile, tiles_m = (M + kTile - 1) / kTile;
     const long long n_blocks = static_cast<long long>(C) * tiles_a * tiles_m;
     if (n_blocks > 0x7fffffffLL) return DCBF_ERR_UNSUPPORTED;
     const double denom = static_cast<double>(N) * sample_period;  // python: (n_channels * sample_period)
     const double half_n = static_cast<double>(N) / 2.0;           // python: (n_channels / 2)
     coeffs_kernel<<<static_cast<unsigned>(n_blocks), kThreads, 0, s>>>(
-        reinterpret_cast<const float4*>(delay_vals), coeffs, B * P, C, A, M, C * xeng_id, half_n, denom, tiles_a,
-        tiles_m);
+        reinterpret_cast<const float4*>(delay_vals), coeffs, B, P, C, A, M, C * xeng_id, half_n, denom, tiles_a, tiles_m,
+        times);
     DCBF_CHECK_LAUNCH("coeffs_kernel");
     return DCBF_OK;
 }

@@ -32,6 +32,7 @@
 #include <cuda.h>
 
 #include <atomic>
+#include <type_traits>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -87,6 +88,9 @@ struct FusedParams {
     int parts;       // 2 = fp16 hi+lo coefficients, 1 = fp16 hi only
     int signed_in;
     int tma_store;   // 1: epilogue through shared memory + TMA tensor stores; 0: st.global from registers
+    int sb_count;    // coefficient sets per (channel, N tile): 1, or B with time-varying steering
+    int ub;          // batches sharing one coefficient set: B, or 1 with time-varying steering
+    float dt_hi[DCBF_MAX_TV_BATCHES], dt_lo[DCBF_MAX_TV_BATCHES];  // per-batch time offset (s) as a float pair
     double chan_centre;      // absolute index of local channel 0, minus N/2
     double turns_per_delay;  // -1 / (N * Ts): half-turns of phase per (second of delay x channel offset)
 };
@@ -390,16 +394,20 @@ constexpr float kInvPiLo = static_cast<float>(kInvPi - static_cast<double>(kInvP
 // Evaluated to float64 accuracy WITHOUT float64 instructions: scale = s_hi + s_lo and 1/pi are split into float
 // pairs, products carry their exact FMA residuals, the big term is reduced mod 2 exactly, and the rounding of
 // the final sum is captured by a two-sum.  Result: r (|r| <= 2) plus a correction `small` for sincospi_reduced.
+// With kPair the delay and the phase are float pairs themselves (time-varying steering).
 // Delays beyond ~1e6 half-turns of phase (milliseconds; nothing physical) take the float64 path.
-__device__ __forceinline__ void steer_phase(float delay, float phase, float s_hi, float s_lo, double scale, float* r,
-                                            float* small) {
-    const float p = delay * s_hi;
-    const float u = phase * kInvPiHi;
+template <bool kPair>
+__device__ __forceinline__ void steer_phase(float d_hi, float d_lo, float ph_hi, float ph_lo, float s_hi, float s_lo,
+                                            double scale, float* r, float* small) {
+    const float p = d_hi * s_hi;
+    const float u = ph_hi * kInvPiHi;
     if (fabsf(p) < 1048576.0f && fabsf(u) < 1048576.0f) {
-        float e = fmaf(delay, s_hi, -p);       // exact residual of p
-        e = fmaf(delay, s_lo, e);
-        e += fmaf(phase, kInvPiHi, -u);        // exact residual of u
-        e = fmaf(phase, kInvPiLo, e);
+        float e = fmaf(d_hi, s_hi, -p);       // exact residual of p
+        e = fmaf(d_hi, s_lo, e);
+        if (kPair) e = fmaf(d_lo, s_hi, e);
+        e += fmaf(ph_hi, kInvPiHi, -u);       // exact residual of u
+        e = fmaf(ph_hi, kInvPiLo, e);
+        if (kPair) e = fmaf(ph_lo, kInvPiHi, e);
         const float qf = fmaf(p, 0.5f, 12582912.0f) - 12582912.0f;  // rint(p / 2)
         const float r0 = fmaf(qf, -2.0f, p);                         // p mod 2 in [-1, 1], exact
         const float s1 = r0 + u;
@@ -408,17 +416,31 @@ __device__ __forceinline__ void steer_phase(float delay, float phase, float s_hi
         *r = s1;
         *small = e + err;
     } else {
-        const double x = fma(static_cast<double>(delay), scale, static_cast<double>(phase) * kInvPi);
+        const double dd = kPair ? static_cast<double>(d_hi) + static_cast<double>(d_lo) : static_cast<double>(d_hi);
+        const double pp = kPair ? static_cast<double>(ph_hi) + static_cast<double>(ph_lo) : static_cast<double>(ph_hi);
+        const double x = fma(dd, scale, pp * kInvPi);
         const double xr = x - 2.0 * rint(0.5 * x);
         *r = static_cast<float>(xr);
         *small = static_cast<float>(xr - static_cast<double>(*r));
     }
 }
 
+// base + rate * dt as a float pair (dt = dt_hi + dt_lo): the model value at a heap's timestamp
+// (beamformer_coefficient_generator/BeamformerKernels.cu:28-35: fDeltaDelay, fDeltaPhase).
+__device__ __forceinline__ void advance_model(float base, float rate, float dt_hi, float dt_lo, float* hi, float* lo) {
+    const float w = rate * dt_hi;
+    float w_e = fmaf(rate, dt_hi, -w);
+    w_e = fmaf(rate, dt_lo, w_e);
+    const float sum = base + w;
+    const float bb = sum - base;
+    *hi = sum;
+    *lo = ((base - (sum - bb)) + (w - bb)) + w_e;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------------
-template <bool kProf>
+template <bool kProf, bool kTv>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_constant__ CUtensorMap tm_in,
                       const __grid_constant__ CUtensorMap tm_out) {
@@ -526,10 +548,10 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         uint32_t slab = 0, unit = 0, step = 0;
         bool ok = true;
         for (uint32_t k = 0; ok && sched_get(ctl, k) < C; ++k)
-            for (int it = 0; it < prm.nt_count && ok; ++it, ++step) {
+            for (int isb = 0; isb < prm.nt_count * prm.sb_count && ok; ++isb, ++step) {  // (N tile, coefficient set)
                 const uint32_t bb = step % kBopBufs;
                 ok = mbar_wait<kProf>(bar(kBopFull + bb), (step / kBopBufs) & 1u, ctl, prm.status, kRoleMma, kBopFull + bb, ps + 0);
-                for (int bh = 0; bh < B * prm.ht_count && ok; ++bh, ++unit) {
+                for (int bh = 0; bh < prm.ub * prm.ht_count && ok; ++bh, ++unit) {
                     const uint32_t ab = unit % kAccBufs;
                     ok = mbar_wait<kProf>(bar(kAccEmpty + ab), ((unit / kAccBufs) & 1u) ^ 1u, ctl, prm.status, kRoleMma, kAccEmpty + ab, ps + 1);
                     if (!ok) break;
@@ -708,15 +730,18 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         // words of one 128-byte B row, so each of the four STS.32 of a warp touches 32 different banks.
         // The loads of the NEXT batch (possibly the next channel's) are issued before the current batch is
         // evaluated, so HBM latency is covered by arithmetic rather than exposed once per batch.
+        // kTv (time-varying steering): one coefficient set per heap, all four delay_vals fields are used.
+        using Dv = typename std::conditional<kTv, float4, float2>::type;
+        constexpr int kBatch = kTv ? 4 : 8;
+        constexpr int kStride = kCoeffWarps * 32;
         const int ctid = threadIdx.x - kCoeffWarp0 * 32;
         const int mt = nt >> 1;  // beams per N tile
-        constexpr int kBatch = 8;
-        constexpr int kStride = kCoeffWarps * 32;
         const int dm = kStride / A, da = kStride - dm * A;  // (beam, antenna) advance per kStride entries
         const int ml_first = ctid / A, a_first = ctid - ml_first * A;
         // common shape (A = 64, 32, ...): a thread keeps its antenna and moves 4k beams per step, so its B
         // address only advances by a constant
         const bool fast_addr = da == 0 && (dm & 3) == 0;
+        const int sb_count = kTv ? prm.sb_count : 1;
 
         // channel scheduler (lane 0 of the first coefficient warp): keeps the sequence published one entry
         // beyond the load cursor; the atomic is issued a batch before its result is stored so its latency
@@ -759,19 +784,20 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         }
         __syncwarp();
 
-        // cursor of the batch whose loads are in flight
+        // cursor of the batch whose loads are in flight: (channel sequence index, N tile, coefficient set, entry)
         uint32_t nk = 0;
-        int nc = sched_get(ctl, 0), nit = 0, ne0 = ctid;
+        int nc = sched_get(ctl, 0), nit = 0, nsb = 0, ne0 = ctid;
         int n_entries = nc < C ? min(mt, M) * A : 0;
         const float4* n_src = prm.dv + static_cast<size_t>(nc < C ? nc : 0) * M * A;
-        float2 nxt[kBatch];  // (delay_s, phase_rad); the two rate fields are ignored like the reference does
+        Dv nxt[kBatch];  // static: (delay_s, phase_rad), the two rate fields are ignored like the reference does
         auto issue_loads = [&]() {
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
                 const int e = ne0 + u * kStride;
                 float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (nc < C && e < n_entries) t4 = ldg_nc_f4(n_src + e);
-                nxt[u] = make_float2(t4.x, t4.z);
+                if constexpr (kTv) nxt[u] = t4;
+                else nxt[u] = make_float2(t4.x, t4.z);
             }
         };
         auto advance_cursor = [&]() {
@@ -781,25 +807,26 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             }
             if (nc >= C) return;
             ne0 += kStride * kBatch;
-            if (ne0 - ctid >= n_entries) {  // next N tile, or the next channel's first
-                ne0 = ctid;
-                if (++nit == prm.nt_count) {
-                    nit = 0;
-                    ++nk;
-                    if (is_sched && sch_n <= static_cast<int>(nk)) {  // not published yet: do it now (rare)
-                        sch_request();
-                        sch_flush();
-                    }
-                    __syncwarp();
-                    nc = sched_get(ctl, nk);
+            if (ne0 - ctid < n_entries) return;
+            ne0 = ctid;
+            if (++nsb < sb_count) return;  // same delay_vals again for the next heap's coefficient set (L2 hits)
+            nsb = 0;
+            if (++nit == prm.nt_count) {  // the next channel's first N tile
+                nit = 0;
+                ++nk;
+                if (is_sched && sch_n <= static_cast<int>(nk)) {  // not published yet: do it now (rare)
+                    sch_request();
+                    sch_flush();
                 }
-                if (nc < C) {
-                    const int m0 = nit * mt;
-                    n_entries = min(mt, M - m0) * A;
-                    n_src = prm.dv + (static_cast<size_t>(nc) * M + m0) * A;
-                    // the channel's first N tile was warmed when the channel was published; warm the next one
-                    if (is_sched && nit + 1 < prm.nt_count) warm_l2(nc, (nit + 1) * mt);
-                }
+                __syncwarp();
+                nc = sched_get(ctl, nk);
+            }
+            if (nc < C) {
+                const int m0 = nit * mt;
+                n_entries = min(mt, M - m0) * A;
+                n_src = prm.dv + (static_cast<size_t>(nc) * M + m0) * A;
+                // the channel's first N tile was warmed when the channel was published; warm the next one
+                if (is_sched && nit + 1 < prm.nt_count) warm_l2(nc, (nit + 1) * mt);
             }
         };
         issue_loads();
@@ -809,10 +836,18 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k) {
             const double scale = (static_cast<double>(c) + prm.chan_centre) * prm.turns_per_delay;  // half-turns per second of delay
             const float s_hi = static_cast<float>(scale), s_lo = static_cast<float>(scale - static_cast<double>(s_hi));
+            float dt_hi = 0.f, dt_lo = 0.f;
             // one (beam, antenna) entry -> four 32-bit words of the B tile at d0 (row 2m) and d1 (row 2m+1)
-            auto emit = [&](float2 dv2, uint32_t d0) {
+            auto emit = [&](const Dv& dv, uint32_t d0) {
                 float r, small, sn, cs;
-                steer_phase(dv2.x, dv2.y, s_hi, s_lo, scale, &r, &small);
+                if constexpr (kTv) {
+                    float d_hi, d_lo, ph_hi, ph_lo;
+                    advance_model(dv.x, dv.y, dt_hi, dt_lo, &d_hi, &d_lo);
+                    advance_model(dv.z, dv.w, dt_hi, dt_lo, &ph_hi, &ph_lo);
+                    steer_phase<true>(d_hi, d_lo, ph_hi, ph_lo, s_hi, s_lo, scale, &r, &small);
+                } else {
+                    steer_phase<false>(dv.x, 0.f, dv.y, 0.f, s_hi, s_lo, scale, &r, &small);
+                }
                 sincospi_reduced(r, small, &sn, &cs);
                 // fp16 hi + fp16 residual of (cos, sin)
                 const uint32_t hi = pack_half2(cs, sn);
@@ -832,7 +867,12 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 return buf + static_cast<uint32_t>(a >> 5) * bop_kb_bytes + static_cast<uint32_t>(row) * 128u +
                        (static_cast<uint32_t>(((al >> 2) ^ (row & 7)) << 4) | static_cast<uint32_t>((al & 3) << 2));
             };
-            for (int it = 0; it < prm.nt_count && ok; ++it, ++step) {
+            for (int isb = 0; isb < prm.nt_count * sb_count && ok; ++isb, ++step) {
+                const int it = isb / sb_count, sb = isb - it * sb_count;
+                if constexpr (kTv) {
+                    dt_hi = prm.dt_hi[sb];
+                    dt_lo = prm.dt_lo[sb];
+                }
                 const uint32_t bb = step % kBopBufs;
                 const int m0 = it * mt;
                 const int entries = min(mt, M - m0) * A;
@@ -842,7 +882,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 uint32_t d_fast = b_addr(buf, ml_first, a_first);
                 const uint32_t d_step = static_cast<uint32_t>(dm) * 256u;  // dm beams = 2 dm rows of 128 B
                 for (int e0 = ctid; e0 - ctid < entries; e0 += kStride * kBatch) {  // e0 - ctid is warp-uniform
-                    float2 v[kBatch];
+                    Dv v[kBatch];
 #pragma unroll
                     for (int u = 0; u < kBatch; ++u) v[u] = nxt[u];
                     advance_cursor();
@@ -870,9 +910,6 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         }
                     }
                 }
-                if (!ok) break;
-                if (!waited)  // this warp had no entries in this step; it still takes part in the hand-shake
-                    ok = mbar_wait<kProf>(bar(kBopEmpty + bb), ((step / kBopBufs) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + bb, ps + 0);
                 if (!ok) break;
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -969,7 +1006,8 @@ static int get_encode_fn(EncodeTiledFn* out) {
 }
 
 int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T,
-                 int M, long long first_chan, double sample_period, unsigned flags, cudaStream_t s) {
+                 int M, long long first_chan, double sample_period, const double* batch_dt_s, unsigned flags,
+                 cudaStream_t s) {
     FusedParams p{};
     p.dv = reinterpret_cast<const float4*>(delay_vals);
     p.out = beams;
@@ -983,6 +1021,17 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     p.chan_centre = static_cast<double>(first_chan) - static_cast<double>(N) / 2.0;
     p.turns_per_delay = -1.0 / (static_cast<double>(N) * sample_period);
     // TMA stores need a 16-byte row pitch (even beam count) and 32-column boxes that stay inside their N tile
+    p.sb_count = 1;
+    p.ub = B;
+    if (batch_dt_s) {  // time-varying steering: one coefficient set per heap
+        if (B > DCBF_MAX_TV_BATCHES) return DCBF_ERR_UNSUPPORTED;
+        p.sb_count = B;
+        p.ub = 1;
+        for (int b = 0; b < B; ++b) {
+            p.dt_hi[b] = static_cast<float>(batch_dt_s[b]);
+            p.dt_lo[b] = static_cast<float>(batch_dt_s[b] - static_cast<double>(p.dt_hi[b]));
+        }
+    }
     p.tma_store = !(flags & DCBF_FLAG_DEBUG_DIRECT_EPILOGUE) && (M % 2 == 0) && (p.nt_count == 1 || p.nt % 32 == 0);
     if (static_cast<long long>(B) * kPols * C > 0x7fffffffLL) return DCBF_ERR_UNSUPPORTED;
     if (int e = get_status_block(&p.status)) return e;
@@ -1026,8 +1075,9 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     DCBF_CUDA_TRY(cudaGetDevice(&dev));
     if (!n_sms[dev]) {
         DCBF_CUDA_TRY(cudaDeviceGetAttribute(&n_sms[dev], cudaDevAttrMultiProcessorCount, dev));
-        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     }
     const int grid = C < n_sms[dev] ? C : n_sms[dev];
     cudaLaunchConfig_t cfg{};
@@ -1040,10 +1090,12 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (flags & DCBF_FLAG_STREAMING) ? 1 : 0;
-    if (p.prof)
-        DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, fused_beamform_kernel<true>, p, tm_in, tm_out));
+    if (batch_dt_s)
+        DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, fused_beamform_kernel<false, true>, p, tm_in, tm_out));
+    else if (p.prof)
+        DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, fused_beamform_kernel<true, false>, p, tm_in, tm_out));
     else
-        DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, fused_beamform_kernel<false>, p, tm_in, tm_out));
+        DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, fused_beamform_kernel<false, false>, p, tm_in, tm_out));
     DCBF_CHECK_LAUNCH("fused_beamform_kernel");
     return DCBF_OK;
 }

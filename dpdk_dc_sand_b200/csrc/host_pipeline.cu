@@ -71,7 +71,7 @@ static int run_plan(HostPlan* p, const uint8_t* h_samples, const float* h_dv, fl
                                       static_cast<size_t>(cc) * p->M * p->A * 16, cudaMemcpyHostToDevice, s.stream));
         const long long first_chan = static_cast<long long>(p->C) * p->xeng_id + c0;
         if (int e = launch_fused(s.samples, s.delay_vals, s.beams, p->B, p->A, cc, p->N, p->T, p->M, first_chan,
-                                 p->sample_period, p->flags, s.stream))
+                                 p->sample_period, nullptr, p->flags, s.stream))
             return e;
         DCBF_CUDA_TRY(cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(h_beams) + c0 * beam_chan, p->C * beam_chan, s.beams,
                                         cc * beam_chan, cc * beam_chan, static_cast<size_t>(p->B) * kPols,

@@ -83,6 +83,15 @@ int dcbf_coeffs(const float* delay_vals, float* coeffs, int n_batches, int n_pol
                 int n_chans_total, int n_ants, int n_beams, int xeng_id, double sample_period,
                 dcbf_stream_t stream);
 
+/* Stage 2, time-varying form (next-row feature; the reference Python path ignores the two rate fields, its native
+ * precursor beamformer_coefficient_generator/BeamformerKernels.cu:25-35 does not): the coefficients of batch b are
+ * evaluated with delay + delay_rate*dt and phase + phase_rate*dt, dt = batch_dt_s[b] seconds since the delay
+ * model's reference time (HOST array of n_batches doubles, read during the call; n_batches <= DCBF_MAX_TV_BATCHES). */
+#define DCBF_MAX_TV_BATCHES 64
+int dcbf_coeffs_tv(const float* delay_vals, float* coeffs, int n_batches, int n_pols, int n_chans,
+                   int n_chans_total, int n_ants, int n_beams, int xeng_id, double sample_period,
+                   const double* batch_dt_s, dcbf_stream_t stream);
+
 /* Stage 3.  out[b,p,c,t,n] = sum_j f32(reordered[b,p,c,t,j]) * coeffs[b,p,c,j,n], fp32 accumulate. */
 int dcbf_beamform(const uint8_t* reordered, const float* coeffs, float* beams, int n_batches, int n_chans,
                   int n_samples, int n_ants, int n_beams, unsigned flags, dcbf_stream_t stream);
@@ -93,6 +102,11 @@ int dcbf_beamform(const uint8_t* reordered, const float* coeffs, float* beams, i
 int dcbf_fused(const uint8_t* samples, const float* delay_vals, float* beams, int n_batches, int n_ants,
                int n_chans, int n_chans_total, int n_samples, int n_beams, int xeng_id, double sample_period,
                unsigned flags, dcbf_stream_t stream);
+
+/* dcbf_fused with time-varying steering: one coefficient set per batch (heap), see dcbf_coeffs_tv. */
+int dcbf_fused_tv(const uint8_t* samples, const float* delay_vals, float* beams, int n_batches, int n_ants,
+                  int n_chans, int n_chans_total, int n_samples, int n_beams, int xeng_id, double sample_period,
+                  const double* batch_dt_s, unsigned flags, dcbf_stream_t stream);
 
 /* Blocks until prior work on the current device is done, then returns the status the last dcbf_fused kernels
  * left behind: DCBF_OK, or DCBF_ERR_TIMEOUT if an in-kernel pipeline wait exceeded its 2 s guard (the kernel

@@ -66,16 +66,28 @@ def rotation(
     xeng_id: int,
     sample_period: float,
     f32_arith: bool = False,
+    dt: float = None,
 ) -> np.ndarray:
     """Rotation angle (radians) per (c, beam, ant).  coeff_generator_cpu.py:125-165.
 
     Operation order is kept identical to the reference expression so that the
     float64 result is bit-identical to the reference loop.
+
+    ``dt`` (seconds since the delay model's reference time; None = the reference Python path, which ignores
+    the rate fields) selects the time-varying form of the native precursor
+    (beamformer_coefficient_generator/BeamformerKernels.cu:25-35): delay -> delay + delay_rate*dt,
+    phase -> phase + phase_rate*dt, evaluated in float64.  (The precursor's ``fDelayN`` line adds the delay
+    RATE where the delay is evidently meant, :31; the intended formula is restated here.)
     """
     ft = np.float32 if f32_arith else np.float64
     delay_s = delay_vals[..., 0].astype(ft)  # (C, M, A)
     phase_rad = delay_vals[..., 2].astype(ft)
-    # delay_vals[..., 1] (delay rate) and [..., 3] (phase rate) are ignored by the reference.
+    # delay_vals[..., 1] (delay rate) and [..., 3] (phase rate) are ignored by the reference Python path.
+    if dt is not None:
+        if f32_arith:
+            raise ValueError("time-varying steering is defined in float64 only")
+        delay_s = delay_s + delay_vals[..., 1].astype(np.float64) * float(dt)
+        phase_rad = phase_rad + delay_vals[..., 3].astype(np.float64) * float(dt)
     ichannel = (np.arange(n_channels_per_stream) + n_channels_per_stream * xeng_id).astype(ft)
     ichannel = ichannel[:, None, None]
     if f32_arith:
@@ -104,14 +116,26 @@ def steering_coeffs(
     sample_period: float,
     f32_arith: bool = False,
     out_dtype=np.float32,
+    batch_dt=None,
+    _dt=None,
 ) -> np.ndarray:
     """(C, M, A, 4) f32 -> (B, P, C, 2A, 2M).  coeff_generator_cpu.py:120-186.
 
     Block for (ant a, beam m): rows 2a,2a+1 / cols 2m,2m+1 = [[cos, sin], [-sin, cos]].
+    ``batch_dt`` (n_batches seconds, see ``rotation``) makes the coefficients of each batch its own.
     """
     if delay_vals.shape != (n_channels_per_stream, n_beams, n_ants, 4):
         raise ValueError(f"delay_vals shape {delay_vals.shape} mismatch")
-    rot = rotation(delay_vals, n_channels_per_stream, n_channels, xeng_id, sample_period, f32_arith)
+    if batch_dt is not None:
+        if len(batch_dt) != n_batches:
+            raise ValueError("batch_dt needs one entry per batch")
+        per_batch = [
+            steering_coeffs(delay_vals, 1, n_pols, n_channels_per_stream, n_channels, n_ants, n_beams, xeng_id,
+                            sample_period, out_dtype=out_dtype, batch_dt=None, _dt=float(t))
+            for t in batch_dt
+        ]
+        return np.concatenate(per_batch, axis=0)
+    rot = rotation(delay_vals, n_channels_per_stream, n_channels, xeng_id, sample_period, f32_arith, dt=_dt)
     rot = rot.astype(np.float64)  # math.cos/math.sin take a C double
     cos = np.cos(rot).transpose(0, 2, 1)  # (C, A, M)
     sin = np.sin(rot).transpose(0, 2, 1)
@@ -212,13 +236,18 @@ def beamform_pipeline(
     sample_period: float,
     signed_input: bool = False,
     acc_dtype=np.float64,
+    batch_dt=None,
 ) -> np.ndarray:
     """(B,A,C,T,P,2) u8 + (C,M,A,4) f32 -> (B,P,C,T//16,16,2M) in ``acc_dtype``."""
     b, a, c, t, p, x = samples.shape
     m = delay_vals.shape[1]
     re = reorder(samples)
-    co = steering_coeffs(delay_vals, 1, 1, c, n_channels, a, m, xeng_id, sample_period, out_dtype=np.float64)
     d = _as_real(re, signed_input, acc_dtype)
+    if batch_dt is not None:
+        co = steering_coeffs(delay_vals, b, 1, c, n_channels, a, m, xeng_id, sample_period, out_dtype=np.float64,
+                             batch_dt=batch_dt)
+        return np.einsum("bpcksj,bcjn->bpcksn", d, co[:, 0].astype(acc_dtype), optimize=True)
+    co = steering_coeffs(delay_vals, 1, 1, c, n_channels, a, m, xeng_id, sample_period, out_dtype=np.float64)
     return np.einsum("bpcksj,cjn->bpcksn", d, co[0, 0].astype(acc_dtype), optimize=True)
 
 

@@ -259,6 +259,71 @@ def test_fused_large_delays(dropin, max_delay_samples):
     assert np.all(err <= 2.0 ** -8 * _budget(x) + 1e-3), f"max err {err.max()}"  # 2^-18 * sum|x|
 
 
+def test_host_reorder_helper_runs_on_the_gpu(dropin):
+    """``beamforming.reorder.reorder`` (reference: beamforming/reorder.py:46) keeps its signature but has no CPU
+    implementation here: it must go through the CUDA kernel and agree with the oracle bit for bit."""
+    from beamforming import reorder as host_reorder
+    from dpdk_dc_sand_b200 import _capi
+
+    x = orc.make_samples(2, 9, 5, 48, seed=77)
+    n0 = _capi.launch_count()
+    got = host_reorder.reorder(x, x.shape, (2, 2, 5, 3, 16, 9, 2))
+    assert _capi.launch_count() == n0 + 1
+    np.testing.assert_array_equal(got, orc.reorder(x))
+    with pytest.raises(ValueError):
+        host_reorder.reorder(x, x.shape, (2, 2, 5, 48, 1, 9, 2))
+
+
+def _tv_delay_vals(c, m, a, seed):
+    """Realistic rate magnitudes: delay rate +-2e-9 s/s, phase rate +-2 rad/s (random junk rates would swamp the phase)."""
+    rng = np.random.default_rng(seed)
+    dv = orc.make_delay_vals_random(c, m, a, seed=seed, max_delay_samples=2000.0)
+    dv[..., 1] = rng.uniform(-2e-9, 2e-9, dv.shape[:3]).astype(np.float32)
+    dv[..., 3] = rng.uniform(-2.0, 2.0, dv.shape[:3]).astype(np.float32)
+    return dv
+
+
+def test_time_varying_steering(dropin):
+    """Next-row feature: per-heap delay/phase rates.  Stand-alone coefficients <= 1e-6 of the float64
+    oracle, fused beams inside the budget at float32 grade, the fused and three-kernel paths agree, and
+    batch_times = 0 reproduces the static path bit for bit."""
+    from beamforming.beamform_op_sequence import OpSequenceTemplate
+
+    ctx, queue = dropin
+    b, a, c, t, m, n, xid = 3, 64, 5, 128, 6, 4096, 6
+    times = [0.0, 1.37, -7.25]
+    x = orc.make_samples(b, a, c, t, seed=41)
+    dv = _tv_delay_vals(c, m, a, seed=42)
+    ref = orc.beamform_pipeline(x, dv, n, xid, TS, batch_dt=times)
+    assert np.abs(ref[1] - orc.beamform_pipeline(x, dv, n, xid, TS)[1]).max() > 100.0  # the rates matter
+    outs = {}
+    for fused in (True, False):
+        op = OpSequenceTemplate(ctx, b, 2, c, n, t // 16, 16, a, m, xid, TS, t).instantiate(queue)
+        op.fused, op.materialize_intermediates, op.batch_times = fused, True, times
+        op.ensure_all_bound()
+        op.buffer("bufin_reorder").set(queue, x)
+        op.buffer("bufin_delay_vals").set(queue, dv)
+        op()
+        outs[fused] = op.buffer("bufout_mult").get(queue).astype(np.float64)
+        co = op.buffer("bufint_coeff").get(queue).astype(np.float64)
+        ref_co = orc.steering_coeffs(dv, b, 2, c, n, a, m, xid, TS, out_dtype=np.float64, batch_dt=times)
+        assert np.abs(co - ref_co).max() <= 1e-6
+    err = np.abs(outs[True] - ref)
+    assert np.all(err <= 2.0 ** -8 * _budget(x) + 1e-3), f"max err {err.max()}"
+    np.testing.assert_allclose(outs[True], outs[False], rtol=0, atol=float(_budget(x).max()) * 2.0 ** -6)
+    # dt = 0 for every heap == the static kernel, bit for bit
+    res = []
+    for bt in (None, [0.0] * b):
+        op = OpSequenceTemplate(ctx, b, 2, c, n, t // 16, 16, a, m, xid, TS, t).instantiate(queue)
+        op.batch_times = bt
+        op.ensure_all_bound()
+        op.buffer("bufin_reorder").set(queue, x)
+        op.buffer("bufin_delay_vals").set(queue, dv)
+        op()
+        res.append(op.buffer("bufout_mult").get(queue))
+    np.testing.assert_array_equal(res[0], res[1])
+
+
 def test_fused_matches_three_kernel_chain_and_materialises_intermediates(dropin):
     from beamforming.beamform_op_sequence import OpSequenceTemplate
 
