@@ -179,6 +179,49 @@ def run_reference(args, wl) -> None:
 # --------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------
+def measure_secondary(name, steps, dev, rank, world, peak):
+    """Kernel-only figure of another BASELINE config on this GPU (inputs resident in HBM; `sets` input/output
+    sets are rotated so that consecutive launches never find their data in the 126 MB L2)."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    desc, A, C, T, M, B = WORKLOADS[name]
+    alg = _capi.fused_bytes(B, A, C, T, M)
+    sets = max(2, -(-(4 * 126_000_000) // alg))  # >= 4 x L2 in flight
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(77 + rank)
+    xs = [torch.randint(0, 256, (B, A, C, T, 2, 2), dtype=torch.uint8, device=dev, generator=gen) for _ in range(sets)]
+    dvs = []
+    for _ in range(sets):
+        d = torch.zeros((C, M, A, 4), dtype=torch.float32, device=dev)
+        d[..., 0] = (torch.rand((C, M, A), device=dev, generator=gen) * 32 - 16) * SAMPLE_PERIOD
+        d[..., 2] = (torch.rand((C, M, A), device=dev, generator=gen) * 2 - 1) * 3.14159265
+        dvs.append(d)
+    outs = [torch.empty((B, 2, C, T // 16, 16, 2 * M), dtype=torch.float32, device=dev) for _ in range(sets)]
+    stream = torch.cuda.Stream()
+
+    def run(n, flags):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for i in range(n):
+                j = i % sets
+                _capi.fused(xs[j], dvs[j], outs[j], B, A, C, C * world, T, M, rank, SAMPLE_PERIOD, flags, stream)
+            e1.record(stream)
+        stream.synchronize()
+        return e0.elapsed_time(e1) / 1e3 / n
+
+    run(2 * sets, 0)
+    sec = run(steps, 0)
+    sec_stream = run(steps, _capi.FLAG_STREAMING)
+    _capi.fused_status()
+    return {"workload": f"{name}: {desc}", "ms_per_step": sec * 1e3, "input_GBps": xs[0].numel() / sec / 1e9,
+            "beam_gsamples_per_s": B * 2 * C * T * M / sec / 1e9, "algorithmic_bytes_per_launch": alg,
+            "roofline_frac": alg / sec / 1e9 / peak, "streaming_ms_per_step": sec_stream * 1e3,
+            "streaming_roofline_frac": alg / sec_stream / 1e9 / peak, "l2": f"{sets} rotating input/output sets"}
+
+
 def run_ours(args, wl) -> None:
     import torch
     import torch.distributed as dist
@@ -327,6 +370,11 @@ def run_ours(args, wl) -> None:
         return
 
     peak, peak_src = _peaks()
+    secondary = None
+    if world == 1 and not args.no_secondary and args.workload == "c3":
+        del samples, dv, beams
+        torch.cuda.empty_cache()
+        secondary = {"c2": measure_secondary("c2", max(args.steps, 40), dev, rank, world, peak)}
     mean_launch_s = statistics.mean(per_launch_ms) / 1e3
     achieved = alg_bytes / mean_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -355,7 +403,11 @@ def run_ours(args, wl) -> None:
         "beam_gsamples_per_s": world * B * 2 * C * T * M / sec_per_step / 1e9,
         "algorithmic_GBps": world * alg_bytes / sec_per_step / 1e9,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "streaming": streaming,
+        "streaming": streaming, "other_workloads": secondary,
+        "pcie": {"note": "e2e is bounded by the host link: pinned copies measured on this pool (tools/bench_standalone.py) "
+                         "reach 55.5 GB/s H2D, 57.3 GB/s D2H alone and 49.9 GB/s each way when both directions run "
+                         "at once; the e2e step moves h2d_bytes_per_step up and d2h_bytes_per_step down",
+                 "e2e_d2h_GBps": (e2e["d2h_bytes_per_step"] / (e2e["ms_per_step"] / 1e3) / 1e9) if e2e else None},
     }
     print(json.dumps(line))
     if world > 1:
@@ -372,6 +424,7 @@ def main() -> None:
     ap.add_argument("--fp16-coeff", action="store_true", help="single fp16 coefficient rounding (DCBF_FLAG_FP16_COEFF)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-streaming", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the extra c2 (BASELINE configs[1]) measurement")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
