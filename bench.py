@@ -331,6 +331,35 @@ def run_ours(args, wl) -> None:
                      "note": "DCBF_FLAG_STREAMING (programmatic dependent launch), 2 alternating output buffers"}
         del beams2
 
+    # ---- requantised int8 output (dcbf_fused_q8): the SURVEY 8f-2 extension, reported beside the headline ----
+    q8 = None
+    if not args.no_q8:
+        gains = torch.full((M,), 0.004, dtype=torch.float32, device=dev)
+        out8 = torch.empty(beams.shape, dtype=torch.int8, device=dev)
+        q8_bytes = _capi.fused_q8_bytes(B, A, C, T, M)
+        for _ in range(3):
+            _capi.fused_q8(samples, dv, gains, out8, B, A, C, n_total, T, M, rank, SAMPLE_PERIOD, flags, stream)
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            q0.record(stream)
+            for _ in range(args.steps):
+                _capi.fused_q8(samples, dv, gains, out8, B, A, C, n_total, T, M, rank, SAMPLE_PERIOD, flags, stream)
+            q1.record(stream)
+        stream.synchronize()
+        barrier()
+        _capi.fused_status()
+        q_ms = q0.elapsed_time(q1)
+        if world > 1:
+            t = torch.tensor([q_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            q_ms = float(t.item())
+        q_sec = q_ms / 1e3 / args.steps
+        q8 = {"ms_per_step": q_sec * 1e3, "value": world * in_bytes / q_sec / 1e9, "unit": UNIT,
+              "algorithmic_bytes_per_launch": q8_bytes, "algorithmic_GBps_per_gpu": q8_bytes / q_sec / 1e9,
+              "note": "int8 beams = clip(rint(beam*gain)); output bytes / 4"}
+        del out8
+
     # ---- end to end through the host-buffer C-ABI call (pinned host arrays, H2D + kernel + D2H timed) ----
     e2e = None
     if not args.no_e2e:
@@ -362,6 +391,26 @@ def run_ours(args, wl) -> None:
                "h2d_bytes_per_step": int(in_bytes + dv.numel() * 4), "d2h_bytes_per_step": int(beams.numel() * 4),
                "ms_per_step": e2e_sec * 1e3, "steps": e2e_steps, "api": "dcbf_host_plan_run (pinned host arrays)",
                "matches_device_path": same}
+        if q8 is not None:
+            h_out8 = torch.empty(beams.shape, dtype=torch.int8, pin_memory=True)
+            n_out8 = h_out8.numpy()
+            plan = _capi.HostPlan(B, A, C, n_total, T, M, rank, SAMPLE_PERIOD, flags, chunk_chans=max(1, C // 16), n_slots=3)
+            plan.set_gains(gains.cpu().numpy())
+            for _ in range(2):
+                plan.run_q8(n_in, n_dv, n_out8)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                plan.run_q8(n_in, n_dv, n_out8)
+            q_e2e = (time.perf_counter() - t0) / e2e_steps
+            if world > 1:
+                t = torch.tensor([q_e2e], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                q_e2e = float(t.item())
+            plan.close()
+            q8["e2e"] = {"value": world * in_bytes / q_e2e / 1e9, "unit": UNIT, "ms_per_step": q_e2e * 1e3,
+                         "h2d_bytes_per_step": int(in_bytes + dv.numel() * 4), "d2h_bytes_per_step": int(beams.numel())}
+            del h_out8
         del h_in, h_dv, h_out
 
     if rank != 0:
@@ -377,6 +426,8 @@ def run_ours(args, wl) -> None:
         secondary = {"c2": measure_secondary("c2", max(args.steps, 40), dev, rank, world, peak)}
     mean_launch_s = statistics.mean(per_launch_ms) / 1e3
     achieved = alg_bytes / mean_launch_s / 1e9
+    if q8 is not None:
+        q8["roofline_frac"] = q8["algorithmic_GBps_per_gpu"] / peak
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": _traffic(args.workload), "kernel": "fused_beamform_kernel",
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_us_mean": mean_launch_s * 1e6,
@@ -403,7 +454,7 @@ def run_ours(args, wl) -> None:
         "beam_gsamples_per_s": world * B * 2 * C * T * M / sec_per_step / 1e9,
         "algorithmic_GBps": world * alg_bytes / sec_per_step / 1e9,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "streaming": streaming, "other_workloads": secondary,
+        "streaming": streaming, "q8_output": q8, "other_workloads": secondary,
         "pcie": {"note": "e2e is bounded by the host link: pinned copies measured on this pool (tools/bench_standalone.py) "
                          "reach 55.5 GB/s H2D, 57.3 GB/s D2H alone and 49.9 GB/s each way when both directions run "
                          "at once; the e2e step moves h2d_bytes_per_step up and d2h_bytes_per_step down",
@@ -424,6 +475,7 @@ def main() -> None:
     ap.add_argument("--fp16-coeff", action="store_true", help="single fp16 coefficient rounding (DCBF_FLAG_FP16_COEFF)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-streaming", action="store_true")
+    ap.add_argument("--no-q8", action="store_true", help="skip the int8-output extension measurement")
     ap.add_argument("--no-secondary", action="store_true", help="skip the extra c2 (BASELINE configs[1]) measurement")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

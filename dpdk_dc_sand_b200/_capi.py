@@ -43,6 +43,10 @@ SIGNATURES = {
                              C.c_int, C.c_double, C.c_uint, C.c_void_p]),
     "dcbf_fused_tv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_double, C.POINTER(C.c_double), C.c_uint, C.c_void_p]),
+    "dcbf_fused_q8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_uint,
+                                C.c_void_p]),
+    "dcbf_fused_q8_bytes": (C.c_ulonglong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dcbf_fused_status": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dcbf_debug_set_profile_buffer": (None, [C.c_void_p]),
     "dcbf_fused_tiling": (None, [C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -50,6 +54,8 @@ SIGNATURES = {
     "dcbf_host_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_double, C.c_uint, C.c_int, C.c_int]),
     "dcbf_host_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcbf_host_plan_set_gains": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dcbf_host_plan_run_q8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_ulonglong)]),
     "dcbf_host_plan_destroy": (C.c_int, [C.c_void_p]),
     "dcbf_launch_count": (C.c_ulonglong, []),
     "dcbf_fused_bytes": (C.c_ulonglong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -153,6 +159,20 @@ def fused(samples, delay_vals, beams, n_batches, n_ants, n_chans, n_chans_total,
           "dcbf_fused")
 
 
+def fused_q8(samples, delay_vals, gains, beams_q8, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams,
+             xeng_id, sample_period, flags=0, stream=None, batch_dt=None, saturated=None) -> None:
+    """Fused path with int8 requantised output; ``saturated`` is an optional 1-element int64 CUDA tensor (counter)."""
+    dt = _dt_array(batch_dt, n_batches) if batch_dt is not None else None
+    check(load().dcbf_fused_q8(_ptr(samples), _ptr(delay_vals), _ptr(gains), _ptr(beams_q8),
+                               _ptr(saturated) if saturated is not None else None, n_batches, n_ants, n_chans,
+                               n_chans_total, n_samples, n_beams, xeng_id, float(sample_period), dt, flags,
+                               _stream_handle(stream)), "dcbf_fused_q8")
+
+
+def fused_q8_bytes(n_batches, n_ants, n_chans, n_samples, n_beams) -> int:
+    return int(load().dcbf_fused_q8_bytes(n_batches, n_ants, n_chans, n_samples, n_beams))
+
+
 def fused_status() -> None:
     """Synchronise and raise if a fused kernel's pipeline watchdog fired."""
     role, barrier, block = C.c_int(0), C.c_int(0), C.c_int(0)
@@ -201,6 +221,29 @@ class HostPlan:
                                  f"{arr.dtype} {arr.shape}")
         check(load().dcbf_host_plan_run(self._h, samples.ctypes.data, delay_vals.ctypes.data, beams.ctypes.data),
               "dcbf_host_plan_run")
+
+    def set_gains(self, gains) -> None:
+        """Per-beam quantisation gains (float32 host array of n_beams) for ``run_q8``."""
+        import numpy as np
+
+        g = np.ascontiguousarray(gains, dtype=np.float32)
+        if g.shape != (self.shape_dv[1],):
+            raise ValueError("gains must have one entry per beam")
+        check(load().dcbf_host_plan_set_gains(self._h, g.ctypes.data), "dcbf_host_plan_set_gains")
+
+    def run_q8(self, samples, delay_vals, beams_q8) -> int:
+        """Like ``run`` with int8 requantised beams; returns the number of clipped values."""
+        import numpy as np
+
+        for arr, shape, dt in ((samples, self.shape_in, np.uint8), (delay_vals, self.shape_dv, np.float32),
+                               (beams_q8, self.shape_out, np.int8)):
+            if tuple(arr.shape) != shape or arr.dtype != dt or not arr.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"expected C-contiguous {np.dtype(dt).name} array of shape {shape}, got "
+                                 f"{arr.dtype} {arr.shape}")
+        sat = C.c_ulonglong(0)
+        check(load().dcbf_host_plan_run_q8(self._h, samples.ctypes.data, delay_vals.ctypes.data, beams_q8.ctypes.data,
+                                           C.byref(sat)), "dcbf_host_plan_run_q8")
+        return int(sat.value)
 
     def close(self) -> None:
         if self._h:

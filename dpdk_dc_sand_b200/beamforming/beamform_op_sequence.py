@@ -117,3 +117,65 @@ class OpSequence(accel.OperationSequence):
             self.prebeamform_reorder()
         if self.slots["bufint_coeff"].is_bound:
             self.beamform_coeff()
+
+
+class QuantisedOpSequenceTemplate(OpSequenceTemplate):
+    """Extension (not in the reference): the fused path with the beam post-stage -- per-beam gain, clip,
+    round to int8 -- folded into the kernel's epilogue (``dcbf_fused_q8``).  Same constructor as
+    ``OpSequenceTemplate``."""
+
+    def instantiate(self, queue) -> "QuantisedOpSequence":
+        return QuantisedOpSequence(self, queue)
+
+
+class QuantisedOpSequence(accel.Operation):
+    """.. rubric:: Slots
+
+    bufin_reorder: (n_batches, n_ants, n_channels_per_stream, n_samples_per_channel, n_pols, 2), uint8
+    bufin_delay_vals: (n_channels_per_stream, n_beams, n_ants, 4), float32
+    bufin_gains: (n_beams,), float32 -- quantisation gain per beam
+    bufout_q8: (n_batches, n_pols, n_channels_per_stream, n_blocks, n_samples_per_block, 2*n_beams), int8
+        = clip(rint(beam * gain), -127, 127)
+
+    Attributes: ``signed_input``, ``fp16_coeff``, ``batch_times`` as on ``OpSequence``; ``saturated`` holds the
+    number of clipped values of the last call once the queue has been synchronised.
+    """
+
+    def __init__(self, template: QuantisedOpSequenceTemplate, queue) -> None:
+        import numpy as np
+
+        super().__init__(queue)
+        self.template = template
+        r, c, m = (template.preBeamformReorder_template, template.beamform_coeff_template,
+                   template.beamform_mult_template)
+        dim = accel.Dimension
+        self.slots["bufin_reorder"] = accel.IOSlot(dimensions=r.inputDataShape, dtype=np.uint8)
+        self.slots["bufin_delay_vals"] = accel.IOSlot(dimensions=c.delay_vals_data_dimensions, dtype=np.float32)
+        self.slots["bufin_gains"] = accel.IOSlot(dimensions=(dim(c.n_beams, exact=True),), dtype=np.float32)
+        self.slots["bufout_q8"] = accel.IOSlot(dimensions=m.output_data_dimensions, dtype=np.int8)
+        self.signed_input = False
+        self.fp16_coeff = False
+        self.batch_times = None
+        self._saturated = None
+
+    @property
+    def saturated(self) -> int:
+        return 0 if self._saturated is None else int(self._saturated.item())
+
+    def _run(self) -> None:
+        import torch
+
+        r = self.template.preBeamformReorder_template
+        c = self.template.beamform_coeff_template
+        gains = self.buffer("bufin_gains").buffer
+        if self._saturated is None:
+            self._saturated = torch.zeros(1, dtype=torch.int64, device=gains.device)
+        with torch.cuda.stream(self.command_queue.stream):
+            self._saturated.zero_()
+        flags = (_capi.FLAG_SIGNED_INPUT if self.signed_input else 0) | (_capi.FLAG_FP16_COEFF if self.fp16_coeff else 0)
+        _capi.fused_q8(
+            self.buffer("bufin_reorder").buffer, self.buffer("bufin_delay_vals").buffer, gains,
+            self.buffer("bufout_q8").buffer, r.n_batches, r.n_ants, r.n_channels_per_stream, c.n_channels,
+            r.n_samples_per_channel, c.n_beams, c.xeng_id, c.sample_period, flags, self.command_queue.stream,
+            batch_dt=self.batch_times, saturated=self._saturated,
+        )

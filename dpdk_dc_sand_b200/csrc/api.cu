@@ -131,6 +131,27 @@ int dcbf_fused_tv(const uint8_t* samples, const float* delay_vals, float* beams,
                         batch_dt_s, flags, static_cast<cudaStream_t>(stream));
 }
 
+int dcbf_fused_q8(const uint8_t* samples, const float* delay_vals, const float* beam_gains, int8_t* beams_q8,
+                  unsigned long long* saturated, int B, int A, int C, int N, int T, int M, int xeng_id,
+                  double sample_period, const double* batch_dt_s, unsigned flags, dcbf_stream_t stream) {
+    if (!samples || !delay_vals || !beam_gains || !beams_q8 || B <= 0 || A <= 0 || C <= 0 || N <= 0 || M <= 0 ||
+        xeng_id < 0 || bad_t(T) || !(sample_period > 0.0))
+        return DCBF_ERR_INVALID_ARG;
+    if (!aligned16(samples) || !aligned16(delay_vals) || !aligned16(beams_q8)) return DCBF_ERR_INVALID_ARG;
+    if (batch_dt_s && B > DCBF_MAX_TV_BATCHES) return DCBF_ERR_UNSUPPORTED;
+    if (int e = check_device()) return e;
+    const QuantisedOut q8{beams_q8, beam_gains, saturated};
+    return launch_fused(samples, delay_vals, nullptr, B, A, C, N, T, M, static_cast<long long>(C) * xeng_id, sample_period,
+                        batch_dt_s, flags, static_cast<cudaStream_t>(stream), &q8);
+}
+
+unsigned long long dcbf_fused_q8_bytes(int B, int A, int C, int T, int M) {
+    const unsigned long long in = 1ull * B * A * C * T * kPols * 2;
+    const unsigned long long dv = 1ull * C * M * A * 16;
+    const unsigned long long out = 1ull * B * kPols * C * T * M * 2;
+    return in + dv + out + 4ull * M;
+}
+
 int dcbf_fused_status(int* role, int* barrier, int* block) {
     if (int e = check_device()) return e;
     return fused_status(role, barrier, block);

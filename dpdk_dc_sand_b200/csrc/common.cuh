@@ -38,10 +38,16 @@ int launch_coeffs(const float* delay_vals, float* coeffs, int B, int P, int C, i
                   double sample_period, const double* batch_dt_s, cudaStream_t s);
 int launch_beamform(const uint8_t* reordered, const float* coeffs, float* beams, int B, int C, int T, int A, int M,
                     unsigned flags, cudaStream_t s);
+// Requantised-output variant of the fused kernel (dcbf_fused_q8): int8 beams, per-beam gains, saturation counter.
+struct QuantisedOut {
+    int8_t* beams;
+    const float* gains;
+    unsigned long long* saturated;
+};
 // first_chan = absolute F-engine channel of local channel 0 (n_chans * xeng_id for a whole stream).
 int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T,
                  int M, long long first_chan, double sample_period, const double* batch_dt_s, unsigned flags,
-                 cudaStream_t s);
+                 cudaStream_t s, const QuantisedOut* q8 = nullptr);
 int fused_status(int* role, int* barrier, int* block);
 void fused_set_profile_buffer(unsigned long long* dev_ptr);
 void fused_tiling(int A, int M, unsigned flags, int* kb_count, int* nt, int* nt_count);

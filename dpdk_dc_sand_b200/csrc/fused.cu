@@ -68,7 +68,8 @@ constexpr int kTmemCols = 512;
 constexpr unsigned long long kWatchdogNs = 2000000000ull;  // 2 s without progress on one barrier = dead-lock
 
 constexpr int kSmemData = kAopStages * kAopStageBytes + kBopBufs * kBopBufBytes + kRawStages * kRawStageBytes + kOutStageBytes;
-constexpr int kSmemBytes = 1024 /*alignment slack*/ + kSmemData + 512 /*barriers + control*/;
+constexpr int kGainTabBytes = 64 * 8;  // q8: (gain, clip level) of the <= 64 beams of a single N tile
+constexpr int kSmemBytes = 1024 /*alignment slack*/ + kSmemData + 512 /*barriers + control*/ + kGainTabBytes;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 enum Role { kRoleProducer = 1, kRoleMma = 2, kRoleEpilogue = 3, kRoleConvert = 4, kRoleCoeff = 5 };
@@ -76,6 +77,9 @@ enum Role { kRoleProducer = 1, kRoleMma = 2, kRoleEpilogue = 3, kRoleConvert = 4
 struct FusedParams {
     const float4* dv;
     float* out;
+    int8_t* out_q8;                 // non-null: requantised int8 beams instead of float32 (dcbf_fused_q8)
+    const float* gains;             // [M] per-beam quantisation gain (q8 only)
+    unsigned long long* saturated;  // optional count of clipped values (q8 only)
     int* status;  // [0]=error code, [1]=role, [2]=barrier id, [3]=blockIdx
     int* sched;   // [0]=next channel counter (beyond the first gridDim.x), [1]=finished CTAs; self-resetting
     unsigned long long* prof;  // optional [grid][6 roles][4]: ns blocked per barrier class, [..][3] = role span
@@ -88,6 +92,7 @@ struct FusedParams {
     int parts;       // 2 = fp16 hi+lo coefficients, 1 = fp16 hi only
     int signed_in;
     int tma_store;   // 1: epilogue through shared memory + TMA tensor stores; 0: st.global from registers
+    int q8_wide;     // q8 only: the N tile is the whole output row (32 / 64 / 128 bytes): one box per 32 rows
     int sb_count;    // coefficient sets per (channel, N tile): 1, or B with time-varying steering
     int ub;          // batches sharing one coefficient set: B, or 1 with time-varying steering
     float dt_hi[DCBF_MAX_TV_BATCHES], dt_lo[DCBF_MAX_TV_BATCHES];  // per-batch time offset (s) as a float pair
@@ -229,6 +234,14 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 }
 __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
     uint32_t v;
@@ -437,10 +450,27 @@ __device__ __forceinline__ void advance_model(float base, float rate, float dt_h
     *lo = ((base - (sum - bb)) + (w - bb)) + w_e;
 }
 
+// Four float32 beam values -> four int8 in one word.  The value is clipped BEFORE scaling (to +-127/gain, so that
+// one FFMA then scales and rounds: adding 1.5*2^23 leaves the two's-complement int8 in the low mantissa byte,
+// round-half-even), three byte permutes pack the word.  kCount also counts clipped values.
+template <bool kCount>
+__device__ __forceinline__ uint32_t quantise4(const uint32_t (&r)[32], int j, float2 g0, float2 g1, int* clipped) {
+    uint32_t m[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 g = i < 2 ? g0 : g1;  // (gain, 127 / gain)
+        const float v = __uint_as_float(r[4 * j + i]);
+        const float cl = fminf(fmaxf(v, -g.y), g.y);
+        if (kCount) *clipped += (cl != v);
+        m[i] = __float_as_uint(fmaf(cl, g.x, 12582912.0f));
+    }
+    return __byte_perm(__byte_perm(m[0], m[1], 0x0040u), __byte_perm(m[2], m[3], 0x0040u), 0x5410u);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------------
-template <bool kProf, bool kTv>
+template <bool kProf, bool kTv, bool kQ8>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_constant__ CUtensorMap tm_in,
                       const __grid_constant__ CUtensorMap tm_out) {
@@ -498,6 +528,13 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         uint4* z = reinterpret_cast<uint4*>(smem_gen);
         for (int i = threadIdx.x; i < kBopBufs * kBopBufBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async_smem();
+    }
+    const uint32_t gain_tab_cta = smem_base + kSmemData + 512;
+    if (kQ8 && prm.q8_wide && threadIdx.x < 64) {  // one table for the CTA (single N tile); padding beams: gain 0
+        const int m = threadIdx.x;
+        const float gi = m < prm.M ? __ldg(prm.gains + m) : 0.f;
+        st_shared_v2(gain_tab_cta + m * 8u, __float_as_uint(gi),
+                     __float_as_uint(m >= prm.M ? 3.0e38f : gi > 0.f ? 127.0f / gi : 0.f));
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
     if (warp == kProducerWarp && lane == 0) prefetch_tensormap(&tm_in);
@@ -598,11 +635,26 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         // =================================== epilogue ===================================
         const int q = warp & 3;  // TMEM lane quarter this warp may read
         const uint32_t ost = ost_base + static_cast<uint32_t>(q) * (2 * kOutBoxBytes);
+        const uint32_t gain_tab = ost + kOutBoxBytes;  // q8 only: its four 1 KiB boxes live in the first half
         uint32_t unit = 0, box = 0;
+        int clipped = 0;
         bool ok = true;
         for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k)
             for (int it = 0; it < prm.nt_count && ok; ++it) {
                 const int n0 = it * nt;
+                if (kQ8 && !prm.q8_wide && (prm.nt_count > 1 || k == 0)) {
+                    // per-warp table of (gain, clip level = 127 / gain) for the 64 beams an N tile can hold, kept
+                    // in the unused part of this warp's staging area; padding beams: gain 0, never "clipped"
+                    __syncwarp();
+#pragma unroll
+                    for (int i = lane; i < 64; i += 32) {
+                        const int m = (n0 >> 1) + i;
+                        const float gi = m < M ? __ldg(prm.gains + m) : 0.f;
+                        st_shared_v2(gain_tab + static_cast<uint32_t>(i) * 8u, __float_as_uint(gi),
+                                     __float_as_uint(m >= M ? 3.0e38f : gi > 0.f ? 127.0f / gi : 0.f));
+                    }
+                    __syncwarp();
+                }
                 for (int b = 0; b < B && ok; ++b)
                     for (int h = 0; h < prm.ht_count && ok; ++h, ++unit) {
                         const uint32_t ab = unit % kAccBufs;
@@ -610,24 +662,124 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         if (!ok) break;
                         tc_fence_after();
                         const int t0 = h * kTileT;
-                        if (prm.tma_store) {
+                        if constexpr (kQ8) {
+                            // requantised output: thread = row, 32 columns -> 32 bytes per row.  Two TMEM reads are
+                            // in flight per wait and four 1 KiB staging boxes rotate, so neither the TMEM latency nor
+                            // the bulk stores' shared-memory reads sit on the critical path.
+                            const int row0 = t0 + 32 * q;
+                            if (prm.q8_wide) {
+                                // whole output rows (nt = 2M bytes: 32, 64 or 128) -> one box of 32 rows per pol:
+                                // 4x fewer, 4x longer rows for the TMA store engine than 32-byte pieces
+                                const uint32_t cmask = static_cast<uint32_t>(nt >> 4) - 1u;  // swizzle span = row length
+                                for (int p = 0; p < kPols && row0 < T; ++p, ++box) {
+                                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kPols + p) * static_cast<uint32_t>(nt);
+                                    const uint32_t sb = ost + (box & 1u) * kOutBoxBytes;
+                                    bulk_wait_group_read<1>();  // (issuing lane) the store that last read this box is done
+                                    __syncwarp();
+                                    // 32 columns of row `lane` -> 16-byte chunks c0/16 and c0/16 + 1, XOR-swizzled by the
+                                    // row's 128-byte group
+                                    auto put32 = [&](const uint32_t (&r)[32], int c0) {
+                                        uint32_t w[8];
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) {
+                                            const float4 gg = ld_shared_f4(gain_tab_cta + static_cast<uint32_t>((c0 >> 1) + 2 * j) * 8u);
+                                            const float2 g0 = make_float2(gg.x, gg.y), g1 = make_float2(gg.z, gg.w);
+                                            w[j] = prm.saturated ? quantise4<true>(r, j, g0, g1, &clipped)
+                                                                 : quantise4<false>(r, j, g0, g1, &clipped);
+                                        }
+                                        const uint32_t a0 = static_cast<uint32_t>(lane * nt + c0);
+                                        const uint32_t a1 = a0 + 16u;
+                                        st_shared_v4(sb + (a0 ^ (((a0 >> 7) & cmask) << 4)), w[0], w[1], w[2], w[3]);
+                                        st_shared_v4(sb + (a1 ^ (((a1 >> 7) & cmask) << 4)), w[4], w[5], w[6], w[7]);
+                                    };
+                                    for (int cb = 0; cb < nt; cb += 32) {
+                                        uint32_t r[32];
+                                        tmem_ld_32x32b_x32(taddr + cb, r);
+                                        tmem_wait_ld();
+                                        put32(r, cb);
+                                    }
+                                    fence_proxy_async_smem();
+                                    __syncwarp();
+                                    if (elect_one()) {
+                                        tma_store_3d(&tm_out, sb, 0, row0, (b * kPols + p) * C + c);
+                                        bulk_commit_group();
+                                    }
+                                }
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(bar(kAccEmpty + ab));
+                                continue;
+                            }
+                            auto emit_block = [&](const uint32_t (&r)[32], int cb, int plane, uint32_t sb) {
+                                uint32_t w[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 gg = ld_shared_f4(gain_tab + static_cast<uint32_t>((cb >> 1) + 2 * j) * 8u);
+                                    w[j] = prm.saturated ? quantise4<true>(r, j, make_float2(gg.x, gg.y), make_float2(gg.z, gg.w), &clipped)
+                                                         : quantise4<false>(r, j, make_float2(gg.x, gg.y), make_float2(gg.z, gg.w), &clipped);
+                                }
+                                if (prm.tma_store) {
+                                    const uint32_t dst = sb + lane * 32;  // [32 rows][32 B], 32B swizzle
+                                    const uint32_t x = static_cast<uint32_t>((lane >> 2) & 1) << 4;
+                                    st_shared_v4(dst + x, w[0], w[1], w[2], w[3]);
+                                    st_shared_v4(dst + (x ^ 16u), w[4], w[5], w[6], w[7]);
+                                    fence_proxy_async_smem();
+                                    __syncwarp();
+                                    if (elect_one()) {
+                                        tma_store_3d(&tm_out, sb, n0 + cb, row0, plane);
+                                        bulk_commit_group();
+                                    }
+                                } else if (row0 + lane < T) {  // ragged beam counts: 2-byte stores (row pitch 2M is even)
+                                    uint8_t* rowp = reinterpret_cast<uint8_t*>(prm.out_q8) +
+                                                    (static_cast<size_t>(plane) * T + row0 + lane) * static_cast<size_t>(N2) + n0 + cb;
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j)
+                                        if (n0 + cb + 2 * j < N2)
+                                            *reinterpret_cast<uint16_t*>(rowp + 2 * j) =
+                                                static_cast<uint16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+                                }
+                            };
+                            for (int p = 0; p < kPols; ++p) {
+                                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kPols + p) * static_cast<uint32_t>(nt);
+                                const int plane = (b * kPols + p) * C + c;
+                                for (int cb = 0; cb < nt && row0 < T && n0 + cb < N2; cb += 64, box += 2) {
+                                    const bool two = cb + 32 < nt && n0 + cb + 32 < N2;
+                                    uint32_t ra[32], rb[32];
+                                    tmem_ld_32x32b_x32(taddr + cb, ra);
+                                    if (two) tmem_ld_32x32b_x32(taddr + cb + 32, rb);
+                                    bulk_wait_group_read<2>();  // (issuing lane) the two boxes used four blocks ago are free
+                                    __syncwarp();
+                                    tmem_wait_ld();
+                                    emit_block(ra, cb, plane, ost + (box & 3u) * 1024u);
+                                    if (two) emit_block(rb, cb + 32, plane, ost + ((box + 1) & 3u) * 1024u);
+                                }
+                            }
+                        } else if (prm.tma_store) {
                             const int row0 = t0 + 32 * q;  // this warp's 32 rows of the tile
                             for (int p = 0; p < kPols; ++p) {
                                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kPols + p) * static_cast<uint32_t>(nt);
                                 const int plane = (b * kPols + p) * C + c;
                                 for (int cb = 0; cb < nt && row0 < T && n0 + cb < N2; cb += 32, ++box) {
                                     uint32_t r[32];
+                                    unsigned long long tp0 = 0, tp1 = 0, tp2 = 0;
+                                    if (kProf && prof_lane) tp0 = global_ns();
                                     tmem_ld_32x32b_x32(taddr + cb, r);
                                     const uint32_t sb = ost + (box & 1u) * kOutBoxBytes;
                                     bulk_wait_group_read<1>();  // (issuing lane) the store that last read this box is done
                                     __syncwarp();
+                                    if (kProf && prof_lane) tp1 = global_ns();
                                     tmem_wait_ld();
+                                    if (kProf && prof_lane) tp2 = global_ns();
                                     const uint32_t dst = sb + lane * 128;
 #pragma unroll
                                     for (int j = 0; j < 8; ++j)
                                         st_shared_v4(dst + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                                     fence_proxy_async_smem();
                                     __syncwarp();
+                                    if (kProf && prof_lane) {  // slot 1: bulk-store read wait, slot 2: TMEM read + fence + stores
+                                        ctl->wait_ns[kRoleEpilogue][1] += tp1 - tp0;
+                                        ctl->wait_ns[kRoleEpilogue][2] += (tp2 - tp1) | ((global_ns() - tp2) << 32);
+                                    }
                                     if (elect_one()) {
                                         tma_store_3d(&tm_out, sb, n0 + cb, row0, plane);
                                         bulk_commit_group();
@@ -681,6 +833,10 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     }
             }
         bulk_wait_group_all();  // (issuing lane) staging memory and the stores themselves are done before exit
+        if (kQ8 && prm.saturated) {
+            clipped = __reduce_add_sync(0xffffffffu, clipped);
+            if (lane == 0 && clipped) atomicAdd(prm.saturated, static_cast<unsigned long long>(clipped));
+        }
     } else if (warp >= kConvertWarp0 && warp < kConvertWarp0 + 4) {
         // =================================== convert ===================================
         // thread = one sample row t; per 4-antenna chunk: 4 conflict-free LDS.32, 8 PRMT + 8 HSUB2, 2 STS.128
@@ -1007,10 +1163,15 @@ static int get_encode_fn(EncodeTiledFn* out) {
 
 int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T,
                  int M, long long first_chan, double sample_period, const double* batch_dt_s, unsigned flags,
-                 cudaStream_t s) {
+                 cudaStream_t s, const QuantisedOut* q8) {
     FusedParams p{};
     p.dv = reinterpret_cast<const float4*>(delay_vals);
     p.out = beams;
+    if (q8) {
+        p.out_q8 = q8->beams;
+        p.gains = q8->gains;
+        p.saturated = q8->saturated;
+    }
     p.B = B, p.A = A, p.C = C, p.T = T, p.M = M;
     p.parts = (flags & DCBF_FLAG_FP16_COEFF) ? 1 : 2;
     p.signed_in = (flags & DCBF_FLAG_SIGNED_INPUT) ? 1 : 0;
@@ -1032,7 +1193,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
             p.dt_lo[b] = static_cast<float>(batch_dt_s[b] - static_cast<double>(p.dt_hi[b]));
         }
     }
-    p.tma_store = !(flags & DCBF_FLAG_DEBUG_DIRECT_EPILOGUE) && (M % 2 == 0) && (p.nt_count == 1 || p.nt % 32 == 0);
+    p.tma_store = !(flags & DCBF_FLAG_DEBUG_DIRECT_EPILOGUE) && (M % (q8 ? 8 : 2) == 0) && (p.nt_count == 1 || p.nt % 32 == 0);
     if (static_cast<long long>(B) * kPols * C > 0x7fffffffLL) return DCBF_ERR_UNSUPPORTED;
     if (int e = get_status_block(&p.status)) return e;
     static std::atomic<unsigned> ticket{0};
@@ -1055,7 +1216,23 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return record_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(samples)");
     }
-    if (p.tma_store) {
+    p.q8_wide = q8 && p.tma_store && p.nt_count == 1 && (p.nt == 32 || p.nt == 64 || p.nt == 128);
+    if (p.tma_store && q8) {
+        // requantised beams as [B*2*C][T][2M] int8; box [1][32][32] with 32B swizzle, or -- when one N tile is the
+        // whole row -- box [1][32][nt] with the swizzle span equal to the row length
+        const cuuint64_t dims[3] = {static_cast<cuuint64_t>(2 * M), static_cast<cuuint64_t>(T),
+                                    static_cast<cuuint64_t>(B) * kPols * C};
+        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(2 * M), static_cast<cuuint64_t>(T) * 2 * M};
+        const cuuint32_t box[3] = {static_cast<cuuint32_t>(p.q8_wide ? p.nt : 32), 32, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUtensorMapSwizzle sw = !p.q8_wide || p.nt == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                      : p.nt == 64             ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                               : CU_TENSOR_MAP_SWIZZLE_128B;
+        const CUresult r = encode(&tm_out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, q8->beams, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return record_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(beams_q8)");
+    } else if (p.tma_store) {
         // beams as [B*2*C][T][2M] fp32, box [1][32][32], 128B swizzle
         const cuuint64_t dims[3] = {static_cast<cuuint64_t>(2 * M), static_cast<cuuint64_t>(T),
                                     static_cast<cuuint64_t>(B) * kPols * C};
@@ -1075,9 +1252,12 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     DCBF_CUDA_TRY(cudaGetDevice(&dev));
     if (!n_sms[dev]) {
         DCBF_CUDA_TRY(cudaDeviceGetAttribute(&n_sms[dev], cudaDevAttrMultiProcessorCount, dev));
-        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     }
     const int grid = C < n_sms[dev] ? C : n_sms[dev];
     cudaLaunchConfig_t cfg{};
@@ -1090,12 +1270,17 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (flags & DCBF_FLAG_STREAMING) ? 1 : 0;
-    if (batch_dt_s)
-        DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, fused_beamform_kernel<false, true>, p, tm_in, tm_out));
-    else if (p.prof)
-        DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, fused_beamform_kernel<true, false>, p, tm_in, tm_out));
+    // (profiling, time-varying steering, int8 output) specialisations; the profiler has no time-varying build
+    auto kernel = fused_beamform_kernel<false, false, false>;
+    if (q8)
+        kernel = batch_dt_s ? fused_beamform_kernel<false, true, true>
+                 : p.prof   ? fused_beamform_kernel<true, false, true>
+                            : fused_beamform_kernel<false, false, true>;
     else
-        DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, fused_beamform_kernel<false, false>, p, tm_in, tm_out));
+        kernel = batch_dt_s ? fused_beamform_kernel<false, true, false>
+                 : p.prof   ? fused_beamform_kernel<true, false, false>
+                            : fused_beamform_kernel<false, false, false>;
+    DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, p, tm_in, tm_out));
     DCBF_CHECK_LAUNCH("fused_beamform_kernel");
     return DCBF_OK;
 }

@@ -24,6 +24,8 @@ struct HostPlan {
         float* beams = nullptr;
     };
     std::vector<Slot> slots;
+    float* gains = nullptr;                    // device [M], set by dcbf_host_plan_set_gains (q8 runs)
+    unsigned long long* saturated = nullptr;   // device counter (q8 runs)
 };
 
 static int destroy_plan(HostPlan* p) {
@@ -35,6 +37,8 @@ static int destroy_plan(HostPlan* p) {
         cudaFree(s.beams);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
+    cudaFree(p->gains);
+    cudaFree(p->saturated);
     delete p;
     cudaGetLastError();
     return DCBF_OK;
@@ -53,12 +57,19 @@ static int create_plan(HostPlan* p) {
     return DCBF_OK;
 }
 
-static int run_plan(HostPlan* p, const uint8_t* h_samples, const float* h_dv, float* h_beams) {
+// h_beams: float32 beams, or int8 requantised beams when q8 (then *h_saturated receives the clip count).
+static int run_plan(HostPlan* p, const uint8_t* h_samples, const float* h_dv, void* h_beams, bool q8,
+                    unsigned long long* h_saturated) {
     int dev = 0;
     DCBF_CUDA_TRY(cudaGetDevice(&dev));
     if (dev != p->device) return DCBF_ERR_INVALID_ARG;
-    const size_t samp_chan = static_cast<size_t>(p->T) * 4;          // bytes per (b, a, c)
-    const size_t beam_chan = static_cast<size_t>(p->T) * p->M * 8;   // bytes per (b, p, c)
+    if (q8) {
+        if (!p->gains) return DCBF_ERR_INVALID_ARG;  // dcbf_host_plan_set_gains first
+        if (!p->saturated) DCBF_CUDA_TRY(cudaMalloc(&p->saturated, sizeof(unsigned long long)));
+        DCBF_CUDA_TRY(cudaMemset(p->saturated, 0, sizeof(unsigned long long)));
+    }
+    const size_t samp_chan = static_cast<size_t>(p->T) * 4;                   // bytes per (b, a, c)
+    const size_t beam_chan = static_cast<size_t>(p->T) * p->M * (q8 ? 2 : 8);  // bytes per (b, p, c)
     int i = 0;
     for (int c0 = 0; c0 < p->C; c0 += p->chunk, ++i) {
         auto& s = p->slots[i % p->slots.size()];
@@ -70,14 +81,17 @@ static int run_plan(HostPlan* p, const uint8_t* h_samples, const float* h_dv, fl
         DCBF_CUDA_TRY(cudaMemcpyAsync(s.delay_vals, h_dv + static_cast<size_t>(c0) * p->M * p->A * 4,
                                       static_cast<size_t>(cc) * p->M * p->A * 16, cudaMemcpyHostToDevice, s.stream));
         const long long first_chan = static_cast<long long>(p->C) * p->xeng_id + c0;
+        const QuantisedOut qo{reinterpret_cast<int8_t*>(s.beams), p->gains, p->saturated};
         if (int e = launch_fused(s.samples, s.delay_vals, s.beams, p->B, p->A, cc, p->N, p->T, p->M, first_chan,
-                                 p->sample_period, nullptr, p->flags, s.stream))
+                                 p->sample_period, nullptr, p->flags, s.stream, q8 ? &qo : nullptr))
             return e;
         DCBF_CUDA_TRY(cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(h_beams) + c0 * beam_chan, p->C * beam_chan, s.beams,
                                         cc * beam_chan, cc * beam_chan, static_cast<size_t>(p->B) * kPols,
                                         cudaMemcpyDeviceToHost, s.stream));
     }
     for (auto& s : p->slots) DCBF_CUDA_TRY(cudaStreamSynchronize(s.stream));
+    if (q8 && h_saturated)
+        DCBF_CUDA_TRY(cudaMemcpy(h_saturated, p->saturated, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return DCBF_OK;
 }
 
@@ -115,7 +129,22 @@ __attribute__((visibility("default"))) int dcbf_host_plan_create(dcbf_host_plan_
 __attribute__((visibility("default"))) int dcbf_host_plan_run(dcbf_host_plan_t plan, const uint8_t* samples,
                                                               const float* delay_vals, float* beams) {
     if (!plan || !samples || !delay_vals || !beams) return DCBF_ERR_INVALID_ARG;
-    return run_plan(static_cast<HostPlan*>(plan), samples, delay_vals, beams);
+    return run_plan(static_cast<HostPlan*>(plan), samples, delay_vals, beams, false, nullptr);
+}
+
+__attribute__((visibility("default"))) int dcbf_host_plan_set_gains(dcbf_host_plan_t plan, const float* beam_gains) {
+    auto* p = static_cast<HostPlan*>(plan);
+    if (!p || !beam_gains) return DCBF_ERR_INVALID_ARG;
+    if (!p->gains) DCBF_CUDA_TRY(cudaMalloc(&p->gains, sizeof(float) * p->M));
+    DCBF_CUDA_TRY(cudaMemcpy(p->gains, beam_gains, sizeof(float) * p->M, cudaMemcpyHostToDevice));
+    return DCBF_OK;
+}
+
+__attribute__((visibility("default"))) int dcbf_host_plan_run_q8(dcbf_host_plan_t plan, const uint8_t* samples,
+                                                                 const float* delay_vals, int8_t* beams_q8,
+                                                                 unsigned long long* saturated) {
+    if (!plan || !samples || !delay_vals || !beams_q8) return DCBF_ERR_INVALID_ARG;
+    return run_plan(static_cast<HostPlan*>(plan), samples, delay_vals, beams_q8, true, saturated);
 }
 
 __attribute__((visibility("default"))) int dcbf_host_plan_destroy(dcbf_host_plan_t plan) {

@@ -108,6 +108,19 @@ int dcbf_fused_tv(const uint8_t* samples, const float* delay_vals, float* beams,
                   int n_chans, int n_chans_total, int n_samples, int n_beams, int xeng_id, double sample_period,
                   const double* batch_dt_s, unsigned flags, dcbf_stream_t stream);
 
+/* Fused path with the beam post-stage folded into the epilogue (next-row feature, SURVEY 8f-2: the reference's
+ * output "reorder further in the pipeline is to be expected", beamformer_coefficient_generator/BeamformerKernels.cuh:142-143;
+ * tied-array-channelised-voltage streams are 8-bit):
+ *     beams_q8[b][p][c][t][2m + x] = int8( clip( rint( beam * beam_gains[m] ), -127, 127 ) )      (round half to even)
+ * beam_gains: device float[n_beams]; saturated: optional device counter incremented by the number of clipped values
+ * (NULL to skip); batch_dt_s: NULL or per-batch time offsets as in dcbf_fused_tv.  Output traffic drops 4x. */
+int dcbf_fused_q8(const uint8_t* samples, const float* delay_vals, const float* beam_gains, int8_t* beams_q8,
+                  unsigned long long* saturated, int n_batches, int n_ants, int n_chans, int n_chans_total,
+                  int n_samples, int n_beams, int xeng_id, double sample_period, const double* batch_dt_s,
+                  unsigned flags, dcbf_stream_t stream);
+/* Algorithmic HBM bytes of one dcbf_fused_q8 call (in + delay_vals + gains + int8 out). */
+unsigned long long dcbf_fused_q8_bytes(int n_batches, int n_ants, int n_chans, int n_samples, int n_beams);
+
 /* Blocks until prior work on the current device is done, then returns the status the last dcbf_fused kernels
  * left behind: DCBF_OK, or DCBF_ERR_TIMEOUT if an in-kernel pipeline wait exceeded its 2 s guard (the kernel
  * then exits early instead of hanging; *role / *barrier / *block say who waited on what).  Clears the status. */
@@ -132,6 +145,11 @@ int dcbf_host_plan_create(dcbf_host_plan_t* plan, int n_batches, int n_ants, int
                           int n_samples, int n_beams, int xeng_id, double sample_period, unsigned flags,
                           int chunk_chans, int n_slots);
 int dcbf_host_plan_run(dcbf_host_plan_t plan, const uint8_t* samples, const float* delay_vals, float* beams);
+/* Requantised-output runs of a plan (dcbf_fused_q8 per chunk): set the per-beam gains (HOST float[n_beams]) once,
+ * then run; beams_q8 is a HOST int8 array [B][2][C][T/16][16][2M]; *saturated (may be NULL) gets the clip count. */
+int dcbf_host_plan_set_gains(dcbf_host_plan_t plan, const float* beam_gains);
+int dcbf_host_plan_run_q8(dcbf_host_plan_t plan, const uint8_t* samples, const float* delay_vals, int8_t* beams_q8,
+                          unsigned long long* saturated);
 int dcbf_host_plan_destroy(dcbf_host_plan_t plan);
 
 /* Number of kernel launches this library has issued since load (all entry points); used by bench.py

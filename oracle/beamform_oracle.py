@@ -266,6 +266,16 @@ def beamform_pipeline_fast(samples, delay_vals, n_channels, xeng_id, sample_peri
     return out.reshape(b, p, c, t // SAMPLES_PER_BLOCK, SAMPLES_PER_BLOCK, 2 * m)
 
 
+def requantise(beams: np.ndarray, gains: np.ndarray):
+    """Beam post-stage of dcbf_fused_q8 (our definition; the reference stops at float32 beams):
+    int8(clip(rint(beam * gain[m]), -127, 127)) with round-half-even, plus the number of clipped values.
+    ``beams`` (..., 2M) float, ``gains`` (M,)."""
+    g = np.repeat(np.asarray(gains, np.float64), 2)
+    v = np.asarray(beams, np.float64) * g
+    clipped = int(np.count_nonzero(np.abs(v) > 127.0))
+    return np.clip(np.rint(v), -127, 127).astype(np.int8), clipped
+
+
 # --------------------------------------------------------------------------------------
 # Synthetic inputs shared by tests / bench (SURVEY.md section 8d)
 # --------------------------------------------------------------------------------------

@@ -324,6 +324,67 @@ def test_time_varying_steering(dropin):
     np.testing.assert_array_equal(res[0], res[1])
 
 
+@pytest.mark.parametrize("case", [(1, 64, 7, 256, 16, 1024, 0, False), (2, 23, 3, 48, 3, 256, 1, True),
+                                  (1, 80, 4, 256, 32, 32768, 3, False), (1, 4, 9, 128, 8, 64, 0, False)],
+                         ids=["M16_tma", "M3_ragged_signed", "M32_A80", "M8_16cols"])
+def test_fused_q8_requantised_output(dropin, case):
+    """Next-row feature: int8 beams = clip(rint(beam * gain[m]), -127, 127) in the fused epilogue.
+    Against the float64 oracle: never more than one quantisation step away, practically always equal (the only
+    differences are float32-vs-float64 ties at .5 boundaries), same saturation count."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m, n, xid, signed = case
+    x = orc.make_samples(b, a, c, t, seed=51)
+    dv = orc.make_delay_vals_random(c, m, a, seed=52)
+    ref = orc.beamform_pipeline(x, dv, n, xid, TS, signed_input=signed)
+    rng = np.random.default_rng(53)
+    gains = (rng.uniform(0.5, 3.0, m) * 100.0 / np.abs(ref).max()).astype(np.float32)  # a few percent saturate
+    want, want_clipped = orc.requantise(ref, gains)
+    out = torch.full(ref.shape, 77, dtype=torch.int8, device="cuda")
+    sat = torch.zeros(1, dtype=torch.int64, device="cuda")
+    flags = _capi.FLAG_SIGNED_INPUT if signed else 0
+    _capi.fused_q8(torch.from_numpy(x).cuda(), torch.from_numpy(dv).cuda(), torch.from_numpy(gains).cuda(), out,
+                   b, a, c, n, t, m, xid, TS, flags=flags, saturated=sat)
+    _capi.fused_status()
+    got = out.cpu().numpy()
+    diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert diff.max() <= 1
+    assert np.count_nonzero(diff) <= 1e-3 * diff.size
+    assert want_clipped > 0 and abs(int(sat.item()) - want_clipped) <= 2 + 1e-3 * want_clipped
+    assert _capi.fused_q8_bytes(b, a, c, t, m) == x.size + dv.size * 4 + got.size + 4 * m
+
+
+def test_q8_operator_and_host_plan(dropin):
+    """The q8 extension through the operator API and through the host-buffer C-ABI plan give the same bytes."""
+    from beamforming.beamform_op_sequence import QuantisedOpSequenceTemplate
+    from dpdk_dc_sand_b200 import _capi
+
+    ctx, queue = dropin
+    b, a, c, t, m, n, xid = 2, 16, 21, 64, 8, 256, 1
+    x = orc.make_samples(b, a, c, t, seed=61)
+    dv = orc.make_delay_vals_random(c, m, a, seed=62)
+    ref = orc.beamform_pipeline(x, dv, n, xid, TS)
+    gains = np.full(m, 90.0 / np.abs(ref).max(), np.float32)
+    op = QuantisedOpSequenceTemplate(ctx, b, 2, c, n, t // 16, 16, a, m, xid, TS, t).instantiate(queue)
+    op.ensure_all_bound()
+    op.buffer("bufin_reorder").set(queue, x)
+    op.buffer("bufin_delay_vals").set(queue, dv)
+    op.buffer("bufin_gains").set(queue, gains)
+    op()
+    got = op.buffer("bufout_q8").get(queue)
+    assert got.dtype == np.int8 and got.shape == ref.shape and op.saturated == 0
+    want, _ = orc.requantise(ref, gains)
+    assert np.abs(got.astype(np.int32) - want).max() <= 1 and np.count_nonzero(got != want) <= 1e-3 * want.size
+    plan = _capi.HostPlan(b, a, c, n, t, m, xid, TS, chunk_chans=8, n_slots=2)
+    plan.set_gains(gains)
+    host = np.zeros(ref.shape, np.int8)
+    assert plan.run_q8(x, dv, host) == 0
+    plan.close()
+    np.testing.assert_array_equal(host, got)
+
+
 def test_fused_matches_three_kernel_chain_and_materialises_intermediates(dropin):
     from beamforming.beamform_op_sequence import OpSequenceTemplate
 
