@@ -63,6 +63,15 @@ def _traffic(workload: str):
     return None
 
 
+def _ncu_kernel_us(workload: str):
+    """gpu__time_duration of one launch in the committed ncu capture (cold, serialised: context only)."""
+    path = os.path.join(ROOT, "profiles", "fused_traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh).get(f"{workload}_detail", {}).get("gpu_time_us")
+    return None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
 
@@ -274,23 +283,33 @@ def run_ours(args, wl) -> None:
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.12)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    # timed region: exactly K steps between two events on the launching stream (an event record between every
+    # pair of launches would itself sit in the stream and lengthen each step by several microseconds)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _capi.launch_count()
     barrier()
     t_begin = time.time()
     with torch.cuda.stream(stream):
-        ev[0].record(stream)
+        ev0.record(stream)
         for i in range(args.steps):
             step()
-            ev[i + 1].record(stream)
+        ev1.record(stream)
     stream.synchronize()
     barrier()
     t_end = time.time()
     launches = _capi.launch_count() - launches0
     clocks = sampler.stop(t_begin, t_end)
     _capi.fused_status()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev0.elapsed_time(ev1)
+    # per-launch spread from a second, separately instrumented pass (not the figure reported as `value`)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(min(args.steps, 10) + 1)]
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for i in range(len(ev) - 1):
+            step()
+            ev[i + 1].record(stream)
+    stream.synchronize()
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(len(ev) - 1)]
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -424,14 +443,15 @@ def run_ours(args, wl) -> None:
         del samples, dv, beams
         torch.cuda.empty_cache()
         secondary = {"c2": measure_secondary("c2", max(args.steps, 40), dev, rank, world, peak)}
-    mean_launch_s = statistics.mean(per_launch_ms) / 1e3
+    mean_launch_s = total_ms / 1e3 / args.steps  # this rank's average launch duration over the timed region
     achieved = alg_bytes / mean_launch_s / 1e9
     if q8 is not None:
         q8["roofline_frac"] = q8["algorithmic_GBps_per_gpu"] / peak
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": _traffic(args.workload), "kernel": "fused_beamform_kernel",
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_us_mean": mean_launch_s * 1e6,
-                "launch_us_min": min(per_launch_ms) * 1e3, "peak_source": peak_src,
+                "launch_us_min": min(per_launch_ms) * 1e3, "launch_us_with_event_between_launches": statistics.mean(per_launch_ms) * 1e3,
+                "kernel_us_under_ncu": _ncu_kernel_us(args.workload), "peak_source": peak_src,
                 "tensor_tflops_real_expanded": B * 2 * C * T * 8 * A * M / mean_launch_s / 1e12}
     cpu = None
     if world == 1 and not args.no_cpu:
