@@ -73,7 +73,10 @@ def _ncu_kernel_us(workload: str):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+    """Samples SM clock and throttle reasons of one GPU while a timed region runs.
+
+    NVML from a thread (one sample per millisecond: the timed region lasts only a few milliseconds), with the
+    recipe's `nvidia-smi -lms` query as the fall-back when pynvml is unavailable."""
 
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -81,48 +84,88 @@ class ClockSampler:
 
     def __init__(self, index: int) -> None:
         self.index = index
-        self.rows = []
+        self.rows = []  # (time, sm_mhz, max_mhz, power_w, set of reasons)
         self.proc = None
+        self.thread = None
+        self._stop = False
+        self.source = None
 
-    def start(self) -> None:
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+    def _nvml_loop(self, nv, handle) -> None:
+        reasons = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                   "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                   "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                   "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        mx = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                pw = nv.nvmlDeviceGetPowerUsage(handle) / 1e3
+                self.rows.append((time.time(), float(sm), float(mx), pw, {k for k, v in reasons.items() if mask & v}))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
-    def _read(self) -> None:
+    def _smi_loop(self) -> None:
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t_begin: float, t_end: float) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        rows = [r for r in self.rows if t_begin <= r[0] <= t_end + 0.1] or self.rows
-        for _, line in rows:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+                rs = {n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")}
+                self.rows.append((time.time(), float(f[0]), float(f[1]), float(f[2]), rs))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def start(self) -> None:
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.source = "nvml, 1 ms period"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.source = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 50"
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def window(self, t_begin: float, t_end: float) -> dict:
+        """Summary of the samples taken inside [t_begin, t_end] (the nearest ones if the window caught none)."""
+        rows = [r for r in self.rows if t_begin <= r[0] <= t_end]
+        inside = len(rows)
+        if not rows and self.rows:
+            mid = 0.5 * (t_begin + t_end)
+            rows = sorted(self.rows, key=lambda r: abs(r[0] - mid))[:2]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples available"], "samples": 0}
+        reasons = set().union(*[r[4] for r in rows])
+        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": max(r[2] for r in rows),
+                "power_w": round(statistics.median(r[3] for r in rows), 1), "reasons": sorted(reasons),
+                "samples": inside, "source": self.source}
+
+    def stop(self) -> None:
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=1)
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -249,7 +292,7 @@ def run_ours(args, wl) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("DCBF_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
     n_total = C * world
     flags = _capi.FLAG_FP16_COEFF if args.fp16_coeff else 0
@@ -282,7 +325,9 @@ def run_ours(args, wl) -> None:
 
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.12)
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 3.0:  # NVML initialisation takes a moment
+        time.sleep(0.01)
     # timed region: exactly K steps between two events on the launching stream (an event record between every
     # pair of launches would itself sit in the stream and lengthen each step by several microseconds)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -298,7 +343,7 @@ def run_ours(args, wl) -> None:
     barrier()
     t_end = time.time()
     launches = _capi.launch_count() - launches0
-    clocks = sampler.stop(t_begin, t_end)
+    clocks = sampler.window(t_begin, t_end)
     _capi.fused_status()
     total_ms = ev0.elapsed_time(ev1)
     # per-launch spread from a second, separately instrumented pass (not the figure reported as `value`)
@@ -310,6 +355,31 @@ def run_ours(args, wl) -> None:
             ev[i + 1].record(stream)
     stream.synchronize()
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(len(ev) - 1)]
+
+    # ---- sustained: the same step after ~0.5 s of uninterrupted launches (a 1 kW part reaches its power cap) ----
+    sustained = None
+    if not args.no_sustained:
+        time.sleep(0.2)
+        t_s0 = time.time()
+        while time.time() - t_s0 < 0.5:
+            for _ in range(100):
+                step()
+            stream.synchronize()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_u0 = time.time()
+        with torch.cuda.stream(stream):
+            u0.record(stream)
+            for _ in range(200):
+                step()
+            u1.record(stream)
+        stream.synchronize()
+        t_u1 = time.time()
+        u_sec = u0.elapsed_time(u1) / 1e3 / 200
+        sustained = {"ms_per_step": u_sec * 1e3, "algorithmic_GBps_per_gpu": alg_bytes / u_sec / 1e9,
+                     "clocks": sampler.window(t_u0, t_u1),
+                     "note": "200 steps timed after 0.5 s of continuous launches; reported beside the K-step figure"}
+        time.sleep(0.3)
+    sampler.stop()
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -474,7 +544,7 @@ def run_ours(args, wl) -> None:
         "beam_gsamples_per_s": world * B * 2 * C * T * M / sec_per_step / 1e9,
         "algorithmic_GBps": world * alg_bytes / sec_per_step / 1e9,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "streaming": streaming, "q8_output": q8, "other_workloads": secondary,
+        "sustained": sustained, "streaming": streaming, "q8_output": q8, "other_workloads": secondary,
         "pcie": {"note": "e2e is bounded by the host link: pinned copies measured on this pool (tools/bench_standalone.py) "
                          "reach 55.5 GB/s H2D, 57.3 GB/s D2H alone and 49.9 GB/s each way when both directions run "
                          "at once; the e2e step moves h2d_bytes_per_step up and d2h_bytes_per_step down",
@@ -495,6 +565,7 @@ def main() -> None:
     ap.add_argument("--fp16-coeff", action="store_true", help="single fp16 coefficient rounding (DCBF_FLAG_FP16_COEFF)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-streaming", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the power-capped sustained-load measurement")
     ap.add_argument("--no-q8", action="store_true", help="skip the int8-output extension measurement")
     ap.add_argument("--no-secondary", action="store_true", help="skip the extra c2 (BASELINE configs[1]) measurement")
     ap.add_argument("--no-cpu", action="store_true")
