@@ -5,12 +5,14 @@
 // Replaces kernel `prebeamform_reorder`
 // (reference: beamformer/beamforming/kernels/prebeamform_reorder_kernel.mako:37-92), which moves one
 // 16-bit word per thread and scatters its stores at a stride of A words.  Here one CTA stages an
-// [A antennas] x [<=64 samples] tile through shared memory:
-//   - loads: each antenna row of the tile is 4*tt contiguous bytes -> 128-bit coalesced loads;
-//   - stores: for a fixed pol the tile's output is ONE contiguous run of tt*A*2 bytes
-//     ([t][a][x] with t the tile's samples) -> 128-bit, fully coalesced stores;
-//   - the transpose itself is a 2-byte gather from shared memory (row pitch tt+1 words keeps the
-//     gather at <=2-way bank conflicts for every antenna count, including odd ones).
+// [A antennas] x [<=64 samples] tile of 4-byte words {p0.re, p0.im, p1.re, p1.im} through shared memory:
+//   - loads: each antenna row of the tile is 4*tt contiguous bytes -> 128-bit coalesced loads, one STS.128 each;
+//   - stores: for a fixed pol the tile's output is ONE contiguous run of tt*A*2 bytes ([t][a][x]); a thread
+//     gathers the 8 words of 8 consecutive (t, a) elements ONCE and emits the 16-byte chunk of BOTH pols
+//     -> 128-bit, fully coalesced stores, 8 LDS + 8 PRMT per 32 output bytes;
+//   - the rows of antenna group a/8 are rotated by 4*(a/8) words, so the 32 lanes of a gather (8 antenna groups
+//     x 4 consecutive samples when A = 64) hit 32 different banks while the staging stores stay 16-byte
+//     aligned.
 // All global offsets are 64-bit (the reference's `int` indices overflow at B*A*C*T*P >= 2^31).
 #include "common.cuh"
 
@@ -37,7 +39,7 @@ __device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
 __global__ void __launch_bounds__(kThreads)
 reorder_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int A, int C, int T, int tile_t,
                int n_tiles) {
-    extern __shared__ uint32_t raw[];  // [A][tt + 1] words; word (a, t) = {p0.re, p0.im, p1.re, p1.im}
+    extern __shared__ __align__(16) uint32_t raw[];  // [A][tile_t] words, row a rotated by 4 * (a / 8)
 
     const long long blk = blockIdx.x;
     const int tile = static_cast<int>(blk % n_tiles);
@@ -45,7 +47,7 @@ reorder_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int A,
     const long long b = blk / (static_cast<long long>(n_tiles) * C);
     const int t0 = tile * tile_t;
     const int tt = min(tile_t, T - t0);  // multiple of 16
-    const int pitch = tt + 1;
+    const int mask = tile_t - 1;         // tile_t is a power of two
 
     // ---- coalesced 128-bit loads of the [A][tt] tile ----
     const int vec_per_row = tt >> 2;
@@ -55,54 +57,54 @@ reorder_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int A,
         const int v = i - a * vec_per_row;
         const size_t row = ((static_cast<size_t>(b) * A + a) * C + c) * static_cast<size_t>(T) + t0;
         const uint4 x = ldg_stream(reinterpret_cast<const uint4*>(in + row * 4) + v);
-        uint32_t* dst = raw + a * pitch + 4 * v;
-        dst[0] = x.x;
-        dst[1] = x.y;
-        dst[2] = x.z;
-        dst[3] = x.w;
+        *reinterpret_cast<uint4*>(raw + a * tile_t + ((4 * v + 4 * (a >> 3)) & mask)) = x;
     }
     __syncthreads();
 
-    // ---- per pol: tt*A elements of 2 bytes, contiguous in the output; 8 elements per 128-bit store ----
+    // ---- tt*A elements of 2 bytes per pol, contiguous in the output; 8 elements per 128-bit store ----
     const int n_chunk = (tt * A) >> 3;  // tt % 8 == 0
+    const size_t base0 = ((static_cast<size_t>(b) * kPols * C + c) * static_cast<size_t>(T) + t0) * A * 2;
+    uint4* dst0 = reinterpret_cast<uint4*>(out + base0);
+    uint4* dst1 = reinterpret_cast<uint4*>(out + base0 + static_cast<size_t>(C) * T * A * 2);  // pol 1 plane
+    for (int i = threadIdx.x; i < n_chunk; i += kThreads) {
+        const int e = i << 3;
+        int t = e / A;
+        int a = e - t * A;
+        uint32_t w[8];
 #pragma unroll
-    for (int p = 0; p < kPols; ++p) {
-        const size_t base = (((static_cast<size_t>(b) * kPols + p) * C + c) * static_cast<size_t>(T) + t0) * A * 2;
-        uint4* dst = reinterpret_cast<uint4*>(out + base);
-        const uint32_t sel = p ? 0x7632u : 0x5410u;  // pick the high/low 16 bits of two words
-        for (int i = threadIdx.x; i < n_chunk; i += kThreads) {
-            const int e = i << 3;
-            int t = e / A;
-            int a = e - t * A;
-            uint32_t w[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                w[j] = raw[a * pitch + t];
-                if (++a == A) {
-                    a = 0;
-                    ++t;
-                }
+        for (int j = 0; j < 8; ++j) {
+            w[j] = raw[a * tile_t + ((t + 4 * (a >> 3)) & mask)];
+            if (++a == A) {
+                a = 0;
+                ++t;
             }
-            uint4 v;
-            v.x = __byte_perm(w[0], w[1], sel);
-            v.y = __byte_perm(w[2], w[3], sel);
-            v.z = __byte_perm(w[4], w[5], sel);
-            v.w = __byte_perm(w[6], w[7], sel);
-            stg_stream(dst + i, v);
         }
+        uint4 v0, v1;  // low / high 16 bits of two words = pol 0 / pol 1 (re, im) of two elements
+        v0.x = __byte_perm(w[0], w[1], 0x5410u);
+        v0.y = __byte_perm(w[2], w[3], 0x5410u);
+        v0.z = __byte_perm(w[4], w[5], 0x5410u);
+        v0.w = __byte_perm(w[6], w[7], 0x5410u);
+        v1.x = __byte_perm(w[0], w[1], 0x7632u);
+        v1.y = __byte_perm(w[2], w[3], 0x7632u);
+        v1.z = __byte_perm(w[4], w[5], 0x7632u);
+        v1.w = __byte_perm(w[6], w[7], 0x7632u);
+        stg_stream(dst0 + i, v0);
+        stg_stream(dst1 + i, v1);
     }
 }
 
 }  // namespace
 
 int launch_reorder(const uint8_t* samples, uint8_t* reordered, int B, int A, int C, int T, cudaStream_t s) {
-    // Largest tile (in samples) whose staging buffer fits in shared memory.
-    int tile_t = 64;
-    auto smem_for = [&](int tt) { return static_cast<size_t>(A) * (tt + 1) * sizeof(uint32_t); };
-    const size_t kMaxSmem = 200 * 1024;
+    // Power-of-two tile (in samples, 16..128): long contiguous DRAM runs per antenna, but small enough (<= 36 KiB of
+    // staging) that six CTAs share an SM; huge arrays take whatever still fits.
+    int tile_t = 128;
+    while (tile_t > 16 && tile_t / 2 >= T) tile_t >>= 1;  // no point in a tile longer than the heap
+    auto smem_for = [&](int tt) { return static_cast<size_t>(A) * tt * sizeof(uint32_t); };
+    const size_t kGoodSmem = 36 * 1024, kMaxSmem = 200 * 1024;
+    while (tile_t > 64 && smem_for(tile_t) > kGoodSmem) tile_t >>= 1;
     while (tile_t > 16 && smem_for(tile_t) > kMaxSmem) tile_t >>= 1;
     if (smem_for(tile_t) > kMaxSmem) return DCBF_ERR_UNSUPPORTED;
-    if (tile_t > T) tile_t = T;
     const int n_tiles = (T + tile_t - 1) / tile_t;
     const long long n_blocks = static_cast<long long>(B) * C * n_tiles;
     if (n_blocks > 0x7fffffffLL) return DCBF_ERR_UNSUPPORTED;
