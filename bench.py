@@ -537,12 +537,13 @@ def run_ours(args, wl) -> None:
         "metric": METRIC, "value": world * in_bytes / sec_per_step / 1e9, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": sec_per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 operands (u8 exact, coefficients fp16 " + ("single" if args.fp16_coeff else "hi+lo") + "), f32 accumulate",
+        "dtype": "f16",  # tcgen05 kind::f16 operands (u8 voltages exact, coefficients fp16 hi+lo pairs), f32 accumulate
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc} per GPU", "n_ants": A, "n_chans_per_gpu": C,
                    "n_chans_total": n_total, "n_samples": T, "n_beams": M, "n_batches": B,
                    "parallelism": f"channel-sharded x{world} (rank == xeng_id), no collective",
                    "l2": f"working set {alg_bytes / 2**20:.0f} MiB per step > 126 MB L2 (inputs larger than L2)",
+                   "arithmetic": "u8 voltages exact in f16; coefficients as f16 " + ("single rounding" if args.fp16_coeff else "hi+lo pair (~2^-24)") + "; f32 accumulate in TMEM; f32 beams",
                    "tiling": dict(zip(("kb_count", "nt", "nt_count"), _capi.fused_tiling(A, M, flags)))},
         "beam_gsamples_per_s": world * B * 2 * C * T * M / sec_per_step / 1e9,
         "algorithmic_GBps": world * alg_bytes / sec_per_step / 1e9,
