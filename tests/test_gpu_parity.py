@@ -207,6 +207,10 @@ FUSED_CASES = [
     (1, 64, 10, 256, 64, 4096, 0, False, True),   # single-fp16 coefficients (fast mode)
     (1, 33, 200, 144, 9, 4096, 2, False, False),  # more channels than SMs, T = 128 + 16
     (1, 256, 2, 256, 2, 1024, 0, False, False),   # 8 k-blocks
+    (1, 300, 2, 64, 5, 512, 0, False, False),     # more antennas than coefficient threads, odd beams, 16-column N tiles
+    (2, 16, 3, 128, 130, 256, 1, False, False),   # 260 columns: three N tiles of 96 (TMA boxes inside their tile)
+    (1, 8, 1, 16, 1, 8, 0, False, False),         # smallest legal problem
+    (1, 64, 149, 16, 4, 4096, 3, True, False),    # one more channel than SMs, 16-sample heaps, signed
 ]
 
 
