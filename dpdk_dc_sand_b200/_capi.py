@@ -61,6 +61,18 @@ SIGNATURES = {
     "dcbf_fused_bytes": (C.c_ulonglong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
 }
 
+class FusedOptions(C.Structure):
+    """dcbf_fused_options (include/dcbf.h)."""
+
+    _fields_ = [("struct_size", C.c_size_t), ("batch_dt_s", C.POINTER(C.c_double)), ("beam_weights", C.c_void_p),
+                ("beam_gains", C.c_void_p), ("beams_q8", C.c_void_p), ("saturated", C.c_void_p)]
+
+
+SIGNATURES["dcbf_fused_ex"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_double, C.POINTER(FusedOptions), C.c_uint, C.c_void_p])
+SIGNATURES["dcbf_coeffs_ex"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_double, C.POINTER(C.c_double), C.c_void_p, C.c_void_p])
+
 _lib = None
 _lock = threading.Lock()
 
@@ -132,7 +144,13 @@ def _dt_array(batch_dt, n_batches):
 
 
 def coeffs(delay_vals, out, n_batches, n_pols, n_chans, n_chans_total, n_ants, n_beams, xeng_id, sample_period,
-           stream=None, batch_dt=None) -> None:
+           stream=None, batch_dt=None, weights=None) -> None:
+    if weights is not None:
+        dt = _dt_array(batch_dt, n_batches) if batch_dt is not None else None
+        check(load().dcbf_coeffs_ex(_ptr(delay_vals), _ptr(out), n_batches, n_pols, n_chans, n_chans_total, n_ants,
+                                    n_beams, xeng_id, float(sample_period), dt, _ptr(weights), _stream_handle(stream)),
+              "dcbf_coeffs_ex")
+        return
     if batch_dt is not None:
         check(load().dcbf_coeffs_tv(_ptr(delay_vals), _ptr(out), n_batches, n_pols, n_chans, n_chans_total, n_ants,
                                     n_beams, xeng_id, float(sample_period), _dt_array(batch_dt, n_batches),
@@ -147,8 +165,30 @@ def beamform(reordered, coeff, beams, n_batches, n_chans, n_samples, n_ants, n_b
                                n_beams, flags, _stream_handle(stream)), "dcbf_beamform")
 
 
+def fused_ex(samples, delay_vals, beams, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id,
+             sample_period, flags=0, stream=None, batch_dt=None, weights=None, gains=None, beams_q8=None,
+             saturated=None) -> None:
+    """dcbf_fused_ex: any combination of per-heap times, per-(beam, antenna) weights and int8 output."""
+    opts = FusedOptions()
+    opts.struct_size = C.sizeof(FusedOptions)
+    dt = _dt_array(batch_dt, n_batches) if batch_dt is not None else None  # keep alive until the call returns
+    if dt is not None:
+        opts.batch_dt_s = C.cast(dt, C.POINTER(C.c_double))
+    opts.beam_weights = _ptr(weights) if weights is not None else None
+    opts.beam_gains = _ptr(gains) if gains is not None else None
+    opts.beams_q8 = _ptr(beams_q8) if beams_q8 is not None else None
+    opts.saturated = _ptr(saturated) if saturated is not None else None
+    check(load().dcbf_fused_ex(_ptr(samples), _ptr(delay_vals), _ptr(beams) if beams is not None else None, n_batches,
+                               n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id, float(sample_period),
+                               C.byref(opts), flags, _stream_handle(stream)), "dcbf_fused_ex")
+
+
 def fused(samples, delay_vals, beams, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id,
-          sample_period, flags=0, stream=None, batch_dt=None) -> None:
+          sample_period, flags=0, stream=None, batch_dt=None, weights=None) -> None:
+    if weights is not None:
+        fused_ex(samples, delay_vals, beams, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id,
+                 sample_period, flags, stream, batch_dt=batch_dt, weights=weights)
+        return
     if batch_dt is not None:
         check(load().dcbf_fused_tv(_ptr(samples), _ptr(delay_vals), _ptr(beams), n_batches, n_ants, n_chans,
                                    n_chans_total, n_samples, n_beams, xeng_id, float(sample_period),

@@ -14,7 +14,7 @@ that code inspecting ``bufint_*`` after a call still finds the reference's conte
 """
 from .. import _capi
 from ..katsdpsigproc import accel
-from .coeff_generator import CoeffGeneratorTemplate
+from .coeff_generator import CoeffGeneratorTemplate, _device_weights
 from .matrix_multiply import MatrixMultiplyTemplate
 from .prebeamform_reorder import PreBeamformReorderTemplate
 
@@ -54,6 +54,7 @@ class OpSequence(accel.OperationSequence):
         fp16_coeff: single fp16 rounding of the coefficients instead of the fp16 hi+lo pair (default False).
         fused: False runs the three stand-alone kernels like the reference (default True).
         batch_times: per-batch time offsets (s) for time-varying steering, see CoeffGenerator (default None).
+        beam_weights: (n_beams, n_ants) real weights folded into the coefficients, see CoeffGenerator (default None).
     """
 
     def __init__(self, template: OpSequenceTemplate, queue) -> None:
@@ -80,6 +81,7 @@ class OpSequence(accel.OperationSequence):
         self.fp16_coeff = False
         self.fused = True
         self.batch_times = None
+        self.beam_weights = None
 
     # -- binding policy ---------------------------------------------------------------------------
     def _needs(self, name: str) -> bool:
@@ -101,6 +103,8 @@ class OpSequence(accel.OperationSequence):
     # -- execution --------------------------------------------------------------------------------
     def _run(self) -> None:
         self.beamform_coeff.batch_times = self.batch_times
+        weights = _device_weights(self)
+        self.beamform_coeff.beam_weights = weights
         if not self.fused:
             self.beamform_mult.signed_input = self.signed_input
             super()._run()
@@ -111,7 +115,7 @@ class OpSequence(accel.OperationSequence):
             self.buffer("bufin_reorder").buffer, self.buffer("bufin_delay_vals").buffer,
             self.buffer("bufout_mult").buffer, r.n_batches, r.n_ants, r.n_channels_per_stream, c.n_channels,
             r.n_samples_per_channel, c.n_beams, c.xeng_id, c.sample_period, self.flags(), self.command_queue.stream,
-            batch_dt=self.batch_times,
+            batch_dt=self.batch_times, weights=weights,
         )
         if self.slots["bufint_data"].is_bound:
             self.prebeamform_reorder()

@@ -51,6 +51,25 @@ class CoeffGeneratorTemplate:
         return CoeffGenerator(self, command_queue)
 
 
+def _device_weights(op):
+    """``op.beam_weights`` (None, a CUDA tensor, or anything array-like of shape (n_beams, n_ants)) as a device tensor."""
+    w = op.beam_weights
+    if w is None:
+        return None
+    import torch
+
+    t = op.template
+    n_beams = getattr(t, "n_beams", None) or op.template.beamform_coeff_template.n_beams
+    n_ants = getattr(t, "n_ants", None) or op.template.beamform_coeff_template.n_ants
+    if not (isinstance(w, torch.Tensor) and w.is_cuda):
+        dev = op.buffer("delay_vals" if "delay_vals" in op.slots else "bufin_delay_vals").buffer.device
+        w = torch.as_tensor(np.ascontiguousarray(w, dtype=np.float32)).to(dev)
+        op.beam_weights = w  # uploaded once; assign a new array to change the weights
+    if tuple(w.shape) != (n_beams, n_ants) or w.dtype != torch.float32:
+        raise ValueError("beam_weights must be float32 of shape (n_beams, n_ants)")
+    return w.contiguous()
+
+
 class CoeffGenerator(Operation):
     """.. rubric:: Slots
 
@@ -61,12 +80,15 @@ class CoeffGenerator(Operation):
     per batch, measured from the delay model's reference time; batch b is then steered with
     ``delay + delay_rate*t_b`` and ``phase + phase_rate*t_b`` (the native precursor's time-varying form,
     beamformer_coefficient_generator/BeamformerKernels.cu:25-35).
+    ``beam_weights`` (attribute, default None): real weights of shape (n_beams, n_ants) multiplied into the
+    coefficients -- the payload of the control plane's ``?beam-weights`` request (ngkcs/ngkcs/corr3_servlet.py:140).
     """
 
     def __init__(self, template: CoeffGeneratorTemplate, command_queue) -> None:
         super().__init__(command_queue)
         self.template = template
         self.batch_times = None
+        self.beam_weights = None
         self.slots["delay_vals"] = IOSlot(dimensions=template.delay_vals_data_dimensions, dtype=np.float32)
         self.slots["outCoeffs"] = IOSlot(dimensions=template.coeff_data_dimensions, dtype=np.float32)
 
@@ -74,4 +96,4 @@ class CoeffGenerator(Operation):
         t = self.template
         _capi.coeffs(self.buffer("delay_vals").buffer, self.buffer("outCoeffs").buffer, t.n_batches, t.n_pols,
                      t.n_channels_per_stream, t.n_channels, t.n_ants, t.n_beams, t.xeng_id, t.sample_period,
-                     self.command_queue.stream, batch_dt=self.batch_times)
+                     self.command_queue.stream, batch_dt=self.batch_times, weights=_device_weights(self))

@@ -82,7 +82,7 @@ int dcbf_coeffs(const float* delay_vals, float* coeffs, int B, int P, int C, int
         return DCBF_ERR_INVALID_ARG;
     if (!aligned16(delay_vals) || !aligned16(coeffs)) return DCBF_ERR_INVALID_ARG;
     if (int e = check_device()) return e;
-    return launch_coeffs(delay_vals, coeffs, B, P, C, N, A, M, xeng_id, sample_period, nullptr,
+    return launch_coeffs(delay_vals, coeffs, B, P, C, N, A, M, xeng_id, sample_period, nullptr, nullptr,
                          static_cast<cudaStream_t>(stream));
 }
 
@@ -94,7 +94,19 @@ int dcbf_coeffs_tv(const float* delay_vals, float* coeffs, int B, int P, int C, 
     if (!aligned16(delay_vals) || !aligned16(coeffs)) return DCBF_ERR_INVALID_ARG;
     if (B > DCBF_MAX_TV_BATCHES) return DCBF_ERR_UNSUPPORTED;
     if (int e = check_device()) return e;
-    return launch_coeffs(delay_vals, coeffs, B, P, C, N, A, M, xeng_id, sample_period, batch_dt_s,
+    return launch_coeffs(delay_vals, coeffs, B, P, C, N, A, M, xeng_id, sample_period, batch_dt_s, nullptr,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int dcbf_coeffs_ex(const float* delay_vals, float* coeffs, int B, int P, int C, int N, int A, int M, int xeng_id,
+                   double sample_period, const double* batch_dt_s, const float* beam_weights, dcbf_stream_t stream) {
+    if (!delay_vals || !coeffs || B <= 0 || P <= 0 || C <= 0 || N <= 0 || A <= 0 || M <= 0 || xeng_id < 0 ||
+        !(sample_period > 0.0))
+        return DCBF_ERR_INVALID_ARG;
+    if (!aligned16(delay_vals) || !aligned16(coeffs)) return DCBF_ERR_INVALID_ARG;
+    if (batch_dt_s && B > DCBF_MAX_TV_BATCHES) return DCBF_ERR_UNSUPPORTED;
+    if (int e = check_device()) return e;
+    return launch_coeffs(delay_vals, coeffs, B, P, C, N, A, M, xeng_id, sample_period, batch_dt_s, beam_weights,
                          static_cast<cudaStream_t>(stream));
 }
 
@@ -150,6 +162,27 @@ unsigned long long dcbf_fused_q8_bytes(int B, int A, int C, int T, int M) {
     const unsigned long long dv = 1ull * C * M * A * 16;
     const unsigned long long out = 1ull * B * kPols * C * T * M * 2;
     return in + dv + out + 4ull * M;
+}
+
+int dcbf_fused_ex(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T,
+                  int M, int xeng_id, double sample_period, const dcbf_fused_options* opts, unsigned flags,
+                  dcbf_stream_t stream) {
+    dcbf_fused_options o{};
+    if (opts) {
+        if (opts->struct_size < sizeof(size_t) || opts->struct_size > sizeof(o)) return DCBF_ERR_INVALID_ARG;
+        memcpy(&o, opts, opts->struct_size);  // older, shorter structs leave the newer fields zero
+    }
+    const bool q8 = o.beams_q8 != nullptr;
+    if (!samples || !delay_vals || (!beams && !q8) || (q8 && !o.beam_gains) || B <= 0 || A <= 0 || C <= 0 || N <= 0 ||
+        M <= 0 || xeng_id < 0 || bad_t(T) || !(sample_period > 0.0))
+        return DCBF_ERR_INVALID_ARG;
+    if (!aligned16(samples) || !aligned16(delay_vals) || !aligned16(q8 ? static_cast<void*>(o.beams_q8) : beams))
+        return DCBF_ERR_INVALID_ARG;
+    if (o.batch_dt_s && B > DCBF_MAX_TV_BATCHES) return DCBF_ERR_UNSUPPORTED;
+    if (int e = check_device()) return e;
+    const QuantisedOut qo{o.beams_q8, o.beam_gains, o.saturated};
+    return launch_fused(samples, delay_vals, beams, B, A, C, N, T, M, static_cast<long long>(C) * xeng_id, sample_period,
+                        o.batch_dt_s, flags, static_cast<cudaStream_t>(stream), q8 ? &qo : nullptr, o.beam_weights);
 }
 
 int dcbf_fused_status(int* role, int* barrier, int* block) {

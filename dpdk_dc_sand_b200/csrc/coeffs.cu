@@ -39,7 +39,7 @@ struct BatchTimes {
 __global__ void __launch_bounds__(kThreads)
 coeffs_kernel(const float4* __restrict__ delay_vals, float* __restrict__ coeffs, int n_batches, int n_pols, int C, int A,
               int M, int chan_offset, double half_n, double denom, int tiles_a, int tiles_m,
-              const __grid_constant__ BatchTimes times) {
+              const __grid_constant__ BatchTimes times, const float* __restrict__ weights) {
     __shared__ float2 cs[kTile][kTile + 1];  // [beam][ant] -> (cos, sin)
 
     const long long blk = blockIdx.x;
@@ -74,6 +74,11 @@ coeffs_kernel(const float4* __restrict__ delay_vals, float* __restrict__ coeffs,
                 const double rot = __dsub_rn(initial, centre);
                 double sn, cn;
                 sincos(rot, &sn, &cn);
+                if (weights) {  // real per-(beam, antenna) weight (?beam-weights), applied in float64 before rounding
+                    const double w = static_cast<double>(__ldg(weights + static_cast<size_t>(m) * A + a));
+                    sn = __dmul_rn(sn, w);
+                    cn = __dmul_rn(cn, w);
+                }
                 cs[mi][lane] = make_float2(static_cast<float>(cn), static_cast<float>(sn));
             }
         }
@@ -102,7 +107,7 @@ coeffs_kernel(const float4* __restrict__ delay_vals, float* __restrict__ coeffs,
 }  // namespace
 
 int launch_coeffs(const float* delay_vals, float* coeffs, int B, int P, int C, int N, int A, int M, int xeng_id,
-                  double sample_period, const double* batch_dt_s, cudaStream_t s) {
+                  double sample_period, const double* batch_dt_s, const float* beam_weights, cudaStream_t s) {
     BatchTimes times{};
     if (batch_dt_s) {
         if (B > DCBF_MAX_TV_BATCHES) return DCBF_ERR_UNSUPPORTED;
@@ -116,7 +121,7 @@ int launch_coeffs(const float* delay_vals, float* coeffs, int B, int P, int C, i
     const double half_n = static_cast<double>(N) / 2.0;           // python: (n_channels / 2)
     coeffs_kernel<<<static_cast<unsigned>(n_blocks), kThreads, 0, s>>>(
         reinterpret_cast<const float4*>(delay_vals), coeffs, B, P, C, A, M, C * xeng_id, half_n, denom, tiles_a, tiles_m,
-        times);
+        times, beam_weights);
     DCBF_CHECK_LAUNCH("coeffs_kernel");
     return DCBF_OK;
 }

@@ -35,7 +35,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int launch_reorder(const uint8_t* samples, uint8_t* reordered, int B, int A, int C, int T, cudaStream_t s);
 // batch_dt_s: NULL (static steering) or B host doubles (seconds since the delay model's reference time)
 int launch_coeffs(const float* delay_vals, float* coeffs, int B, int P, int C, int N, int A, int M, int xeng_id,
-                  double sample_period, const double* batch_dt_s, cudaStream_t s);
+                  double sample_period, const double* batch_dt_s, const float* beam_weights, cudaStream_t s);
 int launch_beamform(const uint8_t* reordered, const float* coeffs, float* beams, int B, int C, int T, int A, int M,
                     unsigned flags, cudaStream_t s);
 // Requantised-output variant of the fused kernel (dcbf_fused_q8): int8 beams, per-beam gains, saturation counter.
@@ -47,7 +47,7 @@ struct QuantisedOut {
 // first_chan = absolute F-engine channel of local channel 0 (n_chans * xeng_id for a whole stream).
 int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T,
                  int M, long long first_chan, double sample_period, const double* batch_dt_s, unsigned flags,
-                 cudaStream_t s, const QuantisedOut* q8 = nullptr);
+                 cudaStream_t s, const QuantisedOut* q8 = nullptr, const float* beam_weights = nullptr);
 int fused_status(int* role, int* barrier, int* block);
 void fused_set_profile_buffer(unsigned long long* dev_ptr);
 void fused_tiling(int A, int M, unsigned flags, int* kb_count, int* nt, int* nt_count);

@@ -79,6 +79,7 @@ struct FusedParams {
     float* out;
     int8_t* out_q8;                 // non-null: requantised int8 beams instead of float32 (dcbf_fused_q8)
     const float* gains;             // [M] per-beam quantisation gain (q8 only)
+    const float* weights;           // optional [M][A] real per-(beam, antenna) weights folded into the coefficients
     unsigned long long* saturated;  // optional count of clipped values (q8 only)
     int* status;  // [0]=error code, [1]=role, [2]=barrier id, [3]=blockIdx
     int* sched;   // [0]=next channel counter (beyond the first gridDim.x), [1]=finished CTAs; self-resetting
@@ -857,26 +858,35 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         if (!ok) break;
                         // antennas beyond A were zero-filled by the TMA box: byte 0 -> value 0 (u8), and
                         // 0 ^ 0x80 - 128 -> 0 (i8), so the K padding of the operand needs no special case
+                        unsigned long long tc0 = 0, tc1 = 0;
+                        if (kProf && prof_lane) tc0 = global_ns();
                         const uint32_t src = raw_base + rs * kRawStageBytes + t * 4;
                         const uint32_t dst0 = aop_base + as * kAopStageBytes + t * 64;
+                        // all 16 loads first (the volatile shared-memory accesses keep their program order, so
+                        // interleaving them with the stores would expose the load latency once per chunk)
+                        uint32_t w[kSlabAnts];
+#pragma unroll
+                        for (int i = 0; i < kSlabAnts; ++i) w[i] = ld_shared_u32(src + i * (kTileT * 4));
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            uint32_t w[4];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) w[i] = ld_shared_u32(src + (4 * j + i) * (kTileT * 4)) ^ flip;
+                            for (int i = 0; i < 4; ++i) w[4 * j + i] ^= flip;
                             const uint32_t off = (static_cast<uint32_t>(j) ^ sw) << 4;
-                            st_shared_v4(dst0 + off, bytes_to_half2(w[0], 0x4140u, bias), bytes_to_half2(w[1], 0x4140u, bias),
-                                         bytes_to_half2(w[2], 0x4140u, bias), bytes_to_half2(w[3], 0x4140u, bias));
-                            st_shared_v4(dst0 + kAopTileBytes + off, bytes_to_half2(w[0], 0x4342u, bias),
-                                         bytes_to_half2(w[1], 0x4342u, bias), bytes_to_half2(w[2], 0x4342u, bias),
-                                         bytes_to_half2(w[3], 0x4342u, bias));
+                            st_shared_v4(dst0 + off, bytes_to_half2(w[4 * j], 0x4140u, bias), bytes_to_half2(w[4 * j + 1], 0x4140u, bias),
+                                         bytes_to_half2(w[4 * j + 2], 0x4140u, bias), bytes_to_half2(w[4 * j + 3], 0x4140u, bias));
+                            st_shared_v4(dst0 + kAopTileBytes + off, bytes_to_half2(w[4 * j], 0x4342u, bias),
+                                         bytes_to_half2(w[4 * j + 1], 0x4342u, bias), bytes_to_half2(w[4 * j + 2], 0x4342u, bias),
+                                         bytes_to_half2(w[4 * j + 3], 0x4342u, bias));
                         }
+                        if (kProf && prof_lane) tc1 = global_ns();
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
                             mbar_arrive(bar(kAopFull + as));
                             mbar_arrive(bar(kRawEmpty + rs));
                         }
+                        if (kProf && prof_lane)  // slot 2: (LDS + convert + STS) | (fence + arrive) << 32
+                            ctl->wait_ns[kRoleConvert][2] += (tc1 - tc0) | ((global_ns() - tc1) << 32);
                     }
     } else if (warp < kCoeffWarp0 + kCoeffWarps) {
         // =================================== steering coefficients ===================================
@@ -993,8 +1003,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             const double scale = (static_cast<double>(c) + prm.chan_centre) * prm.turns_per_delay;  // half-turns per second of delay
             const float s_hi = static_cast<float>(scale), s_lo = static_cast<float>(scale - static_cast<double>(s_hi));
             float dt_hi = 0.f, dt_lo = 0.f;
+            const float* w_tile = nullptr;
             // one (beam, antenna) entry -> four 32-bit words of the B tile at d0 (row 2m) and d1 (row 2m+1)
-            auto emit = [&](const Dv& dv, uint32_t d0) {
+            auto emit = [&](const Dv& dv, uint32_t d0, int e) {
                 float r, small, sn, cs;
                 if constexpr (kTv) {
                     float d_hi, d_lo, ph_hi, ph_lo;
@@ -1005,6 +1016,11 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     steer_phase<false>(dv.x, 0.f, dv.y, 0.f, s_hi, s_lo, scale, &r, &small);
                 }
                 sincospi_reduced(r, small, &sn, &cs);
+                if (w_tile) {  // ?beam-weights: real weight of this (beam, antenna); the table is tiny and stays in L1/L2
+                    const float w = __ldg(w_tile + e);
+                    cs *= w;
+                    sn *= w;
+                }
                 // fp16 hi + fp16 residual of (cos, sin)
                 const uint32_t hi = pack_half2(cs, sn);
                 const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
@@ -1032,6 +1048,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 const uint32_t bb = step % kBopBufs;
                 const int m0 = it * mt;
                 const int entries = min(mt, M - m0) * A;
+                w_tile = prm.weights ? prm.weights + static_cast<size_t>(m0) * A : nullptr;  // entry e <-> [m0 + e / A][e % A]
                 bool waited = false;
                 const uint32_t buf = bop_base + bb * kBopBufBytes;
                 int ml = ml_first, a = a_first;
@@ -1051,12 +1068,12 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     if (fast_addr) {
 #pragma unroll
                         for (int u = 0; u < kBatch; ++u)
-                            if (e0 + u * kStride < entries) emit(v[u], d_fast + static_cast<uint32_t>(u) * d_step);
+                            if (e0 + u * kStride < entries) emit(v[u], d_fast + static_cast<uint32_t>(u) * d_step, e0 + u * kStride);
                         d_fast += kBatch * d_step;
                     } else {
 #pragma unroll
                         for (int u = 0; u < kBatch; ++u) {
-                            if (e0 + u * kStride < entries) emit(v[u], b_addr(buf, ml, a));
+                            if (e0 + u * kStride < entries) emit(v[u], b_addr(buf, ml, a), e0 + u * kStride);
                             ml += dm;
                             a += da;
                             if (a >= A) {
@@ -1163,10 +1180,11 @@ static int get_encode_fn(EncodeTiledFn* out) {
 
 int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T,
                  int M, long long first_chan, double sample_period, const double* batch_dt_s, unsigned flags,
-                 cudaStream_t s, const QuantisedOut* q8) {
+                 cudaStream_t s, const QuantisedOut* q8, const float* beam_weights) {
     FusedParams p{};
     p.dv = reinterpret_cast<const float4*>(delay_vals);
     p.out = beams;
+    p.weights = beam_weights;
     if (q8) {
         p.out_q8 = q8->beams;
         p.gains = q8->gains;

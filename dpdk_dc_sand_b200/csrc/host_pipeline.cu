@@ -83,7 +83,7 @@ static int run_plan(HostPlan* p, const uint8_t* h_samples, const float* h_dv, vo
         const long long first_chan = static_cast<long long>(p->C) * p->xeng_id + c0;
         const QuantisedOut qo{reinterpret_cast<int8_t*>(s.beams), p->gains, p->saturated};
         if (int e = launch_fused(s.samples, s.delay_vals, s.beams, p->B, p->A, cc, p->N, p->T, p->M, first_chan,
-                                 p->sample_period, nullptr, p->flags, s.stream, q8 ? &qo : nullptr))
+                                 p->sample_period, nullptr, p->flags, s.stream, q8 ? &qo : nullptr, nullptr))
             return e;
         DCBF_CUDA_TRY(cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(h_beams) + c0 * beam_chan, p->C * beam_chan, s.beams,
                                         cc * beam_chan, cc * beam_chan, static_cast<size_t>(p->B) * kPols,

@@ -121,6 +121,30 @@ int dcbf_fused_q8(const uint8_t* samples, const float* delay_vals, const float* 
 /* Algorithmic HBM bytes of one dcbf_fused_q8 call (in + delay_vals + gains + int8 out). */
 unsigned long long dcbf_fused_q8_bytes(int n_batches, int n_ants, int n_chans, int n_samples, int n_beams);
 
+/* General form of the fused call: every optional feature through one options block (zero-initialise, set
+ * struct_size = sizeof(dcbf_fused_options), fill what is needed; NULL opts == dcbf_fused).
+ *   batch_dt_s    HOST double[n_batches]  per-heap time offsets, as dcbf_fused_tv
+ *   beam_weights  DEVICE float[n_beams][n_ants]  real weight of every input on every beam, multiplied into the
+ *                 steering coefficient -- what the control plane's `?beam-weights <stream> w_0 .. w_{A-1}` request carries
+ *                 (reference: ngkcs/ngkcs/corr3_servlet.py:140-153, which only forwards it); update it between calls
+ *                 like delay_vals, nothing is cached
+ *   beams_q8 / beam_gains / saturated   int8 output as dcbf_fused_q8 (then `beams` may be NULL) */
+typedef struct dcbf_fused_options {
+    size_t struct_size;
+    const double* batch_dt_s;
+    const float* beam_weights;
+    const float* beam_gains;
+    int8_t* beams_q8;
+    unsigned long long* saturated;
+} dcbf_fused_options;
+int dcbf_fused_ex(const uint8_t* samples, const float* delay_vals, float* beams, int n_batches, int n_ants,
+                  int n_chans, int n_chans_total, int n_samples, int n_beams, int xeng_id, double sample_period,
+                  const dcbf_fused_options* opts, unsigned flags, dcbf_stream_t stream);
+/* dcbf_coeffs with the same options (either pointer may be NULL). */
+int dcbf_coeffs_ex(const float* delay_vals, float* coeffs, int n_batches, int n_pols, int n_chans,
+                   int n_chans_total, int n_ants, int n_beams, int xeng_id, double sample_period,
+                   const double* batch_dt_s, const float* beam_weights, dcbf_stream_t stream);
+
 /* Blocks until prior work on the current device is done, then returns the status the last dcbf_fused kernels
  * left behind: DCBF_OK, or DCBF_ERR_TIMEOUT if an in-kernel pipeline wait exceeded its 2 s guard (the kernel
  * then exits early instead of hanging; *role / *barrier / *block say who waited on what).  Clears the status. */

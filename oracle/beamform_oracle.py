@@ -118,6 +118,7 @@ def steering_coeffs(
     out_dtype=np.float32,
     batch_dt=None,
     _dt=None,
+    weights=None,
 ) -> np.ndarray:
     """(C, M, A, 4) f32 -> (B, P, C, 2A, 2M).  coeff_generator_cpu.py:120-186.
 
@@ -131,7 +132,7 @@ def steering_coeffs(
             raise ValueError("batch_dt needs one entry per batch")
         per_batch = [
             steering_coeffs(delay_vals, 1, n_pols, n_channels_per_stream, n_channels, n_ants, n_beams, xeng_id,
-                            sample_period, out_dtype=out_dtype, batch_dt=None, _dt=float(t))
+                            sample_period, out_dtype=out_dtype, batch_dt=None, _dt=float(t), weights=weights)
             for t in batch_dt
         ]
         return np.concatenate(per_batch, axis=0)
@@ -139,6 +140,9 @@ def steering_coeffs(
     rot = rot.astype(np.float64)  # math.cos/math.sin take a C double
     cos = np.cos(rot).transpose(0, 2, 1)  # (C, A, M)
     sin = np.sin(rot).transpose(0, 2, 1)
+    if weights is not None:  # real weight per (beam, antenna): the ?beam-weights request (ngkcs/ngkcs/corr3_servlet.py:140)
+        w = np.asarray(weights, np.float64).T[None]  # (1, A, M)
+        cos, sin = cos * w, sin * w
     blk = np.empty((n_channels_per_stream, n_ants, 2, n_beams, 2), dtype=np.float64)
     blk[:, :, 0, :, 0] = cos
     blk[:, :, 0, :, 1] = sin
@@ -237,6 +241,7 @@ def beamform_pipeline(
     signed_input: bool = False,
     acc_dtype=np.float64,
     batch_dt=None,
+    weights=None,
 ) -> np.ndarray:
     """(B,A,C,T,P,2) u8 + (C,M,A,4) f32 -> (B,P,C,T//16,16,2M) in ``acc_dtype``."""
     b, a, c, t, p, x = samples.shape
@@ -245,9 +250,10 @@ def beamform_pipeline(
     d = _as_real(re, signed_input, acc_dtype)
     if batch_dt is not None:
         co = steering_coeffs(delay_vals, b, 1, c, n_channels, a, m, xeng_id, sample_period, out_dtype=np.float64,
-                             batch_dt=batch_dt)
+                             batch_dt=batch_dt, weights=weights)
         return np.einsum("bpcksj,bcjn->bpcksn", d, co[:, 0].astype(acc_dtype), optimize=True)
-    co = steering_coeffs(delay_vals, 1, 1, c, n_channels, a, m, xeng_id, sample_period, out_dtype=np.float64)
+    co = steering_coeffs(delay_vals, 1, 1, c, n_channels, a, m, xeng_id, sample_period, out_dtype=np.float64,
+                         weights=weights)
     return np.einsum("bpcksj,cjn->bpcksn", d, co[0, 0].astype(acc_dtype), optimize=True)
 
 

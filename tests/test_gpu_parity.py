@@ -389,6 +389,71 @@ def test_q8_operator_and_host_plan(dropin):
     np.testing.assert_array_equal(host, got)
 
 
+def test_beam_weights(dropin):
+    """Next-row feature: per-(beam, antenna) real weights (the ?beam-weights payload) folded into the
+    coefficients, alone and together with per-heap times; fused == three-kernel chain == float64 oracle."""
+    from beamforming.beamform_op_sequence import OpSequenceTemplate
+
+    ctx, queue = dropin
+    b, a, c, t, m, n, xid = 2, 33, 6, 64, 5, 1024, 2
+    x = orc.make_samples(b, a, c, t, seed=71)
+    dv = _tv_delay_vals(c, m, a, seed=72)
+    w = np.random.default_rng(73).uniform(0.0, 2.0, (m, a)).astype(np.float32)
+    w[1, :] = 0.0  # a muted beam
+    for times in (None, [0.0, 2.5]):
+        ref = orc.beamform_pipeline(x, dv, n, xid, TS, batch_dt=times, weights=w)
+        outs = {}
+        for fused in (True, False):
+            op = OpSequenceTemplate(ctx, b, 2, c, n, t // 16, 16, a, m, xid, TS, t).instantiate(queue)
+            op.fused, op.materialize_intermediates, op.batch_times, op.beam_weights = fused, True, times, w
+            op.ensure_all_bound()
+            op.buffer("bufin_reorder").set(queue, x)
+            op.buffer("bufin_delay_vals").set(queue, dv)
+            op()
+            outs[fused] = op.buffer("bufout_mult").get(queue).astype(np.float64)
+            co = op.buffer("bufint_coeff").get(queue).astype(np.float64)
+            ref_co = orc.steering_coeffs(dv, b, 2, c, n, a, m, xid, TS, out_dtype=np.float64,
+                                         batch_dt=times if times else None, weights=w)
+            assert np.abs(co - ref_co).max() <= 2e-6  # weights up to 2
+        err = np.abs(outs[True] - ref)
+        assert np.all(err <= 2.0 * (2.0 ** -8 * _budget(x) + 1e-3)), f"max err {err.max()}"
+        assert np.abs(outs[True][:, :, :, :, :, 2:4]).max() == 0.0  # beam 1 is muted exactly
+        np.testing.assert_allclose(outs[True], outs[False], rtol=0, atol=float(_budget(x).max()) * 2.0 ** -5)
+
+
+def test_delay_model_updater_switches_at_a_heap_boundary(dropin):
+    """Double-buffered delay_vals / weights update: heaps launched before activate() use the old
+    model, heaps launched after it use the new one, and the upload runs on a side stream."""
+    from beamforming.beamform_op_sequence import OpSequenceTemplate
+    from dpdk_dc_sand_b200.delay_model import DelayModelUpdater
+
+    ctx, queue = dropin
+    b, a, c, t, m, n, xid = 1, 16, 9, 64, 4, 64, 0
+    x = orc.make_samples(b, a, c, t, seed=81)
+    dv0 = orc.make_delay_vals_random(c, m, a, seed=82)
+    dv1 = orc.make_delay_vals_random(c, m, a, seed=83)
+    w1 = np.random.default_rng(84).uniform(0.5, 1.5, (m, a)).astype(np.float32)
+    op = OpSequenceTemplate(ctx, b, 2, c, n, t // 16, 16, a, m, xid, TS, t).instantiate(queue)
+    op.ensure_all_bound()
+    op.buffer("bufin_reorder").set(queue, x)
+    op.buffer("bufin_delay_vals").set(queue, dv0)
+    upd = DelayModelUpdater(op)
+    assert not upd.activate()
+    upd.update(dv1, w1)  # uploads while ...
+    op()                 # ... this heap still sees model 0
+    out0 = op.buffer("bufout_mult").get(queue).astype(np.float64)
+    assert upd.activate()
+    op()
+    out1 = op.buffer("bufout_mult").get(queue).astype(np.float64)
+    assert np.all(np.abs(out0 - orc.beamform_pipeline(x, dv0, n, xid, TS)) <= _budget(x))
+    assert np.all(np.abs(out1 - orc.beamform_pipeline(x, dv1, n, xid, TS, weights=w1)) <= 1.5 * _budget(x))
+    upd.update(dv0)      # back again through the other buffer, weights stay
+    assert upd.activate()
+    op()
+    out2 = op.buffer("bufout_mult").get(queue).astype(np.float64)
+    assert np.all(np.abs(out2 - orc.beamform_pipeline(x, dv0, n, xid, TS, weights=w1)) <= 1.5 * _budget(x))
+
+
 def test_fused_matches_three_kernel_chain_and_materialises_intermediates(dropin):
     from beamforming.beamform_op_sequence import OpSequenceTemplate
 

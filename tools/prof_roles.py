@@ -10,7 +10,7 @@ from dpdk_dc_sand_b200 import _capi  # noqa: E402
 
 ROLES = {1: "producer", 2: "mma", 3: "epilogue", 4: "convert", 5: "coeff"}
 SLOTS = {1: ["raw_empty", "-", "-"], 2: ["bop_full", "acc_empty", "aop_full"], 3: ["acc_full", "store_wait", "tmem|sts+fence"],
-         4: ["raw_full", "aop_empty", "-"], 5: ["bop_empty", "-", "-"]}
+         4: ["raw_full", "aop_empty", "work|fence"], 5: ["bop_empty", "-", "-"]}
 
 
 def main():
@@ -47,7 +47,10 @@ def main():
     raw = prof.cpu().numpy().reshape(n_sm, 6, 4)
     ep2 = raw[:, 3, 2].copy()
     raw[:, 3, 2] = (ep2 & 0xffffffff) + (ep2 >> 32)
+    cv2 = raw[:, 4, 2].copy()
+    raw[:, 4, 2] = (cv2 & 0xffffffff) + (cv2 >> 32)
     p = raw.astype(np.float64) / 1e3  # us
+    print(f"  convert detail: lds+alu+sts {(cv2 & 0xffffffff).mean() / 1e3:.1f} us, fence+arrive {(cv2 >> 32).mean() / 1e3:.1f} us")
     print(f"  epilogue detail: tmem wait {(ep2 & 0xffffffff).mean() / 1e3:.1f} us, sts+fence {(ep2 >> 32).mean() / 1e3:.1f} us")
     print(f"A={A} C={C} T={T} M={M} B={B} flags={flags:#x}{' q8' if q8 else ''}: kernel {e0.elapsed_time(e1)*1e3:.1f} us; "
           f"per-role blocked time, mean over {n_sm} CTAs (us)")
