@@ -73,6 +73,20 @@ SIGNATURES["dcbf_fused_ex"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c
 SIGNATURES["dcbf_coeffs_ex"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_double, C.POINTER(C.c_double), C.c_void_p, C.c_void_p])
 
+SIGNATURES.update({
+    "dcbf_ingest_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong,
+                                     C.c_int]),
+    "dcbf_ingest_heap": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "dcbf_ingest_heap_ptr": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.POINTER(C.c_void_p)]),
+    "dcbf_ingest_heap_done": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int]),
+    "dcbf_ingest_pop": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong),
+                                  C.POINTER(C.c_int), C.c_void_p]),
+    "dcbf_ingest_release": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dcbf_ingest_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong),
+                                    C.POINTER(C.c_ulonglong)]),
+    "dcbf_ingest_destroy": (C.c_int, [C.c_void_p]),
+})
+
 _lib = None
 _lock = threading.Lock()
 
@@ -288,6 +302,68 @@ class HostPlan:
     def close(self) -> None:
         if self._h:
             load().dcbf_host_plan_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Ingest:
+    """dcbf_ingest_*: assembles F-engine heaps into ``(n_batches, n_ants, n_chans, n_samples, 2, 2)`` chunks."""
+
+    def __init__(self, n_chunks, n_batches, n_ants, n_chans, n_samples, timestamp_step, pinned=True):
+        self._h = C.c_void_p(None)
+        self.shape = (n_batches, n_ants, n_chans, n_samples, 2, 2)
+        self.heap_shape = (n_chans, n_samples, 2, 2)
+        check(load().dcbf_ingest_create(C.byref(self._h), n_chunks, n_batches, n_ants, n_chans, n_samples,
+                                        int(timestamp_step), 1 if pinned else 0), "dcbf_ingest_create")
+
+    def heap(self, timestamp, feng_id, payload) -> bool:
+        """Place one heap (any 8-bit array of ``heap_shape``); False if it was dropped (late / no free chunk)."""
+        import numpy as np
+
+        arr = np.ascontiguousarray(payload)
+        if arr.dtype.itemsize != 1 or tuple(arr.shape) != self.heap_shape:
+            raise ValueError(f"heap payload must be an 8-bit array of shape {self.heap_shape}")
+        st = load().dcbf_ingest_heap(self._h, int(timestamp), int(feng_id), arr.ctypes.data)
+        if st == ERR_UNSUPPORTED:
+            return False
+        check(st, "dcbf_ingest_heap")
+        return True
+
+    def pop(self, flush=False):
+        """Next finished chunk as ``(samples view, first_timestamp, present[B, A])`` or None.  The view aliases the
+        ring's memory: call ``release(samples)`` when done with it."""
+        import numpy as np
+
+        ptr, ts, missing = C.c_void_p(None), C.c_longlong(0), C.c_int(0)
+        present = np.zeros(self.shape[:2], np.uint8)
+        got = load().dcbf_ingest_pop(self._h, 1 if flush else 0, C.byref(ptr), C.byref(ts), C.byref(missing),
+                                     present.ctypes.data)
+        if got < 0:
+            check(got, "dcbf_ingest_pop")
+        if got == 0:
+            return None
+        n = int(np.prod(self.shape))
+        buf = (C.c_uint8 * n).from_address(ptr.value)
+        samples = np.frombuffer(buf, dtype=np.uint8).reshape(self.shape)
+        assert int(missing.value) == int(present.size - present.sum())
+        return samples, int(ts.value), present.astype(bool)
+
+    def release(self, samples) -> None:
+        check(load().dcbf_ingest_release(self._h, samples.ctypes.data), "dcbf_ingest_release")
+
+    def stats(self) -> dict:
+        a, b, c = C.c_ulonglong(0), C.c_ulonglong(0), C.c_ulonglong(0)
+        check(load().dcbf_ingest_stats(self._h, C.byref(a), C.byref(b), C.byref(c)), "dcbf_ingest_stats")
+        return {"late_or_dropped": int(a.value), "duplicate": int(b.value), "bad": int(c.value)}
+
+    def close(self) -> None:
+        if self._h:
+            load().dcbf_ingest_destroy(self._h)
             self._h = C.c_void_p(None)
 
     def __del__(self):

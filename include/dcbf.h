@@ -176,6 +176,33 @@ int dcbf_host_plan_run_q8(dcbf_host_plan_t plan, const uint8_t* samples, const f
                           unsigned long long* saturated);
 int dcbf_host_plan_destroy(dcbf_host_plan_t plan);
 
+/* ---- ingest: F-engine heaps -> [B][A][C][T][2][2] chunks in page-locked memory ---------------------------------
+ * The stage before the path (reference: fgpu_send_prototype/fgpu_send_prototype.py:20-22,55-60 defines the heap an
+ * F-engine sends: timestamp 0x1600, feng_id 0x4101, feng_raw 0x4300 = int8 [n_chans][n_samples][2][2];
+ * beamformer/README.md:5-6 the batch layout).  A ring of n_chunks chunks of n_batches consecutive heaps x n_ants;
+ * heaps are placed by (timestamp, feng_id) in any arrival order; n_chunks/2 chunks can be receiving at once, the
+ * rest hold finished chunks until released.  A chunk is finished when all its heaps have arrived, or when newer
+ * heaps push the window past it (missing heaps are zero-filled and reported).  No network code: the receive loop
+ * calls dcbf_ingest_heap (copy) or dcbf_ingest_heap_ptr + dcbf_ingest_heap_done (write in place).
+ * timestamp_step = ADC samples between consecutive heaps of one antenna; pinned = 0 uses ordinary memory (no GPU
+ * needed, for tests).  Thread-safe.  dcbf_ingest_heap returns DCBF_ERR_UNSUPPORTED for a heap that was dropped
+ * (too old, duplicate of a closed chunk, or no free chunk because the consumer is behind). */
+typedef void* dcbf_ingest_t;
+int dcbf_ingest_create(dcbf_ingest_t* ingest, int n_chunks, int n_batches, int n_ants, int n_chans, int n_samples,
+                       long long timestamp_step, int pinned);
+int dcbf_ingest_heap(dcbf_ingest_t ingest, long long timestamp, int feng_id, const void* payload);
+int dcbf_ingest_heap_ptr(dcbf_ingest_t ingest, long long timestamp, int feng_id, void** dst);
+int dcbf_ingest_heap_done(dcbf_ingest_t ingest, long long timestamp, int feng_id);
+/* Next finished chunk in time order: returns 1 and sets *samples (the `samples` argument of dcbf_host_plan_run),
+ * *first_timestamp, *n_missing and present[n_batches * n_ants] (each may be NULL); 0 if none is ready; flush != 0
+ * also hands out chunks that are still incomplete (end of stream).  Give the chunk back with dcbf_ingest_release. */
+int dcbf_ingest_pop(dcbf_ingest_t ingest, int flush, const uint8_t** samples, long long* first_timestamp,
+                    int* n_missing, uint8_t* present);
+int dcbf_ingest_release(dcbf_ingest_t ingest, const uint8_t* samples);
+int dcbf_ingest_stats(dcbf_ingest_t ingest, unsigned long long* n_late, unsigned long long* n_duplicate,
+                      unsigned long long* n_bad);
+int dcbf_ingest_destroy(dcbf_ingest_t ingest);
+
 /* Number of kernel launches this library has issued since load (all entry points); used by bench.py
  * to report gpu_launches. */
 unsigned long long dcbf_launch_count(void);

@@ -454,6 +454,33 @@ def test_delay_model_updater_switches_at_a_heap_boundary(dropin):
     assert np.all(np.abs(out2 - orc.beamform_pipeline(x, dv0, n, xid, TS, weights=w1)) <= 1.5 * _budget(x))
 
 
+def test_ingest_ring_feeds_the_host_plan(dropin):
+    """SURVEY 8f-3 end to end: heaps -> page-locked chunk (dcbf_ingest_*) -> dcbf_host_plan_run -> beams."""
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m, n, xid, step = 2, 6, 10, 32, 3, 64, 0, 4096
+    dv = orc.make_delay_vals_random(c, m, a, seed=92)
+    ing = _capi.Ingest(4, b, a, c, t, step, pinned=True)
+    plan = _capi.HostPlan(b, a, c, n, t, m, xid, TS, chunk_chans=4, n_slots=2)
+    rng = np.random.default_rng(93)
+    heaps = rng.integers(0, 256, (2 * b, a, c, t, 2, 2), dtype=np.uint8)
+    order = [(h, ant) for h in range(2 * b) for ant in range(a)]
+    rng.shuffle(order)
+    for h, ant in order:
+        assert ing.heap(h * step, ant, heaps[h, ant])
+    for k in range(2):
+        samples, ts, present = ing.pop()
+        assert ts == k * b * step and present.all()
+        out = np.zeros((b, 2, c, t // 16, 16, 2 * m), np.float32)
+        plan.run(samples, dv, out)
+        ref = orc.beamform_pipeline(heaps[k * b:(k + 1) * b], dv, n, xid, TS)
+        assert np.all(np.abs(out - ref) <= _budget(heaps[k * b:(k + 1) * b]))
+        ing.release(samples)
+    assert ing.pop() is None
+    plan.close()
+    ing.close()
+
+
 def test_fused_matches_three_kernel_chain_and_materialises_intermediates(dropin):
     from beamforming.beamform_op_sequence import OpSequenceTemplate
 

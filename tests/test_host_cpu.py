@@ -176,3 +176,49 @@ def test_channel_sharding_composes_to_full_band_gloo_world2():
     assert status == "ok", err
     assert shape == (1, 2, 8, 2, 16, 6)
     assert err < 1e-9  # same float64 arithmetic, channel offset carried by xeng_id
+
+
+def test_ingest_ring_assembles_heaps_in_any_order():
+    """The ingest stage (host C++, no GPU): heaps placed by (timestamp, feng_id) in shuffled order come out as
+    [B][A][C][T][2][2] chunks in time order; a lost heap is zero-filled and flagged once newer data forces its
+    chunk out; late and duplicate heaps are counted, never written."""
+    from dpdk_dc_sand_b200 import _capi
+
+    n_chunks, B, A, C_, T, step = 4, 2, 3, 2, 16, 8192
+    ing = _capi.Ingest(n_chunks, B, A, C_, T, step, pinned=False)
+    rng = np.random.default_rng(11)
+    n_heaps_t = 8  # 4 chunks of 2 heaps
+    truth = rng.integers(0, 256, (n_heaps_t, A, C_, T, 2, 2), dtype=np.uint8)
+    lost = (3, 1)  # (heap number, antenna) that never arrives
+    popped = []
+
+    def drain(flush=False):
+        while True:
+            got = ing.pop(flush)
+            if got is None:
+                return
+            samples, ts, present = got
+            popped.append((ts, samples.copy(), present.copy()))
+            ing.release(samples)
+
+    for pair in range(0, n_heaps_t, 4):  # feed two chunks' worth at a time, shuffled inside
+        order = [(h, a) for h in range(pair, min(pair + 4, n_heaps_t)) for a in range(A) if (h, a) != lost]
+        rng.shuffle(order)
+        for h, a in order:
+            assert ing.heap(h * step, a, truth[h, a])
+        drain()
+    assert not ing.heap(0, 0, truth[0, 0])            # chunk 0 is long gone: dropped, not written
+    assert ing.stats()["late_or_dropped"] == 1
+    with pytest.raises(ValueError):
+        ing.heap(step // 2, 0, truth[0, 0])           # not a heap boundary
+    drain(flush=True)
+    assert [p[0] for p in popped] == [0, 2 * step, 4 * step, 6 * step]  # time order
+    for k, (ts, samples, present) in enumerate(popped):
+        want = truth[2 * k:2 * k + 2].copy()
+        exp_present = np.ones((B, A), bool)
+        if k == 1:
+            want[1, 1] = 0
+            exp_present[1, 1] = False
+        np.testing.assert_array_equal(present, exp_present)
+        np.testing.assert_array_equal(samples, want)
+    ing.close()
