@@ -93,6 +93,7 @@ struct FusedParams {
     int parts;       // 2 = fp16 hi+lo coefficients, 1 = fp16 hi only
     int signed_in;
     int tma_store;   // 1: epilogue through shared memory + TMA tensor stores; 0: st.global from registers
+    int merged;      // hi and lo coefficient rows form ONE N = 2 nt tile per MMA (nt <= 64); the epilogue adds the halves
     int q8_wide;     // q8 only: the N tile is the whole output row (32 / 64 / 128 bytes): one box per 32 rows
     int sb_count;    // coefficient sets per (channel, N tile): 1, or B with time-varying steering
     int ub;          // batches sharing one coefficient set: B, or 1 with time-varying steering
@@ -471,7 +472,7 @@ __device__ __forceinline__ uint32_t quantise4(const uint32_t (&r)[32], int j, fl
 // ------------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------------
-template <bool kProf, bool kTv, bool kQ8>
+template <bool kProf, bool kTv, bool kQ8, bool kMerged>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_constant__ CUtensorMap tm_in,
                       const __grid_constant__ CUtensorMap tm_out) {
@@ -580,7 +581,11 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         }
     } else if (warp == kMmaWarp) {
         // =================================== MMA issuer ===================================
-        const uint32_t idesc = make_idesc_f16(nt);
+        // merged: the lo rows follow the hi rows in the B tile, so one N = 2 nt MMA replaces two N = nt MMAs and the
+        // A tile is read from shared memory once; its two halves land in adjacent TMEM column ranges
+        const int mma_parts = kMerged ? 1 : parts;
+        const uint32_t acc_cols = static_cast<uint32_t>(kMerged ? 2 * nt : nt);  // TMEM columns per (buffer, pol)
+        const uint32_t idesc = make_idesc_f16(static_cast<int>(acc_cols));
         const uint32_t a_lo0 = desc_lo(aop_base), b_lo0 = desc_lo(bop_base);
         const uint32_t part_lo = part_bytes >> 4, kb_lo = bop_kb_bytes >> 4;
         uint32_t slab = 0, unit = 0, step = 0;
@@ -594,7 +599,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     ok = mbar_wait<kProf>(bar(kAccEmpty + ab), ((unit / kAccBufs) & 1u) ^ 1u, ctl, prm.status, kRoleMma, kAccEmpty + ab, ps + 1);
                     if (!ok) break;
                     tc_fence_after();
-                    const uint32_t d_tmem0 = tmem_base + ab * kPols * static_cast<uint32_t>(nt);
+                    const uint32_t d_tmem0 = tmem_base + ab * kPols * acc_cols;
                     for (int s = 0; s < prm.slab_count; ++s, ++slab) {
                         const uint32_t as = slab % kAopStages;
                         ok = mbar_wait<kProf>(bar(kAopFull + as), (slab / kAopStages) & 1u, ctl, prm.status, kRoleMma, kAopFull + as, ps + 2);
@@ -608,10 +613,10 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         if (elect_one()) {
 #pragma unroll
                             for (int p = 0; p < kPols; ++p) {
-                                const uint32_t d_tmem = d_tmem0 + p * static_cast<uint32_t>(nt);
+                                const uint32_t d_tmem = d_tmem0 + p * acc_cols;
 #pragma unroll
                                 for (int part = 0; part < 2; ++part) {
-                                    if (part < parts) {
+                                    if (part < mma_parts) {
 #pragma unroll
                                         for (int k = 0; k < 2; ++k) {
                                             if (k < k_steps)
@@ -637,6 +642,20 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         const int q = warp & 3;  // TMEM lane quarter this warp may read
         const uint32_t ost = ost_base + static_cast<uint32_t>(q) * (2 * kOutBoxBytes);
         const uint32_t gain_tab = ost + kOutBoxBytes;  // q8 only: its four 1 KiB boxes live in the first half
+        constexpr bool merged = kMerged;  // a specialisation: the extra 32 registers must not weigh on the wide-tile build
+        const uint32_t acc_cols = static_cast<uint32_t>(merged ? 2 * nt : nt);  // TMEM columns per (buffer, pol)
+        // 32 accumulator columns of this thread's row; merged tiles keep the hi and lo coefficient parts in two
+        // column ranges nt apart, which are summed here (the wait for both loads is then already done)
+        auto ld32 = [&](uint32_t taddr, uint32_t (&r)[32]) {
+            tmem_ld_32x32b_x32(taddr, r);
+            if constexpr (merged) {
+                uint32_t l[32];
+                tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(nt), l);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(l[i]));
+            }
+        };
         uint32_t unit = 0, box = 0;
         int clipped = 0;
         bool ok = true;
@@ -664,16 +683,15 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         tc_fence_after();
                         const int t0 = h * kTileT;
                         if constexpr (kQ8) {
-                            // requantised output: thread = row, 32 columns -> 32 bytes per row.  Two TMEM reads are
-                            // in flight per wait and four 1 KiB staging boxes rotate, so neither the TMEM latency nor
-                            // the bulk stores' shared-memory reads sit on the critical path.
+                            // requantised output: thread = row, 32 columns -> 32 bytes per row; four 1 KiB staging boxes
+                            // rotate so the bulk stores' shared-memory reads stay off the critical path.
                             const int row0 = t0 + 32 * q;
                             if (prm.q8_wide) {
                                 // whole output rows (nt = 2M bytes: 32, 64 or 128) -> one box of 32 rows per pol:
                                 // 4x fewer, 4x longer rows for the TMA store engine than 32-byte pieces
                                 const uint32_t cmask = static_cast<uint32_t>(nt >> 4) - 1u;  // swizzle span = row length
                                 for (int p = 0; p < kPols && row0 < T; ++p, ++box) {
-                                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kPols + p) * static_cast<uint32_t>(nt);
+                                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kPols + p) * acc_cols;
                                     const uint32_t sb = ost + (box & 1u) * kOutBoxBytes;
                                     bulk_wait_group_read<1>();  // (issuing lane) the store that last read this box is done
                                     __syncwarp();
@@ -695,7 +713,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                     };
                                     for (int cb = 0; cb < nt; cb += 32) {
                                         uint32_t r[32];
-                                        tmem_ld_32x32b_x32(taddr + cb, r);
+                                        ld32(taddr + cb, r);
                                         tmem_wait_ld();
                                         put32(r, cb);
                                     }
@@ -741,30 +759,27 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                 }
                             };
                             for (int p = 0; p < kPols; ++p) {
-                                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kPols + p) * static_cast<uint32_t>(nt);
+                                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kPols + p) * acc_cols;
                                 const int plane = (b * kPols + p) * C + c;
-                                for (int cb = 0; cb < nt && row0 < T && n0 + cb < N2; cb += 64, box += 2) {
-                                    const bool two = cb + 32 < nt && n0 + cb + 32 < N2;
-                                    uint32_t ra[32], rb[32];
-                                    tmem_ld_32x32b_x32(taddr + cb, ra);
-                                    if (two) tmem_ld_32x32b_x32(taddr + cb + 32, rb);
-                                    bulk_wait_group_read<2>();  // (issuing lane) the two boxes used four blocks ago are free
+                                for (int cb = 0; cb < nt && row0 < T && n0 + cb < N2; cb += 32, ++box) {
+                                    uint32_t r[32];
+                                    ld32(taddr + cb, r);
+                                    bulk_wait_group_read<3>();  // (issuing lane) the box used four blocks ago is free
                                     __syncwarp();
                                     tmem_wait_ld();
-                                    emit_block(ra, cb, plane, ost + (box & 3u) * 1024u);
-                                    if (two) emit_block(rb, cb + 32, plane, ost + ((box + 1) & 3u) * 1024u);
+                                    emit_block(r, cb, plane, ost + (box & 3u) * 1024u);
                                 }
                             }
                         } else if (prm.tma_store) {
                             const int row0 = t0 + 32 * q;  // this warp's 32 rows of the tile
                             for (int p = 0; p < kPols; ++p) {
-                                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kPols + p) * static_cast<uint32_t>(nt);
+                                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kPols + p) * acc_cols;
                                 const int plane = (b * kPols + p) * C + c;
                                 for (int cb = 0; cb < nt && row0 < T && n0 + cb < N2; cb += 32, ++box) {
                                     uint32_t r[32];
                                     unsigned long long tp0 = 0, tp1 = 0, tp2 = 0;
                                     if (kProf && prof_lane) tp0 = global_ns();
-                                    tmem_ld_32x32b_x32(taddr + cb, r);
+                                    ld32(taddr + cb, r);
                                     const uint32_t sb = ost + (box & 1u) * kOutBoxBytes;
                                     bulk_wait_group_read<1>();  // (issuing lane) the store that last read this box is done
                                     __syncwarp();
@@ -789,7 +804,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                             }
                         } else {
                             for (int p = 0; p < kPols; ++p) {
-                                const uint32_t col0 = (ab * kPols + p) * static_cast<uint32_t>(nt);
+                                const uint32_t col0 = (ab * kPols + p) * acc_cols;
                                 float* tile_out = prm.out + (((static_cast<size_t>(b) * kPols + p) * C + c) * static_cast<size_t>(T) + t0) * N2 + n0;
 #pragma unroll 1
                                 for (int half = 0; half < 2; ++half) {
@@ -802,6 +817,13 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                     for (; cb + 64 <= nt; cb += 64) {
                                         uint32_t r[32];
                                         tmem_ld_16x256b_x8(taddr + cb, r);
+                                        if constexpr (merged) {
+                                            uint32_t l[32];
+                                            tmem_ld_16x256b_x8(taddr + cb + static_cast<uint32_t>(nt), l);
+                                            tmem_wait_ld();
+#pragma unroll
+                                            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(l[i]));
+                                        }
                                         tmem_wait_ld();
 #pragma unroll
                                         for (int i = 0; i < 8; ++i) {
@@ -815,6 +837,13 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                     for (; cb < nt; cb += 16) {
                                         uint32_t r[8];
                                         tmem_ld_16x256b_x2(taddr + cb, r);
+                                        if constexpr (merged) {
+                                            uint32_t l[8];
+                                            tmem_ld_16x256b_x2(taddr + cb + static_cast<uint32_t>(nt), l);
+                                            tmem_wait_ld();
+#pragma unroll
+                                            for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(l[i]));
+                                        }
                                         tmem_wait_ld();
 #pragma unroll
                                         for (int i = 0; i < 2; ++i) {
@@ -1117,6 +1146,17 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
 }
 
 constexpr int kSchedSlots = 64;  // concurrent launches per device that can share the pool without interfering
+using KernelFn = void (*)(const FusedParams, const CUtensorMap, const CUtensorMap);
+// index = 6 * q8 + 2 * variant (0 plain, 1 profiling, 2 time-varying) + merged
+KernelFn const kKernels[12] = {
+    fused_beamform_kernel<false, false, false, false>, fused_beamform_kernel<false, false, false, true>,
+    fused_beamform_kernel<true, false, false, false>,  fused_beamform_kernel<true, false, false, true>,
+    fused_beamform_kernel<false, true, false, false>,  fused_beamform_kernel<false, true, false, true>,
+    fused_beamform_kernel<false, false, true, false>,  fused_beamform_kernel<false, false, true, true>,
+    fused_beamform_kernel<true, false, true, false>,   fused_beamform_kernel<true, false, true, true>,
+    fused_beamform_kernel<false, true, true, false>,   fused_beamform_kernel<false, true, true, true>,
+};
+
 int* g_status_dev[64] = {};  // per-device: 4-int status block + kSchedSlots x {next, done} channel counters
 unsigned long long* g_prof_dev = nullptr;  // set by fused_set_profile_buffer (developer aid)
 
@@ -1211,6 +1251,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
             p.dt_lo[b] = static_cast<float>(batch_dt_s[b] - static_cast<double>(p.dt_hi[b]));
         }
     }
+    p.merged = p.parts == 2 && p.nt <= 64;
     p.tma_store = !(flags & DCBF_FLAG_DEBUG_DIRECT_EPILOGUE) && (M % (q8 ? 8 : 2) == 0) && (p.nt_count == 1 || p.nt % 32 == 0);
     if (static_cast<long long>(B) * kPols * C > 0x7fffffffLL) return DCBF_ERR_UNSUPPORTED;
     if (int e = get_status_block(&p.status)) return e;
@@ -1270,12 +1311,8 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     DCBF_CUDA_TRY(cudaGetDevice(&dev));
     if (!n_sms[dev]) {
         DCBF_CUDA_TRY(cudaDeviceGetAttribute(&n_sms[dev], cudaDevAttrMultiProcessorCount, dev));
-        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DCBF_CUDA_TRY(cudaFuncSetAttribute(fused_beamform_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        for (int i = 0; i < 12; ++i)
+            DCBF_CUDA_TRY(cudaFuncSetAttribute(kKernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     }
     const int grid = C < n_sms[dev] ? C : n_sms[dev];
     cudaLaunchConfig_t cfg{};
@@ -1288,16 +1325,10 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (flags & DCBF_FLAG_STREAMING) ? 1 : 0;
-    // (profiling, time-varying steering, int8 output) specialisations; the profiler has no time-varying build
-    auto kernel = fused_beamform_kernel<false, false, false>;
-    if (q8)
-        kernel = batch_dt_s ? fused_beamform_kernel<false, true, true>
-                 : p.prof   ? fused_beamform_kernel<true, false, true>
-                            : fused_beamform_kernel<false, false, true>;
-    else
-        kernel = batch_dt_s ? fused_beamform_kernel<false, true, false>
-                 : p.prof   ? fused_beamform_kernel<true, false, false>
-                            : fused_beamform_kernel<false, false, false>;
+    // (int8 output, variant, merged) specialisation; variant: 0 plain, 1 profiling, 2 time-varying steering (the
+    // profiler has no time-varying build)
+    const int variant = batch_dt_s ? 2 : p.prof ? 1 : 0;
+    auto kernel = kKernels[(q8 ? 6 : 0) + 2 * variant + (p.merged ? 1 : 0)];
     DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, p, tm_in, tm_out));
     DCBF_CHECK_LAUNCH("fused_beamform_kernel");
     return DCBF_OK;
