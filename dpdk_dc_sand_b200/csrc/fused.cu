@@ -15,14 +15,14 @@
 //   W[2a+x][2m+y] = {{cos, sin}, {-sin, cos}}[x][y] of rot(c, m, a), carried as fp16 hi + fp16 lo
 //                  (two accumulating MMAs; coefficient error ~2^-24) or fp16 hi only (DCBF_FLAG_FP16_COEFF).
 //
-// One persistent CTA per SM walks channels c = blockIdx.x, +gridDim.x, ...  Warp roles (576 threads):
+// One persistent CTA per SM takes channels from a dynamic queue.  Warp roles (608 threads):
 //   warps 0-7     coeffs    : delay_vals (coalesced float4, one batch prefetched in registers) -> f64 phase
 //                             -> sincospi -> fp16 hi/lo -> 128B-swizzled B tiles, one channel ahead
 //   warps 8-11    convert   : raw bytes -> fp16, pol de-interleave, a<->t transpose into 64B-swizzled A tiles
 //   warps 12-15   epilogue  : tcgen05.ld 32x32b -> 128B-swizzled staging tile -> TMA tensor store (32x32 boxes)
 //                             (odd beam counts / ragged N tiles: 16x256b -> st.global.v2 from registers)
 //   warp 16       producer  : one tensor-map TMA box [16 ant][128 samples][4 B] per slab -> raw ring
-//   warp 17       MMA       : one lane issues tcgen05.mma (M=128, N<=128, K=16), accumulators in TMEM
+//   warps 17, 18  MMA       : one lane each issues the tcgen05.mma (M=128, N<=128, K=16) of one pol, accumulators in TMEM
 // Pipelines (mbarrier full/empty pairs): raw ring (TMA->convert), A ring (convert->MMA), B double buffer
 // (coeffs->MMA), TMEM accumulator double buffer (MMA->epilogue), per-warp staging pairs (bulk groups).
 //
@@ -49,8 +49,9 @@ constexpr int kCoeffWarp0 = 0, kCoeffWarps = 8;  // warps 0..7
 constexpr int kConvertWarp0 = 8;                 // warps 8..11
 constexpr int kEpilogueWarp0 = 12;               // warps 12..15 (warp % 4 = TMEM lane quarter)
 constexpr int kProducerWarp = 16;
-constexpr int kMmaWarp = 17;
-constexpr int kThreads = 18 * 32;
+constexpr int kMmaWarp = 17;     // issues the pol-0 MMAs (and owns the TMEM allocation)
+constexpr int kMmaWarp2 = 18;    // issues the pol-1 MMAs: the issue path, not the tensor pipe, limits narrow tiles
+constexpr int kThreads = 19 * 32;
 constexpr int kTileT = 128;    // samples per MMA tile (UMMA M)
 constexpr int kSlabAnts = 16;  // antennas per raw slab / A stage
 constexpr int kKbAnts = 32;    // antennas per B k-block (128-byte swizzle row of fp16)
@@ -509,14 +510,14 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         }
         for (int s = 0; s < kAopStages; ++s) {
             mbar_init(bar(kAopFull + s), 4);
-            mbar_init(bar(kAopEmpty + s), 1);
+            mbar_init(bar(kAopEmpty + s), 2);  // one tcgen05.commit per MMA warp
         }
         for (int s = 0; s < kBopBufs; ++s) {
             mbar_init(bar(kBopFull + s), kCoeffWarps);
-            mbar_init(bar(kBopEmpty + s), 1);
+            mbar_init(bar(kBopEmpty + s), 2);
         }
         for (int s = 0; s < kAccBufs; ++s) {
-            mbar_init(bar(kAccFull + s), 1);
+            mbar_init(bar(kAccFull + s), 2);
             mbar_init(bar(kAccEmpty + s), 4);
         }
         ctl->abort = 0;
@@ -555,7 +556,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     const bool prof_lane = kProf && lane == 0 && (warp == kProducerWarp || warp == kMmaWarp || warp == kEpilogueWarp0 ||
                                          warp == kConvertWarp0 || warp == kCoeffWarp0);
     const int ps = prof_lane ? 0 : -100;
-    const int my_role = warp == kProducerWarp ? kRoleProducer : warp == kMmaWarp ? kRoleMma
+    const int my_role = warp == kProducerWarp ? kRoleProducer : (warp == kMmaWarp || warp == kMmaWarp2) ? kRoleMma
                         : warp >= kEpilogueWarp0 ? kRoleEpilogue : warp >= kConvertWarp0 ? kRoleConvert : kRoleCoeff;
     const unsigned long long role_t0 = prof_lane ? global_ns() : 0ull;
     const unsigned long long role_t0_cta = (kProf && threadIdx.x < 24) ? global_ns() : 0ull;
@@ -579,7 +580,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                             }
                             __syncwarp();
                         }
-    } else if (warp == kMmaWarp) {
+    } else if (warp == kMmaWarp || warp == kMmaWarp2) {
         // =================================== MMA issuer ===================================
         // merged: the lo rows follow the hi rows in the B tile, so one N = 2 nt MMA replaces two N = nt MMAs and the
         // A tile is read from shared memory once; its two halves land in adjacent TMEM column ranges
@@ -611,8 +612,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         // B: k-block s/2, 64-byte half s%2 of its 128-byte rows
                         const uint32_t b_lo = b_lo0 + bb * (kBopBufBytes >> 4) + static_cast<uint32_t>(s >> 1) * kb_lo + static_cast<uint32_t>(s & 1) * 4u;
                         if (elect_one()) {
-#pragma unroll
-                            for (int p = 0; p < kPols; ++p) {
+                            {
+                                const uint32_t p = warp == kMmaWarp ? 0u : 1u;  // this warp's pol
                                 const uint32_t d_tmem = d_tmem0 + p * acc_cols;
 #pragma unroll
                                 for (int part = 0; part < 2; ++part) {
