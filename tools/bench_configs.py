@@ -23,6 +23,11 @@ TS = orc.SAMPLE_PERIOD
 
 
 def main():
+    flags = 0
+    if "--flags" in sys.argv:
+        i = sys.argv.index("--flags")
+        flags = int(sys.argv[i + 1], 0)
+        del sys.argv[i:i + 2]
     names = sys.argv[1:] or ["c2", "c3", "c4", "c5"]
     peak = 6550.1
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -40,13 +45,13 @@ def main():
         dv[..., 2] = (torch.rand((C, M, A), device=dev, generator=g) * 2 - 1) * 3.14159265
         out = torch.empty((B, 2, C, T // 16, 16, 2 * M), dtype=torch.float32, device=dev)
         for _ in range(2):
-            _capi.fused(x, dv, out, B, A, C, C, T, M, 0, TS)
+            _capi.fused(x, dv, out, B, A, C, C, T, M, 0, TS, flags)
         torch.cuda.synchronize()
         n = 5 if name in ("c4", "c5") else 20
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
-            _capi.fused(x, dv, out, B, A, C, C, T, M, 0, TS)
+            _capi.fused(x, dv, out, B, A, C, C, T, M, 0, TS, flags)
         e1.record()
         torch.cuda.synchronize()
         _capi.fused_status()
@@ -64,7 +69,7 @@ def main():
             worst = max(worst, float(np.max(np.abs(got - ref) / bound)))
         res[name] = {"n_ants": A, "n_chans": C, "n_beams": M, "us": sec * 1e6, "algorithmic_bytes": by,
                      "GBps": by / sec / 1e9, "frac_hbm": by / sec / 1e9 / peak, "tflops_real_expanded": fl / sec / 1e12,
-                     "tiling": _capi.fused_tiling(A, M, 0), "max_err_over_sum_abs_x": worst,
+                     "tiling": _capi.fused_tiling(A, M, flags), "flags": flags, "max_err_over_sum_abs_x": worst,
                      "within_budget": worst <= 2.0 ** -10}
         del x, dv, out
         torch.cuda.empty_cache()
