@@ -23,7 +23,6 @@ ERR_TIMEOUT = -5
 FLAG_SIGNED_INPUT = 0x1
 FLAG_FP16_COEFF = 0x2
 FLAG_STREAMING = 0x4
-FLAG_FAST_SINCOS = 0x8
 FLAG_DEBUG_DIRECT_EPILOGUE = 0x100
 
 _ROLE_NAMES = {1: "producer", 2: "mma", 3: "epilogue", 4: "convert", 5: "coeff"}
@@ -106,7 +105,7 @@ def load() -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB_PATH
+        path = os.environ.get("DCBF_LIB") or _build.LIB_PATH  # DCBF_LIB: developer A/B runs against another build
         if not os.path.exists(path):
             path = _build.build()
         lib = C.CDLL(path)

@@ -93,7 +93,6 @@ struct FusedParams {
     int ht_count;    // ceil(T / 128)
     int parts;       // 2 = fp16 hi+lo coefficients, 1 = fp16 hi only
     int signed_in;
-    int fast_sincos;  // MUFU sin/cos (abs error ~5e-7) instead of the polynomial (~1e-7)
     int tma_store;   // 1: epilogue through shared memory + TMA tensor stores; 0: st.global from registers
     int merged;      // hi and lo coefficient rows form ONE N = 2 nt tile per MMA (nt <= 64); the epilogue adds the halves
     int q8_wide;     // q8 only: the N tile is the whole output row (32 / 64 / 128 bytes): one box per 32 rows
@@ -933,14 +932,10 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         constexpr int kStride = kCoeffWarps * 32;
         const int ctid = threadIdx.x - kCoeffWarp0 * 32;
         const int mt = nt >> 1;  // beams per N tile
-        // Entries per step of the walk: a whole number of beams when a beam fits (A <= 256; the last few threads
-        // then idle), so that every thread keeps its antenna and only its beam advances, by dm per step.
-        const int stride = A <= kStride ? (kStride / A) * A : kStride;
-        const bool active = ctid < stride;
-        const int dm = stride / A, da = stride - dm * A;  // (beam, antenna) advance per step; da = 0 when A <= 256
+        const int dm = kStride / A, da = kStride - dm * A;  // (beam, antenna) advance per kStride entries
         const int ml_first = ctid / A, a_first = ctid - ml_first * A;
-        // common shape (A = 64, 32, ...): the beam advances by a multiple of 4, the swizzle phase (row & 7) never
-        // changes and the B address only advances by a constant
+        // common shape (A = 64, 32, ...): a thread keeps its antenna and moves 4k beams per step, so its B
+        // address only advances by a constant
         const bool fast_addr = da == 0 && (dm & 3) == 0;
         const int sb_count = kTv ? prm.sb_count : 1;
 
@@ -994,9 +989,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         auto issue_loads = [&]() {
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
-                const int e = ne0 + u * stride;
+                const int e = ne0 + u * kStride;
                 float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (active && nc < C && e < n_entries) t4 = ldg_nc_f4(n_src + e);
+                if (nc < C && e < n_entries) t4 = ldg_nc_f4(n_src + e);
                 if constexpr (kTv) nxt[u] = t4;
                 else nxt[u] = make_float2(t4.x, t4.z);
             }
@@ -1007,7 +1002,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 if (sch_n <= static_cast<int>(nk) + 1) sch_request();
             }
             if (nc >= C) return;
-            ne0 += stride * kBatch;
+            ne0 += kStride * kBatch;
             if (ne0 - ctid < n_entries) return;
             ne0 = ctid;
             if (++nsb < sb_count) return;  // same delay_vals again for the next heap's coefficient set (L2 hits)
@@ -1050,13 +1045,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 } else {
                     steer_phase<false>(dv.x, 0.f, dv.y, 0.f, s_hi, s_lo, scale, &r, &small);
                 }
-                if (prm.fast_sincos) {  // DCBF_FLAG_FAST_SINCOS: two special-function instructions instead of ~22
-                    const float x = (r + small) * 3.14159274f;
-                    sn = __sinf(x);
-                    cs = __cosf(x);
-                } else {
-                    sincospi_reduced(r, small, &sn, &cs);
-                }
+                sincospi_reduced(r, small, &sn, &cs);
                 if (w_tile) {  // ?beam-weights: real weight of this (beam, antenna); the table is tiny and stays in L1/L2
                     const float w = __ldg(w_tile + e);
                     cs *= w;
@@ -1080,13 +1069,6 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 return buf + static_cast<uint32_t>(a >> 5) * bop_kb_bytes + static_cast<uint32_t>(row) * 128u +
                        (static_cast<uint32_t>(((al >> 2) ^ (row & 7)) << 4) | static_cast<uint32_t>((al & 3) << 2));
             };
-            // fixed antenna: everything but the row and its swizzle phase is constant for the thread
-            const uint32_t a_off = static_cast<uint32_t>(a_first >> 5) * bop_kb_bytes + static_cast<uint32_t>((a_first & 3) << 2);
-            const uint32_t a_chunk = static_cast<uint32_t>((a_first & (kKbAnts - 1)) >> 2);
-            auto b_addr_fixed = [&](uint32_t buf, int ml) {
-                const uint32_t row = 2u * static_cast<uint32_t>(ml);
-                return buf + a_off + row * 128u + ((a_chunk ^ (row & 7u)) << 4);
-            };
             for (int isb = 0; isb < prm.nt_count * sb_count && ok; ++isb, ++step) {
                 const int it = isb / sb_count, sb = isb - it * sb_count;
                 if constexpr (kTv) {
@@ -1102,7 +1084,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 int ml = ml_first, a = a_first;
                 uint32_t d_fast = b_addr(buf, ml_first, a_first);
                 const uint32_t d_step = static_cast<uint32_t>(dm) * 256u;  // dm beams = 2 dm rows of 128 B
-                for (int e0 = ctid; e0 - ctid < entries; e0 += stride * kBatch) {  // e0 - ctid is warp-uniform
+                for (int e0 = ctid; e0 - ctid < entries; e0 += kStride * kBatch) {  // e0 - ctid is warp-uniform
                     Dv v[kBatch];
 #pragma unroll
                     for (int u = 0; u < kBatch; ++u) v[u] = nxt[u];
@@ -1116,18 +1098,12 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     if (fast_addr) {
 #pragma unroll
                         for (int u = 0; u < kBatch; ++u)
-                            if (active && e0 + u * stride < entries) emit(v[u], d_fast + static_cast<uint32_t>(u) * d_step, e0 + u * stride);
+                            if (e0 + u * kStride < entries) emit(v[u], d_fast + static_cast<uint32_t>(u) * d_step, e0 + u * kStride);
                         d_fast += kBatch * d_step;
-                    } else if (da == 0) {
-#pragma unroll
-                        for (int u = 0; u < kBatch; ++u) {
-                            if (active && e0 + u * stride < entries) emit(v[u], b_addr_fixed(buf, ml), e0 + u * stride);
-                            ml += dm;
-                        }
                     } else {
 #pragma unroll
                         for (int u = 0; u < kBatch; ++u) {
-                            if (e0 + u * stride < entries) emit(v[u], b_addr(buf, ml, a), e0 + u * stride);
+                            if (e0 + u * kStride < entries) emit(v[u], b_addr(buf, ml, a), e0 + u * kStride);
                             ml += dm;
                             a += da;
                             if (a >= A) {
@@ -1258,7 +1234,6 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     p.B = B, p.A = A, p.C = C, p.T = T, p.M = M;
     p.parts = (flags & DCBF_FLAG_FP16_COEFF) ? 1 : 2;
     p.signed_in = (flags & DCBF_FLAG_SIGNED_INPUT) ? 1 : 0;
-    p.fast_sincos = (flags & DCBF_FLAG_FAST_SINCOS) ? 1 : 0;
     pick_n_tiling(A, M, p.parts, &p.kb_count, &p.nt, &p.nt_count);
     if (p.nt < 16) return DCBF_ERR_UNSUPPORTED;  // more than 128 k-blocks (4096 antennas)
     p.slab_count = (A + kSlabAnts - 1) / kSlabAnts;

@@ -65,9 +65,6 @@ typedef enum dcbf_status {
                                        reads or writes, e.g. consecutive heaps into alternating output buffers), so its
                                        CTAs may start on SMs that kernel has already left (programmatic dependent
                                        launch).  Copies and events keep their normal stream ordering. */
-#define DCBF_FLAG_FAST_SINCOS 0x8u  /* dcbf_fused*: hardware sin/cos (MUFU) for the steering coefficients: absolute
-                                       coefficient error ~5e-7 instead of ~1e-7, ~30 % less work for the coefficient
-                                       warps (matters when they are the limiter: many beams x antennas per channel) */
 #define DCBF_FLAG_DEBUG_DIRECT_EPILOGUE 0x100u /* dcbf_fused: st.global from registers instead of TMA stores (cross-check) */
 
 int dcbf_version(void);
