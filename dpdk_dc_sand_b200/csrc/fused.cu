@@ -16,8 +16,9 @@
 //                  (two accumulating MMAs; coefficient error ~2^-24) or fp16 hi only (DCBF_FLAG_FP16_COEFF).
 //
 // One persistent CTA per SM takes channels from a dynamic queue.  Warp roles (608 threads):
-//   warps 0-7     coeffs    : delay_vals (coalesced float4, one batch prefetched in registers) -> f64 phase
-//                             -> sincospi -> fp16 hi/lo -> 128B-swizzled B tiles, one channel ahead
+//   warps 0-7     coeffs    : delay_vals (coalesced float4, one batch prefetched in registers) -> phase to float64
+//                             accuracy in float pairs -> sincospi -> fp16 hi/lo -> 128B-swizzled B tiles, one
+//                             channel ahead; lane 0 of warp 0 also draws the CTA's channels from the global queue
 //   warps 8-11    convert   : raw bytes -> fp16, pol de-interleave, a<->t transpose into 64B-swizzled A tiles
 //   warps 12-15   epilogue  : tcgen05.ld 32x32b -> 128B-swizzled staging tile -> TMA tensor store (32x32 boxes)
 //                             (odd beam counts / ragged N tiles: 16x256b -> st.global.v2 from registers)
@@ -28,7 +29,11 @@
 //
 // Tiling: time tiles of 128 samples (UMMA M), slabs of 16 antennas (K = 32 = two MMA K-steps), B k-blocks of
 // 32 antennas (one 128-byte swizzle row), N tiles of <=128 columns chosen so that one B tile set (all k-blocks,
-// hi+lo) fits 64 KiB.  With more than one N tile the voltages of a channel are re-read (from L2).
+// hi+lo) fits 64 KiB.  With more than one N tile the voltages of a channel are re-read (from L2).  Tiles of
+// <= 64 columns run hi and lo as ONE N = 2 nt MMA (kMerged).
+//
+// Template specialisations: kProf (per-role blocked-time accounting, tools/prof_roles.py), kTv (per-heap delay /
+// phase rates, dcbf_fused_tv), kQ8 (int8 requantised output, dcbf_fused_q8), kMerged.
 #include <cuda.h>
 
 #include <atomic>
