@@ -32,20 +32,11 @@ class CoeffGeneratorTemplate:
         self.xeng_id = xeng_id
         self.sample_period = sample_period
 
-        dim = accel.Dimension
-        self.delay_vals_data_dimensions = (
-            dim(self.n_channels_per_stream, exact=True),
-            dim(self.n_beams, exact=True),
-            dim(self.n_ants, exact=True),
-            dim(4, exact=True),
-        )
-        self.coeff_data_dimensions = (
-            dim(self.n_batches, exact=True),
-            dim(self.n_pols, exact=True),
-            dim(self.n_channels_per_stream, exact=True),
-            dim(self.n_ants * 2, exact=True),
-            dim(self.n_beams * 2, exact=True),
-        )
+        # {delay_s, delay_rate, phase_rad, phase_rate} per (channel, beam, antenna)            coeff_generator.py:164-169
+        self.delay_vals_data_dimensions = accel.exact_dimensions(n_channels_per_stream, n_beams, n_ants, 4)
+        # one [[cos, sin], [-sin, cos]] block per (antenna, beam), replicated over batch and pol    :171-177
+        self.coeff_data_dimensions = accel.exact_dimensions(n_batches, n_pols, n_channels_per_stream, 2 * n_ants,
+                                                            2 * n_beams)
 
     def instantiate(self, command_queue) -> "CoeffGenerator":
         return CoeffGenerator(self, command_queue)

@@ -30,31 +30,11 @@ class MatrixMultiplyTemplate:
             raise ValueError(f"samples_per_channel must be divisible by {self.n_samples_per_block}.")
         self.length = self.n_batches * self.n_pols * self.n_channels_per_stream * self.n_blocks * self.n_samples_per_block
 
-        dim = accel.Dimension
-        self.input_data_dimensions = (
-            dim(self.n_batches, exact=True),
-            dim(self.n_pols, exact=True),
-            dim(self.n_channels_per_stream, exact=True),
-            dim(self.n_blocks, exact=True),
-            dim(self.n_samples_per_block, exact=True),
-            dim(self.n_ants, exact=True),
-            dim(self.complexity, exact=True),
-        )
-        self.output_data_dimensions = (
-            dim(self.n_batches, exact=True),
-            dim(self.n_pols, exact=True),
-            dim(self.n_channels_per_stream, exact=True),
-            dim(self.n_blocks, exact=True),
-            dim(self.n_samples_per_block, exact=True),
-            dim(self.beams * self.complexity, exact=True),
-        )
-        self.coeff_data_dimensions = (
-            dim(self.n_batches, exact=True),
-            dim(self.n_pols, exact=True),
-            dim(self.n_channels_per_stream, exact=True),
-            dim(self.n_ants * 2, exact=True),
-            dim(self.beams * 2, exact=True),
-        )
+        b, p, c, k, spb, a, m2 = (self.n_batches, self.n_pols, self.n_channels_per_stream, self.n_blocks,
+                                   self.n_samples_per_block, self.n_ants, self.beams * self.complexity)
+        self.input_data_dimensions = accel.exact_dimensions(b, p, c, k, spb, a, self.complexity)  # matrix_multiply.py:86-94
+        self.output_data_dimensions = accel.exact_dimensions(b, p, c, k, spb, m2)                  # :95-102
+        self.coeff_data_dimensions = accel.exact_dimensions(b, p, c, 2 * a, m2)                    # :104-110
 
     def instantiate(self, command_queue) -> "MatrixMultiply":
         return MatrixMultiply(self, command_queue)

@@ -51,24 +51,12 @@ class PreBeamformReorderTemplate:
             if getattr(self, name) <= 0:
                 raise ValueError(f"{name} must be positive")
 
-        dim = accel.Dimension
-        self.inputDataShape = (
-            dim(self.n_batches, exact=True),
-            dim(self.n_ants, exact=True),
-            dim(self.n_channels_per_stream, exact=True),
-            dim(self.n_samples_per_channel, exact=True),
-            dim(self.n_pols, exact=True),
-            dim(self.complexity, exact=True),
-        )
-        self.outputDataShape = (
-            dim(self.n_batches, exact=True),
-            dim(self.n_pols, exact=True),
-            dim(self.n_channels_per_stream, exact=True),
-            dim(self.n_blocks, exact=True),
-            dim(self.n_samples_per_block, exact=True),
-            dim(self.n_ants, exact=True),
-            dim(self.complexity, exact=True),
-        )
+        self.inputDataShape = accel.exact_dimensions(   # prebeamform_reorder.py:68-75
+            self.n_batches, self.n_ants, self.n_channels_per_stream, self.n_samples_per_channel, self.n_pols,
+            self.complexity)
+        self.outputDataShape = accel.exact_dimensions(  # :77-85
+            self.n_batches, self.n_pols, self.n_channels_per_stream, self.n_blocks, self.n_samples_per_block,
+            self.n_ants, self.complexity)
         self.matrix_size = self.n_ants * self.n_channels_per_stream * self.n_samples_per_channel * self.n_pols
         # Launch-shape attributes of the reference kernel, kept for API compatibility only.
         self.threads_per_block = 1024

@@ -287,6 +287,11 @@ class Dimension:
             self.exact = other.exact = True
 
 
+def exact_dimensions(*sizes: int) -> Tuple[Dimension, ...]:
+    """Unpadded dimensions of the given sizes (every slot of the beamformer operators is ``exact=True``)."""
+    return tuple(Dimension(int(n), exact=True) for n in sizes)
+
+
 class IOSlotBase:
     def __init__(self) -> None:
         self.buffer: Optional[DeviceArray] = None
