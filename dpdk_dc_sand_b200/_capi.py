@@ -24,6 +24,7 @@ FLAG_SIGNED_INPUT = 0x1
 FLAG_FP16_COEFF = 0x2
 FLAG_STREAMING = 0x4
 FLAG_DEBUG_DIRECT_EPILOGUE = 0x100
+FLAG_DEBUG_NO_KSTREAM = 0x200
 
 _ROLE_NAMES = {1: "producer", 2: "mma", 3: "epilogue", 4: "convert", 5: "coeff"}
 

@@ -63,6 +63,8 @@ constexpr int kKbAnts = 32;    // antennas per B k-block (128-byte swizzle row o
 constexpr int kRawStages = 4;
 constexpr int kAopStages = 2;
 constexpr int kBopBufs = 2;
+constexpr int kBopSlots = 4;    // kStream: B k-block ring (4 x 32 KiB) instead of 2 whole tile sets
+constexpr int kBopSlotBytes = kBopBufs * 64 * 1024 / kBopSlots;
 constexpr int kAccBufs = 2;
 constexpr int kRawStageBytes = kSlabAnts * kTileT * 4;  // 8 KiB: [ant][t][pol][re,im]
 constexpr int kAopTileBytes = kTileT * 64;              // 8 KiB: [t][32 fp16], 64B swizzle
@@ -478,7 +480,7 @@ __device__ __forceinline__ uint32_t quantise4(const uint32_t (&r)[32], int j, fl
 // ------------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------------
-template <bool kProf, bool kTv, bool kQ8, bool kMerged>
+template <bool kProf, bool kTv, bool kQ8, bool kMerged, bool kStream>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_constant__ CUtensorMap tm_in,
                       const __grid_constant__ CUtensorMap tm_out) {
@@ -500,9 +502,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
 
     // barrier ids (also reported by the watchdog)
     const int kRawFull = 0, kRawEmpty = kRawFull + kRawStages, kAopFull = kRawEmpty + kRawStages,
-              kAopEmpty = kAopFull + kAopStages, kBopFull = kAopEmpty + kAopStages, kBopEmpty = kBopFull + kBopBufs,
-              kAccFull = kBopEmpty + kBopBufs, kAccEmpty = kAccFull + kAccBufs, kNumBars = kAccEmpty + kAccBufs;
-    static_assert(2 * (kRawStages + kAopStages + kBopBufs + kAccBufs) * 8 <= 192, "barrier area");
+              kAopEmpty = kAopFull + kAopStages, kBopFull = kAopEmpty + kAopStages, kBopEmpty = kBopFull + kBopSlots,
+              kAccFull = kBopEmpty + kBopSlots, kAccEmpty = kAccFull + kAccBufs, kNumBars = kAccEmpty + kAccBufs;
+    static_assert(2 * (kRawStages + kAopStages + kBopSlots + kAccBufs) * 8 <= 192, "barrier area");
     auto bar = [&](int id) { return bar_base + 8u * static_cast<uint32_t>(id); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -517,7 +519,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             mbar_init(bar(kAopFull + s), 4);
             mbar_init(bar(kAopEmpty + s), 2);  // one tcgen05.commit per MMA warp
         }
-        for (int s = 0; s < kBopBufs; ++s) {
+        for (int s = 0; s < kBopSlots; ++s) {
             mbar_init(bar(kBopFull + s), kCoeffWarps);
             mbar_init(bar(kBopEmpty + s), 2);
         }
@@ -570,11 +572,15 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         // =================================== TMA producer ===================================
         uint32_t slab = 0;
         bool ok = true;
+        // slab order inside a (channel, N tile, batch): time tile outer, antenna slab inner; kStream: slab outer
+        // (every B k-block is then used for both time tiles before it is released)
+        const int n_inner = kStream ? prm.ht_count : prm.slab_count, n_outer = kStream ? prm.slab_count : prm.ht_count;
         for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k)
             for (int it = 0; it < prm.nt_count && ok; ++it)
                 for (int b = 0; b < B && ok; ++b)
-                    for (int h = 0; h < prm.ht_count && ok; ++h)
-                        for (int s = 0; s < prm.slab_count; ++s, ++slab) {
+                    for (int o = 0; o < n_outer && ok; ++o)
+                        for (int i = 0; i < n_inner; ++i, ++slab) {
+                            const int h = kStream ? i : o, s = kStream ? o : i;
                             const uint32_t rs = slab % kRawStages, ph = (slab / kRawStages) & 1u;
                             ok = mbar_wait<kProf>(bar(kRawEmpty + rs), ph ^ 1u, ctl, prm.status, kRoleProducer, kRawEmpty + rs, ps + 0);
                             if (!ok) break;
@@ -596,6 +602,57 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         const uint32_t part_lo = part_bytes >> 4, kb_lo = bop_kb_bytes >> 4;
         uint32_t slab = 0, unit = 0, step = 0;
         bool ok = true;
+        if constexpr (kStream) {
+            // K-streamed B: one ring slot per 32-antenna k-block; all (time tile, pol) accumulators of a
+            // (channel, N tile, batch) unit are open at once (ht x 2 x nt TMEM columns), slabs outer, time tiles inner
+            const uint32_t pol = warp == kMmaWarp ? 0u : 1u;
+            uint32_t kstep = 0;
+            for (uint32_t k = 0; ok && sched_get(ctl, k) < C; ++k)
+                for (int itb = 0; itb < prm.nt_count * B && ok; ++itb, ++unit) {
+                    ok = mbar_wait<kProf>(bar(kAccEmpty), (unit & 1u) ^ 1u, ctl, prm.status, kRoleMma, kAccEmpty, ps + 1);
+                    if (!ok) break;
+                    tc_fence_after();
+                    for (int s = 0; s < prm.slab_count && ok; ++s) {
+                        const uint32_t slot = kstep % kBopSlots;
+                        if ((s & 1) == 0)
+                            ok = mbar_wait<kProf>(bar(kBopFull + slot), (kstep / kBopSlots) & 1u, ctl, prm.status, kRoleMma, kBopFull + slot, ps + 0);
+                        const int n_ants = min(kSlabAnts, A - s * kSlabAnts);
+                        const int k_steps = (n_ants + 7) >> 3;
+                        const uint32_t b_lo = b_lo0 + slot * (kBopSlotBytes >> 4) + static_cast<uint32_t>(s & 1) * 4u;
+                        for (int h = 0; h < prm.ht_count && ok; ++h, ++slab) {
+                            const uint32_t as = slab % kAopStages;
+                            ok = mbar_wait<kProf>(bar(kAopFull + as), (slab / kAopStages) & 1u, ctl, prm.status, kRoleMma, kAopFull + as, ps + 2);
+                            if (!ok) break;
+                            tc_fence_after();
+                            const uint32_t a_lo = a_lo0 + as * (kAopStageBytes >> 4) + pol * (kAopTileBytes >> 4);
+                            const uint32_t d_tmem = tmem_base + (static_cast<uint32_t>(h) * kPols + pol) * static_cast<uint32_t>(nt);
+                            if (elect_one()) {
+#pragma unroll
+                                for (int part = 0; part < 2; ++part) {
+                                    if (part < parts) {
+#pragma unroll
+                                        for (int kk = 0; kk < 2; ++kk) {
+                                            if (kk < k_steps)
+                                                umma_f16(d_tmem, make_desc(a_lo + 2u * kk, kDescHiSw64),
+                                                         make_desc(b_lo + part * part_lo + 2u * kk, kDescHiSw128), idesc,
+                                                         (s | part | kk) != 0);
+                                        }
+                                    }
+                                }
+                                umma_commit(bar(kAopEmpty + as));
+                            }
+                            __syncwarp();
+                        }
+                        if (ok && ((s & 1) == 1 || s == prm.slab_count - 1)) {  // last use of this k-block
+                            if (elect_one()) umma_commit(bar(kBopEmpty + slot));
+                            __syncwarp();
+                            ++kstep;
+                        }
+                    }
+                    if (ok && elect_one()) umma_commit(bar(kAccFull));
+                    __syncwarp();
+                }
+        } else
         for (uint32_t k = 0; ok && sched_get(ctl, k) < C; ++k)
             for (int isb = 0; isb < prm.nt_count * prm.sb_count && ok; ++isb, ++step) {  // (N tile, coefficient set)
                 const uint32_t bb = step % kBopBufs;
@@ -665,6 +722,107 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         uint32_t unit = 0, box = 0;
         int clipped = 0;
         bool ok = true;
+        // One accumulator tile (128 rows x nt columns at TMEM column col0) -> beams[b][p][c][t0 ..][n0 ..], float32.
+        auto store_tile_f32 = [&](uint32_t col0, int b, int p, uint32_t c, int t0, int n0) {
+            if (prm.tma_store) {
+                const int row0 = t0 + 32 * q;  // this warp's 32 rows of the tile
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + col0;
+                const int plane = (b * kPols + p) * C + static_cast<int>(c);
+                for (int cb = 0; cb < nt && row0 < T && n0 + cb < N2; cb += 32, ++box) {
+                    uint32_t r[32];
+                    unsigned long long tp0 = 0, tp1 = 0, tp2 = 0;
+                    if (kProf && prof_lane) tp0 = global_ns();
+                    ld32(taddr + cb, r);
+                    const uint32_t sb = ost + (box & 1u) * kOutBoxBytes;
+                    bulk_wait_group_read<1>();  // (issuing lane) the store that last read this box is done
+                    __syncwarp();
+                    if (kProf && prof_lane) tp1 = global_ns();
+                    tmem_wait_ld();
+                    if (kProf && prof_lane) tp2 = global_ns();
+                    const uint32_t dst = sb + lane * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        st_shared_v4(dst + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (kProf && prof_lane) {  // slot 1: bulk-store read wait, slot 2: TMEM read + fence + stores
+                        ctl->wait_ns[kRoleEpilogue][1] += tp1 - tp0;
+                        ctl->wait_ns[kRoleEpilogue][2] += (tp2 - tp1) | ((global_ns() - tp2) << 32);
+                    }
+                    if (elect_one()) {
+                        tma_store_3d(&tm_out, sb, n0 + cb, row0, plane);
+                        bulk_commit_group();
+                    }
+                }
+            } else {
+                float* tile_out = prm.out + (((static_cast<size_t>(b) * kPols + p) * C + c) * static_cast<size_t>(T) + t0) * N2 + n0;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    const int r_lo = 32 * q + 16 * half + (lane >> 2);
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q + 16 * half) << 16) + col0;
+                    float* row_lo = tile_out + static_cast<size_t>(r_lo) * N2 + 2 * (lane & 3);
+                    float* row_hi = row_lo + 8 * static_cast<size_t>(N2);
+                    const bool v_lo = t0 + r_lo < T, v_hi = t0 + r_lo + 8 < T;
+                    int cb = 0;
+                    for (; cb + 64 <= nt; cb += 64) {
+                        uint32_t r[32];
+                        tmem_ld_16x256b_x8(taddr + cb, r);
+                        if constexpr (merged) {
+                            uint32_t l[32];
+                            tmem_ld_16x256b_x8(taddr + cb + static_cast<uint32_t>(nt), l);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(l[i]));
+                        }
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int col = cb + 8 * i;
+                            if (n0 + col + 2 * (lane & 3) < N2) {
+                                if (v_lo) st_global_v2(row_lo + col, r[4 * i], r[4 * i + 1]);
+                                if (v_hi) st_global_v2(row_hi + col, r[4 * i + 2], r[4 * i + 3]);
+                            }
+                        }
+                    }
+                    for (; cb < nt; cb += 16) {
+                        uint32_t r[8];
+                        tmem_ld_16x256b_x2(taddr + cb, r);
+                        if constexpr (merged) {
+                            uint32_t l[8];
+                            tmem_ld_16x256b_x2(taddr + cb + static_cast<uint32_t>(nt), l);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(l[i]));
+                        }
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int col = cb + 8 * i;
+                            if (n0 + col + 2 * (lane & 3) < N2) {
+                                if (v_lo) st_global_v2(row_lo + col, r[4 * i], r[4 * i + 1]);
+                                if (v_hi) st_global_v2(row_hi + col, r[4 * i + 2], r[4 * i + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+        };
+        if constexpr (kStream) {
+            // all (time tile, pol) accumulators of a (channel, N tile, batch) unit complete together
+            for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k)
+                for (int it = 0; it < prm.nt_count && ok; ++it)
+                    for (int b = 0; b < B && ok; ++b, ++unit) {
+                        ok = mbar_wait<kProf>(bar(kAccFull), unit & 1u, ctl, prm.status, kRoleEpilogue, kAccFull, ps + 0);
+                        if (!ok) break;
+                        tc_fence_after();
+                        for (int h = 0; h < prm.ht_count; ++h)
+                            for (int p = 0; p < kPols; ++p)
+                                store_tile_f32((static_cast<uint32_t>(h) * kPols + p) * static_cast<uint32_t>(nt), b, p, c, h * kTileT, it * nt);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(kAccEmpty));
+                    }
+        } else
         for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k)
             for (int it = 0; it < prm.nt_count && ok; ++it) {
                 const int n0 = it * nt;
@@ -776,92 +934,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                     emit_block(r, cb, plane, ost + (box & 3u) * 1024u);
                                 }
                             }
-                        } else if (prm.tma_store) {
-                            const int row0 = t0 + 32 * q;  // this warp's 32 rows of the tile
-                            for (int p = 0; p < kPols; ++p) {
-                                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kPols + p) * acc_cols;
-                                const int plane = (b * kPols + p) * C + c;
-                                for (int cb = 0; cb < nt && row0 < T && n0 + cb < N2; cb += 32, ++box) {
-                                    uint32_t r[32];
-                                    unsigned long long tp0 = 0, tp1 = 0, tp2 = 0;
-                                    if (kProf && prof_lane) tp0 = global_ns();
-                                    ld32(taddr + cb, r);
-                                    const uint32_t sb = ost + (box & 1u) * kOutBoxBytes;
-                                    bulk_wait_group_read<1>();  // (issuing lane) the store that last read this box is done
-                                    __syncwarp();
-                                    if (kProf && prof_lane) tp1 = global_ns();
-                                    tmem_wait_ld();
-                                    if (kProf && prof_lane) tp2 = global_ns();
-                                    const uint32_t dst = sb + lane * 128;
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j)
-                                        st_shared_v4(dst + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-                                    fence_proxy_async_smem();
-                                    __syncwarp();
-                                    if (kProf && prof_lane) {  // slot 1: bulk-store read wait, slot 2: TMEM read + fence + stores
-                                        ctl->wait_ns[kRoleEpilogue][1] += tp1 - tp0;
-                                        ctl->wait_ns[kRoleEpilogue][2] += (tp2 - tp1) | ((global_ns() - tp2) << 32);
-                                    }
-                                    if (elect_one()) {
-                                        tma_store_3d(&tm_out, sb, n0 + cb, row0, plane);
-                                        bulk_commit_group();
-                                    }
-                                }
-                            }
                         } else {
-                            for (int p = 0; p < kPols; ++p) {
-                                const uint32_t col0 = (ab * kPols + p) * acc_cols;
-                                float* tile_out = prm.out + (((static_cast<size_t>(b) * kPols + p) * C + c) * static_cast<size_t>(T) + t0) * N2 + n0;
-#pragma unroll 1
-                                for (int half = 0; half < 2; ++half) {
-                                    const int r_lo = 32 * q + 16 * half + (lane >> 2);
-                                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q + 16 * half) << 16) + col0;
-                                    float* row_lo = tile_out + static_cast<size_t>(r_lo) * N2 + 2 * (lane & 3);
-                                    float* row_hi = row_lo + 8 * static_cast<size_t>(N2);
-                                    const bool v_lo = t0 + r_lo < T, v_hi = t0 + r_lo + 8 < T;
-                                    int cb = 0;
-                                    for (; cb + 64 <= nt; cb += 64) {
-                                        uint32_t r[32];
-                                        tmem_ld_16x256b_x8(taddr + cb, r);
-                                        if constexpr (merged) {
-                                            uint32_t l[32];
-                                            tmem_ld_16x256b_x8(taddr + cb + static_cast<uint32_t>(nt), l);
-                                            tmem_wait_ld();
-#pragma unroll
-                                            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(l[i]));
-                                        }
-                                        tmem_wait_ld();
-#pragma unroll
-                                        for (int i = 0; i < 8; ++i) {
-                                            const int col = cb + 8 * i;
-                                            if (n0 + col + 2 * (lane & 3) < N2) {
-                                                if (v_lo) st_global_v2(row_lo + col, r[4 * i], r[4 * i + 1]);
-                                                if (v_hi) st_global_v2(row_hi + col, r[4 * i + 2], r[4 * i + 3]);
-                                            }
-                                        }
-                                    }
-                                    for (; cb < nt; cb += 16) {
-                                        uint32_t r[8];
-                                        tmem_ld_16x256b_x2(taddr + cb, r);
-                                        if constexpr (merged) {
-                                            uint32_t l[8];
-                                            tmem_ld_16x256b_x2(taddr + cb + static_cast<uint32_t>(nt), l);
-                                            tmem_wait_ld();
-#pragma unroll
-                                            for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(l[i]));
-                                        }
-                                        tmem_wait_ld();
-#pragma unroll
-                                        for (int i = 0; i < 2; ++i) {
-                                            const int col = cb + 8 * i;
-                                            if (n0 + col + 2 * (lane & 3) < N2) {
-                                                if (v_lo) st_global_v2(row_lo + col, r[4 * i], r[4 * i + 1]);
-                                                if (v_hi) st_global_v2(row_hi + col, r[4 * i + 2], r[4 * i + 3]);
-                                            }
-                                        }
-                                    }
-                                }
-                            }
+                            for (int p = 0; p < kPols; ++p) store_tile_f32((ab * kPols + p) * acc_cols, b, p, c, t0, n0);
                         }
                         tc_fence_before();
                         __syncwarp();
@@ -985,6 +1059,105 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         }
         __syncwarp();
 
+        if constexpr (kStream) {
+            // K-streamed B tiles: one step = one 32-antenna k-block of one (channel, N tile, batch) unit, written to
+            // ring slot step % 4.  lane <-> antenna of the k-block (a 512-byte run of delay_vals per beam), warp w
+            // takes beams w, w + 8, ...: 8 beams per warp and step.  Coefficients are regenerated per batch in
+            // this mode (the ring does not keep them).
+            constexpr int kPer = 8;
+            const int wl = warp - kCoeffWarp0;
+            const int mt = nt >> 1;
+            uint32_t nk = 0;
+            int nc = sched_get(ctl, 0), nit = 0, nb = 0, nkb = 0;
+            float2 nxt[kPer];
+            auto issue_loads = [&]() {
+                const int m0 = nit * mt, mte = min(mt, M - m0), a = kKbAnts * nkb + lane;
+#pragma unroll
+                for (int u = 0; u < kPer; ++u) {
+                    const int m = wl + kCoeffWarps * u;
+                    float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (nc < C && m < mte && a < A) t4 = ldg_nc_f4(prm.dv + (static_cast<size_t>(nc) * M + m0 + m) * A + a);
+                    nxt[u] = make_float2(t4.x, t4.z);
+                }
+            };
+            auto advance_cursor = [&]() {
+                if (is_sched) {
+                    sch_flush();
+                    if (sch_n <= static_cast<int>(nk) + 1) sch_request();
+                }
+                if (nc >= C) return;
+                if (++nkb < prm.kb_count) return;
+                nkb = 0;
+                if (++nb < B) return;
+                nb = 0;
+                if (++nit < prm.nt_count) {
+                    if (is_sched) warm_l2(nc, nit * mt);
+                    return;
+                }
+                nit = 0;
+                ++nk;
+                if (is_sched && sch_n <= static_cast<int>(nk)) {
+                    sch_request();
+                    sch_flush();
+                }
+                __syncwarp();
+                nc = sched_get(ctl, nk);
+            };
+            issue_loads();
+            uint32_t kstep = 0;
+            bool ok = true;
+            for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k) {
+                const double scale = (static_cast<double>(c) + prm.chan_centre) * prm.turns_per_delay;
+                const float s_hi = static_cast<float>(scale), s_lo = static_cast<float>(scale - static_cast<double>(s_hi));
+                for (int it = 0; it < prm.nt_count && ok; ++it) {
+                    const int m0 = it * mt, mte = min(mt, M - m0);
+                    const float* w_tile = prm.weights ? prm.weights + static_cast<size_t>(m0) * A : nullptr;
+                    for (int bkb = 0; bkb < B * prm.kb_count && ok; ++bkb, ++kstep) {
+                        const int kb = bkb % prm.kb_count;
+                        const uint32_t slot = kstep % kBopSlots;
+                        float2 v[kPer];
+#pragma unroll
+                        for (int u = 0; u < kPer; ++u) v[u] = nxt[u];
+                        advance_cursor();
+                        issue_loads();
+                        ok = mbar_wait<kProf>(bar(kBopEmpty + slot), ((kstep / kBopSlots) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + slot, ps + 0);
+                        if (!ok) break;
+                        const int a = kKbAnts * kb + lane;
+                        const uint32_t buf = bop_base + slot * kBopSlotBytes;
+#pragma unroll
+                        for (int u = 0; u < kPer; ++u) {
+                            const int m = wl + kCoeffWarps * u;
+                            if (m < mte && a < A) {
+                                float r, small, sn, cs;
+                                steer_phase<false>(v[u].x, 0.f, v[u].y, 0.f, s_hi, s_lo, scale, &r, &small);
+                                sincospi_reduced(r, small, &sn, &cs);
+                                if (w_tile) {
+                                    const float w = __ldg(w_tile + static_cast<size_t>(m) * A + a);
+                                    cs *= w;
+                                    sn *= w;
+                                }
+                                const uint32_t hi = pack_half2(cs, sn);
+                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+                                const uint32_t lo = pack_half2(cs - hf.x, sn - hf.y);
+                                const uint32_t row = 2u * static_cast<uint32_t>(m);
+                                const uint32_t d0 = buf + row * 128u + (((static_cast<uint32_t>(lane) >> 2) ^ (row & 7u)) << 4) +
+                                                    ((static_cast<uint32_t>(lane) & 3u) << 2);
+                                const uint32_t d1 = (d0 + 128u) ^ 16u;
+                                st_shared_u32(d0, hi ^ 0x80000000u);
+                                st_shared_u32(d1, __byte_perm(hi, 0u, 0x1032u));
+                                if (parts > 1) {
+                                    st_shared_u32(d0 + part_bytes, lo ^ 0x80000000u);
+                                    st_shared_u32(d1 + part_bytes, __byte_perm(lo, 0u, 0x1032u));
+                                }
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(kBopFull + slot));
+                    }
+                }
+            }
+        } else {
         // cursor of the batch whose loads are in flight: (channel sequence index, N tile, coefficient set, entry)
         uint32_t nk = 0;
         int nc = sched_get(ctl, 0), nit = 0, nsb = 0, ne0 = ctid;
@@ -1124,6 +1297,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 if (lane == 0) mbar_arrive(bar(kBopFull + bb));
             }
         }
+        }
     }
 
     // ---- teardown ----
@@ -1153,14 +1327,15 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
 
 constexpr int kSchedSlots = 64;  // concurrent launches per device that can share the pool without interfering
 using KernelFn = void (*)(const FusedParams, const CUtensorMap, const CUtensorMap);
-// index = 6 * q8 + 2 * variant (0 plain, 1 profiling, 2 time-varying) + merged
-KernelFn const kKernels[12] = {
-    fused_beamform_kernel<false, false, false, false>, fused_beamform_kernel<false, false, false, true>,
-    fused_beamform_kernel<true, false, false, false>,  fused_beamform_kernel<true, false, false, true>,
-    fused_beamform_kernel<false, true, false, false>,  fused_beamform_kernel<false, true, false, true>,
-    fused_beamform_kernel<false, false, true, false>,  fused_beamform_kernel<false, false, true, true>,
-    fused_beamform_kernel<true, false, true, false>,   fused_beamform_kernel<true, false, true, true>,
-    fused_beamform_kernel<false, true, true, false>,   fused_beamform_kernel<false, true, true, true>,
+// index = 6 * q8 + 2 * variant (0 plain, 1 profiling, 2 time-varying) + merged; [12], [13] = K-streamed B (plain, profiling)
+KernelFn const kKernels[14] = {
+    fused_beamform_kernel<false, false, false, false, false>, fused_beamform_kernel<false, false, false, true, false>,
+    fused_beamform_kernel<true, false, false, false, false>,  fused_beamform_kernel<true, false, false, true, false>,
+    fused_beamform_kernel<false, true, false, false, false>,  fused_beamform_kernel<false, true, false, true, false>,
+    fused_beamform_kernel<false, false, true, false, false>,  fused_beamform_kernel<false, false, true, true, false>,
+    fused_beamform_kernel<true, false, true, false, false>,   fused_beamform_kernel<true, false, true, true, false>,
+    fused_beamform_kernel<false, true, true, false, false>,   fused_beamform_kernel<false, true, true, true, false>,
+    fused_beamform_kernel<false, false, false, false, true>,  fused_beamform_kernel<true, false, false, false, true>,
 };
 
 int* g_status_dev[64] = {};  // per-device: 4-int status block + kSchedSlots x {next, done} channel counters
@@ -1257,7 +1432,15 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
             p.dt_lo[b] = static_cast<float>(batch_dt_s[b] - static_cast<double>(p.dt_hi[b]));
         }
     }
-    p.merged = p.parts == 2 && p.nt <= 64;
+    // Many antennas x beams: a whole B tile set no longer fits 64 KiB with a useful width (the voltages would be
+    // re-converted for every narrow N tile).  Stream B by 32-antenna k-blocks instead: N tiles of up to 128 columns.
+    const bool kstream = p.nt_count > 1 && !q8 && !batch_dt_s && p.ht_count <= 2 && !(flags & DCBF_FLAG_DEBUG_NO_KSTREAM);
+    if (kstream) {
+        const int n_pad = ((2 * M + 15) / 16) * 16;
+        p.nt_count = (n_pad + 127) / 128;
+        p.nt = ((((n_pad + p.nt_count - 1) / p.nt_count) + 31) / 32) * 32;
+    }
+    p.merged = !kstream && p.parts == 2 && p.nt <= 64;
     p.tma_store = !(flags & DCBF_FLAG_DEBUG_DIRECT_EPILOGUE) && (M % (q8 ? 8 : 2) == 0) && (p.nt_count == 1 || p.nt % 32 == 0);
     if (static_cast<long long>(B) * kPols * C > 0x7fffffffLL) return DCBF_ERR_UNSUPPORTED;
     if (int e = get_status_block(&p.status)) return e;
@@ -1317,7 +1500,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     DCBF_CUDA_TRY(cudaGetDevice(&dev));
     if (!n_sms[dev]) {
         DCBF_CUDA_TRY(cudaDeviceGetAttribute(&n_sms[dev], cudaDevAttrMultiProcessorCount, dev));
-        for (int i = 0; i < 12; ++i)
+        for (int i = 0; i < 14; ++i)
             DCBF_CUDA_TRY(cudaFuncSetAttribute(kKernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     }
     const int grid = C < n_sms[dev] ? C : n_sms[dev];
@@ -1334,7 +1517,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     // (int8 output, variant, merged) specialisation; variant: 0 plain, 1 profiling, 2 time-varying steering (the
     // profiler has no time-varying build)
     const int variant = batch_dt_s ? 2 : p.prof ? 1 : 0;
-    auto kernel = kKernels[(q8 ? 6 : 0) + 2 * variant + (p.merged ? 1 : 0)];
+    auto kernel = kstream ? kKernels[12 + (p.prof ? 1 : 0)] : kKernels[(q8 ? 6 : 0) + 2 * variant + (p.merged ? 1 : 0)];
     DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, p, tm_in, tm_out));
     DCBF_CHECK_LAUNCH("fused_beamform_kernel");
     return DCBF_OK;

@@ -512,6 +512,35 @@ def test_concurrent_launches_on_several_streams_do_not_share_the_channel_queue(d
             assert torch.equal(outs[i][rep], want[i]), (i, rep)
 
 
+@pytest.mark.parametrize("case", [(1, 197, 3, 256, 256, 4096, 1), (2, 45, 4, 128, 131, 512, 0), (3, 64, 2, 48, 80, 256, 2),
+                                  (1, 33, 150, 16, 70, 4096, 5)],
+                         ids=["C5_geometry", "odd_beams_direct_epilogue_2_heaps", "3_heaps_partial_tile", "150_channels"])
+def test_k_streamed_b_tiles_match_whole_tile_sets(dropin, case):
+    """Many antennas x beams switch the fused kernel to K-streamed B tiles (a ring of 32-antenna k-blocks, N tiles up
+    to 128 columns, all time-tile accumulators open at once).  Same result as the whole-tile-set mode
+    (DCBF_FLAG_DEBUG_NO_KSTREAM) to float32 rounding, and both inside the oracle budget."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m, n, xid = case
+    assert _capi.fused_tiling(a, m)[2] > 1  # the shape really needs several N tiles
+    x = orc.make_samples(b, a, c, t, seed=3 * a)
+    dv = orc.make_delay_vals_random(c, m, a, seed=5 * m)
+    dx, ddv = torch.from_numpy(x).cuda(), torch.from_numpy(dv).cuda()
+    outs = []
+    for flags in (0, _capi.FLAG_DEBUG_NO_KSTREAM):
+        o = torch.full((b, 2, c, t // 16, 16, 2 * m), float("nan"), dtype=torch.float32, device="cuda")
+        _capi.fused(dx, ddv, o, b, a, c, n, t, m, xid, TS, flags)
+        _capi.fused_status()
+        outs.append(o.cpu().numpy().astype(np.float64))
+    ref = orc.beamform_pipeline(x, dv, n, xid, TS)
+    for o in outs:
+        assert not np.isnan(o).any()
+        assert np.all(np.abs(o - ref) <= 2.0 ** -8 * _budget(x) + 1e-3)
+    np.testing.assert_allclose(outs[0], outs[1], rtol=0, atol=float(_budget(x).max()) * 2.0 ** -8)
+
+
 def test_fused_matches_three_kernel_chain_and_materialises_intermediates(dropin):
     from beamforming.beamform_op_sequence import OpSequenceTemplate
 
