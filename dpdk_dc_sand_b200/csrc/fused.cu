@@ -1123,31 +1123,36 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         ok = mbar_wait<kProf>(bar(kBopEmpty + slot), ((kstep / kBopSlots) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + slot, ps + 0);
                         if (!ok) break;
                         const int a = kKbAnts * kb + lane;
-                        const uint32_t buf = bop_base + slot * kBopSlotBytes;
+                        // beam m = wl + 8 u: row 2 m has the same swizzle phase for every u, so the four words of
+                        // entry u sit at a constant 2048-byte stride from those of entry 0
+                        const uint32_t row0 = 2u * static_cast<uint32_t>(wl);
+                        const uint32_t d_base = bop_base + slot * kBopSlotBytes + row0 * 128u +
+                                                (((static_cast<uint32_t>(lane) >> 2) ^ (row0 & 7u)) << 4) +
+                                                ((static_cast<uint32_t>(lane) & 3u) << 2);
+                        if (a < A) {
 #pragma unroll
-                        for (int u = 0; u < kPer; ++u) {
-                            const int m = wl + kCoeffWarps * u;
-                            if (m < mte && a < A) {
-                                float r, small, sn, cs;
-                                steer_phase<false>(v[u].x, 0.f, v[u].y, 0.f, s_hi, s_lo, scale, &r, &small);
-                                sincospi_reduced(r, small, &sn, &cs);
-                                if (w_tile) {
-                                    const float w = __ldg(w_tile + static_cast<size_t>(m) * A + a);
-                                    cs *= w;
-                                    sn *= w;
-                                }
-                                const uint32_t hi = pack_half2(cs, sn);
-                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-                                const uint32_t lo = pack_half2(cs - hf.x, sn - hf.y);
-                                const uint32_t row = 2u * static_cast<uint32_t>(m);
-                                const uint32_t d0 = buf + row * 128u + (((static_cast<uint32_t>(lane) >> 2) ^ (row & 7u)) << 4) +
-                                                    ((static_cast<uint32_t>(lane) & 3u) << 2);
-                                const uint32_t d1 = (d0 + 128u) ^ 16u;
-                                st_shared_u32(d0, hi ^ 0x80000000u);
-                                st_shared_u32(d1, __byte_perm(hi, 0u, 0x1032u));
-                                if (parts > 1) {
-                                    st_shared_u32(d0 + part_bytes, lo ^ 0x80000000u);
-                                    st_shared_u32(d1 + part_bytes, __byte_perm(lo, 0u, 0x1032u));
+                            for (int u = 0; u < kPer; ++u) {
+                                const int m = wl + kCoeffWarps * u;
+                                if (m < mte) {
+                                    float r, small, sn, cs;
+                                    steer_phase<false>(v[u].x, 0.f, v[u].y, 0.f, s_hi, s_lo, scale, &r, &small);
+                                    sincospi_reduced(r, small, &sn, &cs);
+                                    if (w_tile) {
+                                        const float w = __ldg(w_tile + static_cast<size_t>(m) * A + a);
+                                        cs *= w;
+                                        sn *= w;
+                                    }
+                                    const uint32_t hi = pack_half2(cs, sn);
+                                    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+                                    const uint32_t lo = pack_half2(cs - hf.x, sn - hf.y);
+                                    const uint32_t d0 = d_base + static_cast<uint32_t>(u) * (2u * kCoeffWarps * 128u);
+                                    const uint32_t d1 = (d0 + 128u) ^ 16u;
+                                    st_shared_u32(d0, hi ^ 0x80000000u);
+                                    st_shared_u32(d1, __byte_perm(hi, 0u, 0x1032u));
+                                    if (parts > 1) {
+                                        st_shared_u32(d0 + part_bytes, lo ^ 0x80000000u);
+                                        st_shared_u32(d1 + part_bytes, __byte_perm(lo, 0u, 0x1032u));
+                                    }
                                 }
                             }
                         }
