@@ -60,7 +60,8 @@ constexpr int kThreads = 19 * 32;
 constexpr int kTileT = 128;    // samples per MMA tile (UMMA M)
 constexpr int kSlabAnts = 16;  // antennas per raw slab / A stage
 constexpr int kKbAnts = 32;    // antennas per B k-block (128-byte swizzle row of fp16)
-constexpr int kRawStages = 4;
+constexpr int kRawStages = 4;      // raw stages with their own shared memory ...
+constexpr int kMaxRawStages = 8;   // ... plus up to 4 more in the unused tail of the two B buffers (narrow N tiles)
 constexpr int kAopStages = 2;
 constexpr int kBopBufs = 2;
 constexpr int kBopSlots = 4;    // kStream: B k-block ring (4 x 32 KiB) instead of 2 whole tile sets
@@ -77,7 +78,8 @@ constexpr unsigned long long kWatchdogNs = 2000000000ull;  // 2 s without progre
 
 constexpr int kSmemData = kAopStages * kAopStageBytes + kBopBufs * kBopBufBytes + kRawStages * kRawStageBytes + kOutStageBytes;
 constexpr int kGainTabBytes = 64 * 8;  // q8: (gain, clip level) of the <= 64 beams of a single N tile
-constexpr int kSmemBytes = 1024 /*alignment slack*/ + kSmemData + 512 /*barriers + control*/ + kGainTabBytes;
+constexpr int kCtlBytes = 640;  // 320 B of mbarriers + Control
+constexpr int kSmemBytes = 1024 /*alignment slack*/ + kSmemData + kCtlBytes + kGainTabBytes;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 enum Role { kRoleProducer = 1, kRoleMma = 2, kRoleEpilogue = 3, kRoleConvert = 4, kRoleCoeff = 5 };
@@ -105,6 +107,8 @@ struct FusedParams {
     int q8_wide;     // q8 only: the N tile is the whole output row (32 / 64 / 128 bytes): one box per 32 rows
     int sb_count;    // coefficient sets per (channel, N tile): 1, or B with time-varying steering
     int ub;          // batches sharing one coefficient set: B, or 1 with time-varying steering
+    int raw_stages;  // depth of the raw TMA ring: kRawStages + extra stages placed behind the B tiles
+    int raw_extra_off;  // byte offset of the first extra stage inside each 64 KiB B buffer
     float dt_hi[DCBF_MAX_TV_BATCHES], dt_lo[DCBF_MAX_TV_BATCHES];  // per-batch time offset (s) as a float pair
     double chan_centre;      // absolute index of local channel 0, minus N/2
     double turns_per_delay;  // -1 / (N * Ts): half-turns of phase per (second of delay x channel offset)
@@ -498,20 +502,27 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     const uint32_t aop_base = ost_base + kOutStageBytes;                    // [stage][pol][128 x 64 B]
     const uint32_t raw_base = aop_base + kAopStages * kAopStageBytes;       // [stage][ant][t][4 B]
     const uint32_t bar_base = raw_base + kRawStages * kRawStageBytes;       // 8-byte mbarriers
-    Control* ctl = reinterpret_cast<Control*>(smem_gen + kSmemData + 192);
+    Control* ctl = reinterpret_cast<Control*>(smem_gen + kSmemData + 320);
 
     // barrier ids (also reported by the watchdog)
-    const int kRawFull = 0, kRawEmpty = kRawFull + kRawStages, kAopFull = kRawEmpty + kRawStages,
+    const int kRawFull = 0, kRawEmpty = kRawFull + kMaxRawStages, kAopFull = kRawEmpty + kMaxRawStages,
               kAopEmpty = kAopFull + kAopStages, kBopFull = kAopEmpty + kAopStages, kBopEmpty = kBopFull + kBopSlots,
               kAccFull = kBopEmpty + kBopSlots, kAccEmpty = kAccFull + kAccBufs, kNumBars = kAccEmpty + kAccBufs;
-    static_assert(2 * (kRawStages + kAopStages + kBopSlots + kAccBufs) * 8 <= 192, "barrier area");
+    static_assert(2 * (kMaxRawStages + kAopStages + kBopSlots + kAccBufs) * 8 <= 320, "barrier area");
+    static_assert(320 + sizeof(Control) <= kCtlBytes, "control area");
+    // raw stage s: its own 8 KiB for s < kRawStages, else alternately behind the tiles of B buffer 0 / 1
+    const uint32_t raw_stages = static_cast<uint32_t>(prm.raw_stages);
+    auto raw_addr = [&](uint32_t s) {
+        return s < kRawStages ? raw_base + s * kRawStageBytes
+                              : bop_base + ((s - kRawStages) & 1u) * kBopBufBytes + prm.raw_extra_off + ((s - kRawStages) >> 1) * kRawStageBytes;
+    };
     auto bar = [&](int id) { return bar_base + 8u * static_cast<uint32_t>(id); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- one-time setup ----
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kRawStages; ++s) {
+        for (int s = 0; s < kMaxRawStages; ++s) {
             mbar_init(bar(kRawFull + s), 1);
             mbar_init(bar(kRawEmpty + s), 4);
         }
@@ -539,7 +550,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         for (int i = threadIdx.x; i < kBopBufs * kBopBufBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async_smem();
     }
-    const uint32_t gain_tab_cta = smem_base + kSmemData + 512;
+    const uint32_t gain_tab_cta = smem_base + kSmemData + kCtlBytes;
     if (kQ8 && prm.q8_wide && threadIdx.x < 64) {  // one table for the CTA (single N tile); padding beams: gain 0
         const int m = threadIdx.x;
         const float gi = m < prm.M ? __ldg(prm.gains + m) : 0.f;
@@ -570,7 +581,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
 
     if (warp == kProducerWarp) {
         // =================================== TMA producer ===================================
-        uint32_t slab = 0;
+        uint32_t rs = 0, ph = 0;
         bool ok = true;
         // slab order inside a (channel, N tile, batch): time tile outer, antenna slab inner; kStream: slab outer
         // (every B k-block is then used for both time tiles before it is released)
@@ -579,17 +590,16 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             for (int it = 0; it < prm.nt_count && ok; ++it)
                 for (int b = 0; b < B && ok; ++b)
                     for (int o = 0; o < n_outer && ok; ++o)
-                        for (int i = 0; i < n_inner; ++i, ++slab) {
+                        for (int i = 0; i < n_inner; ++i) {
                             const int h = kStream ? i : o, s = kStream ? o : i;
-                            const uint32_t rs = slab % kRawStages, ph = (slab / kRawStages) & 1u;
                             ok = mbar_wait<kProf>(bar(kRawEmpty + rs), ph ^ 1u, ctl, prm.status, kRoleProducer, kRawEmpty + rs, ps + 0);
                             if (!ok) break;
                             if (elect_one()) {
                                 mbar_arrive_expect_tx(bar(kRawFull + rs), kRawStageBytes);
-                                tma_load_4d(raw_base + rs * kRawStageBytes, &tm_in, bar(kRawFull + rs), h * kTileT, c,
-                                            s * kSlabAnts, b);
+                                tma_load_4d(raw_addr(rs), &tm_in, bar(kRawFull + rs), h * kTileT, c, s * kSlabAnts, b);
                             }
                             __syncwarp();
+                            if (++rs == raw_stages) rs = 0, ph ^= 1u;
                         }
     } else if (warp == kMmaWarp || warp == kMmaWarp2) {
         // =================================== MMA issuer ===================================
@@ -955,21 +965,21 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         const uint32_t bias = prm.signed_in ? 0x64806480u : 0x64006400u;  // 1152 | 1024 as fp16 pairs
         const uint32_t flip = prm.signed_in ? 0x80808080u : 0u;
         const uint32_t sw = static_cast<uint32_t>((t >> 1) & 3);
-        uint32_t slab = 0;
+        uint32_t slab = 0, rs = 0, rph = 0;
         bool ok = true;
         for (uint32_t k = 0; ok && sched_get(ctl, k) < C; ++k)
             for (int it = 0; it < prm.nt_count && ok; ++it)
                 for (int bh = 0; bh < B * prm.ht_count && ok; ++bh)
                     for (int s = 0; s < prm.slab_count; ++s, ++slab) {
-                        const uint32_t rs = slab % kRawStages, as = slab % kAopStages;
-                        ok = mbar_wait2<kProf>(bar(kRawFull + rs), (slab / kRawStages) & 1u, kRawFull + rs, bar(kAopEmpty + as),
+                        const uint32_t as = slab % kAopStages;
+                        ok = mbar_wait2<kProf>(bar(kRawFull + rs), rph, kRawFull + rs, bar(kAopEmpty + as),
                                                ((slab / kAopStages) & 1u) ^ 1u, kAopEmpty + as, ctl, prm.status, kRoleConvert, ps + 0);
                         if (!ok) break;
                         // antennas beyond A were zero-filled by the TMA box: byte 0 -> value 0 (u8), and
                         // 0 ^ 0x80 - 128 -> 0 (i8), so the K padding of the operand needs no special case
                         unsigned long long tc0 = 0, tc1 = 0;
                         if (kProf && prof_lane) tc0 = global_ns();
-                        const uint32_t src = raw_base + rs * kRawStageBytes + t * 4;
+                        const uint32_t src = raw_addr(rs) + t * 4;
                         const uint32_t dst0 = aop_base + as * kAopStageBytes + t * 64;
                         // all 16 loads first (the volatile shared-memory accesses keep their program order, so
                         // interleaving them with the stores would expose the load latency once per chunk)
@@ -994,6 +1004,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                             mbar_arrive(bar(kAopFull + as));
                             mbar_arrive(bar(kRawEmpty + rs));
                         }
+                        if (++rs == raw_stages) rs = 0, rph ^= 1u;
                         if (kProf && prof_lane)  // slot 2: (LDS + convert + STS) | (fence + arrive) << 32
                             ctl->wait_ns[kRoleConvert][2] += (tc1 - tc0) | ((global_ns() - tc1) << 32);
                     }
@@ -1446,6 +1457,17 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
         p.nt = ((((n_pad + p.nt_count - 1) / p.nt_count) + 31) / 32) * 32;
     }
     p.merged = !kstream && p.parts == 2 && p.nt <= 64;
+    // Raw ring depth: narrow N tiles leave the tail of both 64 KiB B buffers unused; every spare 8 KiB becomes one
+    // more TMA stage in flight (HBM latency x bandwidth per SM is ~40 KiB, the dedicated 4 stages hold 32 KiB)
+    p.raw_stages = kRawStages;
+    if (!kstream) {
+        const int used = p.kb_count * p.parts * p.nt * 128;
+        const int spare = (kBopBufBytes - used) / kRawStageBytes;
+        p.raw_extra_off = used;
+        p.raw_stages = kRawStages + 2 * std::min(spare, (kMaxRawStages - kRawStages) / 2);
+        static const int forced = [] { const char* e = getenv("DCBF_DEBUG_RAW_STAGES"); return e ? atoi(e) : 0; }();
+        if (forced >= 1 && forced <= p.raw_stages) p.raw_stages = forced;
+    }
     p.tma_store = !(flags & DCBF_FLAG_DEBUG_DIRECT_EPILOGUE) && (M % (q8 ? 8 : 2) == 0) && (p.nt_count == 1 || p.nt % 32 == 0);
     if (static_cast<long long>(B) * kPols * C > 0x7fffffffLL) return DCBF_ERR_UNSUPPORTED;
     if (int e = get_status_block(&p.status)) return e;
