@@ -25,6 +25,7 @@ FLAG_FP16_COEFF = 0x2
 FLAG_STREAMING = 0x4
 FLAG_DEBUG_DIRECT_EPILOGUE = 0x100
 FLAG_DEBUG_NO_KSTREAM = 0x200
+FLAG_DEBUG_CUDA_CORES = 0x400
 
 _ROLE_NAMES = {1: "producer", 2: "mma", 3: "epilogue", 4: "convert", 5: "coeff"}
 

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdcbf.so")
-SOURCES = ["api.cu", "reorder.cu", "coeffs.cu", "beamform.cu", "fused.cu", "host_pipeline.cu", "host_ingest.cu"]
+SOURCES = ["api.cu", "reorder.cu", "coeffs.cu", "beamform.cu", "beamform_tc.cu", "fused.cu", "host_pipeline.cu", "host_ingest.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

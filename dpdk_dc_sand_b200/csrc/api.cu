@@ -116,6 +116,8 @@ int dcbf_beamform(const uint8_t* reordered, const float* coeffs, float* beams, i
         return DCBF_ERR_INVALID_ARG;
     if (!aligned16(reordered) || !aligned16(coeffs) || !aligned16(beams)) return DCBF_ERR_INVALID_ARG;
     if (int e = check_device()) return e;
+    if (!(flags & DCBF_FLAG_DEBUG_CUDA_CORES) && beamform_tc_supported(reordered, coeffs, beams, A, M))
+        return launch_beamform_tc(reordered, coeffs, beams, B, C, T, A, M, flags, static_cast<cudaStream_t>(stream));
     return launch_beamform(reordered, coeffs, beams, B, C, T, A, M, flags, static_cast<cudaStream_t>(stream));
 }
 

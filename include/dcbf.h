@@ -66,6 +66,7 @@ typedef enum dcbf_status {
                                        CTAs may start on SMs that kernel has already left (programmatic dependent
                                        launch).  Copies and events keep their normal stream ordering. */
 #define DCBF_FLAG_DEBUG_NO_KSTREAM 0x200u /* dcbf_fused: keep whole B tile sets even when several N tiles are needed (cross-check) */
+#define DCBF_FLAG_DEBUG_CUDA_CORES 0x400u /* dcbf_beamform: float32 CUDA-core kernel even where the tcgen05 one applies (cross-check) */
 #define DCBF_FLAG_DEBUG_DIRECT_EPILOGUE 0x100u /* dcbf_fused: st.global from registers instead of TMA stores (cross-check) */
 
 int dcbf_version(void);

@@ -106,7 +106,8 @@ def test_coeff_generator_random(dropin, n_ants, n_beams, xid):
     np.testing.assert_array_equal(got[..., 1::2, 1::2], got[..., 0::2, 0::2])
 
 
-@pytest.mark.parametrize("n_ants,n_beams,signed", [(4, 2, False), (64, 16, False), (23, 5, True), (130, 2, False)])
+@pytest.mark.parametrize("n_ants,n_beams,signed", [(4, 2, False), (64, 16, False), (23, 5, True), (130, 2, False),
+                                                   (80, 32, True), (64, 64, False)])
 def test_matrix_multiply(dropin, n_ants, n_beams, signed):
     from beamforming.matrix_multiply import MatrixMultiplyTemplate
 
@@ -125,6 +126,45 @@ def test_matrix_multiply(dropin, n_ants, n_beams, signed):
     ref = orc.beamform(re, co, signed_input=signed)
     scale = np.abs(orc.beamform(re, np.abs(co), signed_input=False))  # sum |x||w|
     assert np.all(np.abs(got - ref) <= 1e-5 * scale + 1e-6)
+
+
+TC_CASES = [  # B, C, T, A, M, signed: shapes the tcgen05 stand-alone kernel takes (A % 8 == 0, M even)
+    (1, 3, 128, 16, 16, False), (2, 3, 64, 64, 16, False), (1, 5, 256, 64, 64, False), (1, 2, 384, 80, 32, True),
+    (1, 2, 256, 8, 2, False), (1, 3, 640, 72, 6, False), (1, 2, 256, 136, 130, False), (1, 2, 48, 24, 70, True),
+    (1, 300, 256, 64, 64, False),  # more work items than SMs: the persistent loop wraps and the rings change phase
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "B{}C{}T{}A{}M{}s{:d}".format(*c))
+def test_beamform_tensor_core_kernel(dropin, case):
+    """dcbf_beamform on its tcgen05 path (bf16 x 3-term bf16 split of ARBITRARY float32 coefficients, here spanning
+    2^-20 .. 2^20): within a few float32 ulps of sum |x||w| of the float64 value, like the float32 CUDA-core kernel
+    it is cross-checked against (DCBF_FLAG_DEBUG_CUDA_CORES); every output element is written."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, c, t, n_ants, n_beams, signed = case
+    rng = np.random.default_rng(31)
+    re = rng.integers(0, 256, (b, 2, c, t // 16, 16, n_ants, 2), dtype=np.uint8)
+    co = rng.standard_normal((b, 2, c, 2 * n_ants, 2 * n_beams)).astype(np.float32)
+    co *= np.exp2(rng.integers(-20, 21, co.shape)).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    d_re, d_co = torch.from_numpy(re).to(dev), torch.from_numpy(co).to(dev)
+    outs = []
+    for extra in (0, _capi.FLAG_DEBUG_CUDA_CORES):
+        out = torch.full((b, 2, c, t // 16, 16, 2 * n_beams), float("nan"), dtype=torch.float32, device=dev)
+        _capi.beamform(d_re, d_co, out, b, c, t, n_ants, n_beams, (_capi.FLAG_SIGNED_INPUT if signed else 0) | extra)
+        torch.cuda.synchronize()
+        _capi.fused_status()  # the in-kernel watchdog reports through the same status block
+        outs.append(out.cpu().numpy())
+    ref = orc.beamform(re, co.astype(np.float64), signed_input=signed)
+    xs = re.view(np.int8) if signed else re
+    scale = np.abs(orc.beamform(np.abs(xs.astype(np.int16)).astype(np.uint8), np.abs(co).astype(np.float64), signed_input=False))
+    for got in outs:
+        assert not np.isnan(got).any()
+        assert np.all(np.abs(got - ref) <= 4e-6 * scale + 1e-30)
+    assert np.all(np.abs(outs[0] - outs[1]) <= 4e-6 * scale + 1e-30)
 
 
 @pytest.mark.parametrize("n_ants", [4, 64, 79, 19])
