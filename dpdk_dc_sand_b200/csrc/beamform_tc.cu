@@ -11,13 +11,13 @@
 //
 // HBM-bound: per unit it reads T x 2A bytes + 2A x 2M x 4 bytes and writes T x 2M x 4 bytes, each once.
 //
-// One persistent CTA per SM, 19 warps:
+// One persistent CTA per SM, 20 warps:
 //   warps 0-7   split     W k-block (TMA-staged float32, 128B-swizzled 32x32 boxes) -> 3 bf16 K-major B tiles
 //   warps 8-11  convert   X stage ([128 t][32 B] bytes, 32B-swizzled) -> bf16 K-major A stage (64B swizzle)
 //   warps 12-15 epilogue  TMEM -> registers -> 128B-swizzled staging -> TMA tensor store
-//   warp 16     X producer (TMA), warp 17 W producer (TMA), warp 18 MMA issuer
+//   warp 16     X producer (TMA), warp 17 W producer (TMA), warps 18-19 MMA issuers (one per time tile of a group)
 // A work item is (unit, N tile of <= 128 columns, group of <= 2 time tiles); its k-blocks of 32 contraction
-// elements (16 antennas) stream through a 4-slot B ring while both time tiles' accumulators stay open, and the
+// elements (16 antennas) stream through a 2-slot B ring while both time tiles' accumulators stay open, and the
 // accumulators are double-buffered across items so the epilogue of one overlaps the MMAs of the next.
 //
 // Shapes the TMA descriptors cannot express (2A or 8M not a multiple of 16 bytes, i.e. A % 8 != 0 or M odd)
@@ -38,18 +38,19 @@ constexpr int kConvertWarp0 = 8;
 constexpr int kEpilogueWarp0 = 12;  // warp % 4 = TMEM lane quarter
 constexpr int kXProducerWarp = 16;
 constexpr int kWProducerWarp = 17;
-constexpr int kMmaWarp = 18;
-constexpr int kThreads = 19 * 32;
+constexpr int kMmaWarp = 18;   // MMAs of a group's first time tile (and owns the TMEM allocation)
+constexpr int kMmaWarp2 = 19;  // second time tile: the issue path, not the tensor pipe, limits narrow tiles
+constexpr int kThreads = 20 * 32;
 constexpr int kTileT = 128;  // samples per MMA tile (UMMA M)
 constexpr int kKb = 32;      // contraction elements per k-block: 16 antennas x (re, im) = two K = 16 MMA steps
 constexpr int kParts = 3;    // bf16 hi + mid + lo
 constexpr int kNtMax = 128;
-constexpr int kBSlots = 4;
+constexpr int kBSlots = 2;
 constexpr int kBSlotBytes = kParts * kNtMax * 64;  // [part][n][32 bf16], 64B swizzle
-constexpr int kWStages = 2;
+constexpr int kWStages = 4;
 constexpr int kWBoxBytes = 32 * 128;               // 32 k rows x 32 float32 columns, 128B swizzle
 constexpr int kWStageBytes = (kNtMax / 32) * kWBoxBytes;
-constexpr int kXStages = 8;
+constexpr int kXStages = 12;
 constexpr int kXStageBytes = kTileT * kKb;         // [t][32 bytes], 32B swizzle
 constexpr int kAStages = 4;
 constexpr int kAStageBytes = kTileT * 64;          // [t][32 bf16], 64B swizzle
@@ -61,7 +62,7 @@ constexpr int kTmemCols = 512;  // kAccBufs x kGroupTiles x kNtMax
 
 constexpr int kSmemData = kBSlots * kBSlotBytes + kWStages * kWStageBytes + kOutStageBytes + kAStages * kAStageBytes +
                           kXStages * kXStageBytes;
-constexpr int kBarBytes = 320;
+constexpr int kBarBytes = 384;
 constexpr int kCtlBytes = 640;
 constexpr int kSmemBytes = 1024 /*alignment slack*/ + kSmemData + kCtlBytes;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -77,6 +78,7 @@ struct TcParams {
     int ht_count;     // ceil(T / 128)
     int hg_count;     // ceil(ht_count / 2)
     int signed_in;
+    int mma_warps;    // 2: one issuing warp per time tile of a group (narrow tiles are issue-bound); 1: wide tiles
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -135,10 +137,10 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
         }
         for (int s = 0; s < kBSlots; ++s) {
             mbar_init(bar(kBFull + s), kSplitWarps);
-            mbar_init(bar(kBEmpty + s), 1);
+            mbar_init(bar(kBEmpty + s), prm.mma_warps);  // one tcgen05.commit per MMA warp
         }
         for (int s = 0; s < kAccBufs; ++s) {
-            mbar_init(bar(kAccFull + s), 1);
+            mbar_init(bar(kAccFull + s), prm.mma_warps);
             mbar_init(bar(kAccEmpty + s), 4);
         }
         ctl->abort = 0;
@@ -206,8 +208,9 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
                 if (++ws == kWStages) ws = 0, ph ^= 1u;
             }
         }
-    } else if (warp == kMmaWarp) {
-        // =================================== MMA issuer ===================================
+    } else if (warp == kMmaWarp || (warp == kMmaWarp2 && prm.mma_warps == 2)) {
+        // =================================== MMA issuers ===================================
+        const int my_h = prm.mma_warps == 1 ? -1 : warp == kMmaWarp ? 0 : 1;  // -1: every time tile
         const uint32_t idesc = make_idesc_f16(nt, true, true);  // bf16 x bf16 (kind::f16 rejects mixed fp16 / bf16 operands)
         const uint32_t a_lo0 = desc_lo(a_base), b_lo0 = desc_lo(b_base), part_lo = part_bytes >> 4;
         uint32_t as = 0, aph = 0, bs = 0, bph = 0, n_item = 0;
@@ -223,6 +226,10 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
                 const int k_steps = min(2, (prm.K2 - s * kKb + 15) >> 4);
                 const uint32_t b_lo = b_lo0 + bs * (kBSlotBytes >> 4);
                 for (int h = 0; h < hn && ok; ++h) {
+                    if (my_h >= 0 && h != my_h) {  // the other warp's stage
+                        if (++as == kAStages) as = 0, aph ^= 1u;
+                        continue;
+                    }
                     ok = mbar_wait<false>(bar(kAFull + as), aph, ctl, prm.status, kRoleMma, kAFull + as);
                     if (!ok) break;
                     tc_fence_after();
@@ -335,6 +342,21 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
         // reads (rows 2kp, 2kp+1 of an 8-row group) and the 64B-swizzled bf16-pair writes touch 32 distinct banks.
         const int kp = lane & 3, nn = lane >> 2;
         const int steps = nt >> 1;  // (k group of 8) x (column group of 8) = 4 x nt / 8
+        // Step j = warp + 8 i covers k group j & 3 = warp & 3 and columns 8 (j >> 2) + nn: two steps 16 apart are 32
+        // columns = one W box and 32 B rows apart, so every swizzle term below is fixed per thread.
+        uint32_t src0[2], src1[2], dst[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int j = warp + i * kSplitWarps;
+            const int kg = j & 3, n = (j >> 2) * 8 + nn;  // n < 32
+            const int k = kg * 8 + 2 * kp;
+            const uint32_t col = static_cast<uint32_t>(n & 3) * 4u, chunk = static_cast<uint32_t>(n >> 2);
+            src0[i] = col + k * 128 + ((chunk ^ static_cast<uint32_t>(k & 7)) << 4);
+            src1[i] = col + (k + 1) * 128 + ((chunk ^ static_cast<uint32_t>((k + 1) & 7)) << 4);
+            dst[i] = static_cast<uint32_t>(n) * 64u + ((static_cast<uint32_t>(kg) ^ static_cast<uint32_t>((n >> 1) & 3)) << 4) +
+                     static_cast<uint32_t>(kp) * 4u;
+        }
+        const int rounds = steps >> 4;  // nt / 32
         uint32_t ws = 0, wph = 0, bs = 0, bph = 0;
         for (long long item = blockIdx.x; item < items && ok; item += stride) {
             int u, it, hg, hn;
@@ -343,21 +365,13 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
                 ok = mbar_wait2<false>(bar(kWFull + ws), wph, kWFull + ws, bar(kBEmpty + bs), bph ^ 1u, kBEmpty + bs, ctl,
                                        prm.status, kRoleSplit);
                 if (!ok) break;
-                const uint32_t wst = w_base + ws * kWStageBytes, bsl = b_base + bs * kBSlotBytes;
-                for (int j0 = warp; j0 < steps; j0 += 2 * kSplitWarps) {
+                uint32_t wst = w_base + ws * kWStageBytes, bsl = b_base + bs * kBSlotBytes;
+                for (int r = 0; r < rounds; ++r, wst += kWBoxBytes, bsl += 32 * 64) {
                     float w0[2], w1[2];
-                    uint32_t dst[2];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {  // steps is a multiple of 16: both halves of the pair exist
-                        const int j = j0 + i * kSplitWarps;
-                        const int kg = j & 3, n = (j >> 2) * 8 + nn;
-                        const int k = kg * 8 + 2 * kp;
-                        const uint32_t col = wst + static_cast<uint32_t>(n >> 5) * kWBoxBytes + static_cast<uint32_t>(n & 3) * 4u;
-                        const uint32_t chunk = static_cast<uint32_t>((n & 31) >> 2);
-                        w0[i] = __uint_as_float(ld_shared_u32(col + k * 128 + ((chunk ^ static_cast<uint32_t>(k & 7)) << 4)));
-                        w1[i] = __uint_as_float(ld_shared_u32(col + (k + 1) * 128 + ((chunk ^ static_cast<uint32_t>((k + 1) & 7)) << 4)));
-                        dst[i] = bsl + static_cast<uint32_t>(n) * 64u + ((static_cast<uint32_t>(kg) ^ static_cast<uint32_t>((n >> 1) & 3)) << 4) +
-                                 static_cast<uint32_t>(kp) * 4u;
+                    for (int i = 0; i < 2; ++i) {
+                        w0[i] = __uint_as_float(ld_shared_u32(wst + src0[i]));
+                        w1[i] = __uint_as_float(ld_shared_u32(wst + src1[i]));
                     }
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
@@ -367,9 +381,9 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
                         const uint32_t p_mid = pack_bf16x2(r0, r1);
                         const float s0 = r0 - __uint_as_float(p_mid << 16), s1 = r1 - __uint_as_float(p_mid & 0xffff0000u);
                         const uint32_t p_lo = pack_bf16x2(s0, s1);
-                        st_shared_u32(dst[i], p_hi);
-                        st_shared_u32(dst[i] + part_bytes, p_mid);
-                        st_shared_u32(dst[i] + 2u * part_bytes, p_lo);
+                        st_shared_u32(bsl + dst[i], p_hi);
+                        st_shared_u32(bsl + dst[i] + part_bytes, p_mid);
+                        st_shared_u32(bsl + dst[i] + 2u * part_bytes, p_lo);
                     }
                 }
                 fence_proxy_async_smem();
@@ -413,6 +427,9 @@ int launch_beamform_tc(const uint8_t* reordered, const float* coeffs, float* bea
     p.hg_count = (p.ht_count + kGroupTiles - 1) / kGroupTiles;
     p.items = units * p.nt_count * p.hg_count;
     p.signed_in = (flags & DCBF_FLAG_SIGNED_INPUT) ? 1 : 0;
+    p.mma_warps = p.nt <= 64 ? 2 : 1;
+    static const int forced = [] { const char* e = getenv("DCBF_DEBUG_TC_MMA_WARPS"); return e ? atoi(e) : 0; }();
+    if (forced == 1 || forced == 2) p.mma_warps = forced;
     if (int e = get_status_block(&p.status)) return e;
 
     EncodeTiledFn encode = nullptr;
