@@ -81,6 +81,8 @@ SIGNATURES.update({
     "dcbf_ingest_heap": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "dcbf_ingest_heap_ptr": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.POINTER(C.c_void_p)]),
     "dcbf_ingest_heap_done": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int]),
+    "dcbf_ingest_packet": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "dcbf_ingest_set_frequency": (C.c_int, [C.c_void_p, C.c_longlong]),
     "dcbf_ingest_pop": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong),
                                   C.POINTER(C.c_int), C.c_void_p]),
     "dcbf_ingest_release": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -335,6 +337,20 @@ class Ingest:
             return False
         check(st, "dcbf_ingest_heap")
         return True
+
+    def packet(self, data, default_feng_id=-1) -> bool:
+        """Place the payload of one raw SPEAD-64-48 packet (bytes-like); False if it was dropped or carries no data
+        (late, another sub-band, descriptor heap); ValueError for a malformed packet."""
+        buf = bytes(data)
+        st = load().dcbf_ingest_packet(self._h, buf, len(buf), int(default_feng_id))
+        if st == ERR_UNSUPPORTED:
+            return False
+        check(st, "dcbf_ingest_packet")
+        return True
+
+    def set_frequency(self, first_channel) -> None:
+        """Only accept heaps whose frequency item (0x4103) equals ``first_channel`` (-1: any)."""
+        check(load().dcbf_ingest_set_frequency(self._h, int(first_channel)), "dcbf_ingest_set_frequency")
 
     def pop(self, flush=False):
         """Next finished chunk as ``(samples view, first_timestamp, present[B, A])`` or None.  The view aliases the

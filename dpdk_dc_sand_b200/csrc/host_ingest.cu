@@ -16,6 +16,7 @@
 #include <cstring>
 #include <deque>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -32,6 +33,7 @@ struct Ingest {
         uint8_t* data = nullptr;
         long long index = -1;          // chunk number = timestamp / (B * step); -1: free
         std::vector<uint8_t> present;  // [B * A]
+        std::vector<uint32_t> received;  // [B * A] payload bytes placed so far by dcbf_ingest_packet
         int n_present = 0;
         bool handed_out = false;
     };
@@ -39,6 +41,14 @@ struct Ingest {
     std::deque<int> ready;             // chunk slots waiting for dcbf_ingest_pop, in time order
     long long newest = -1;             // highest chunk index seen
     unsigned long long n_late = 0, n_duplicate = 0, n_bad = 0;
+    long long expect_frequency = -1;   // dcbf_ingest_packet: drop heaps of another sub-band (-1: accept any)
+    // dcbf_ingest_packet: (timestamp, feng_id) of heaps whose later packets do not repeat the item pointers
+    struct HeapKey {
+        long long timestamp;
+        int feng_id;
+    };
+    std::unordered_map<unsigned long long, HeapKey> heap_keys;
+    std::deque<unsigned long long> heap_key_order;
     std::mutex mu;
 };
 
@@ -92,6 +102,7 @@ static int slot_for(Ingest* g, long long index) {
             c.n_present = 0;
             c.handed_out = false;
             std::fill(c.present.begin(), c.present.end(), 0);
+            std::fill(c.received.begin(), c.received.end(), 0u);
             return s;
         }
     }
@@ -162,6 +173,7 @@ int dcbf_ingest_create(dcbf_ingest_t* ingest, int n_chunks, int n_batches, int n
             return DCBF_ERR_UNSUPPORTED;
         }
         c.present.assign(static_cast<size_t>(n_batches) * n_ants, 0);
+        c.received.assign(static_cast<size_t>(n_batches) * n_ants, 0u);
     }
     *ingest = g;
     return DCBF_OK;
@@ -196,6 +208,95 @@ int dcbf_ingest_heap_done(dcbf_ingest_t ingest, long long timestamp, int feng_id
     int slot = 0, cell = 0;
     if (int e = locate(g, timestamp, feng_id, &slot, &cell)) return e;
     mark_present(g, slot, cell);
+    return DCBF_OK;
+}
+
+// SPEAD-64-48 (flavour 4, 64, 48: what MeerKAT F-engines and fgpu_send_prototype.py:18 emit).  Packet = 8-byte header
+// {0x53, 0x04, item-pointer id bytes = 2, heap-address bytes = 6, reserved u16, n_items u16}, n_items big-endian
+// 64-bit item pointers {immediate flag : 1, id : 15, value or payload address : 48}, then the payload bytes.
+int dcbf_ingest_packet(dcbf_ingest_t ingest, const void* packet, size_t length, int default_feng_id) {
+    auto* g = static_cast<Ingest*>(ingest);
+    if (!g || !packet) return DCBF_ERR_INVALID_ARG;
+    const auto* p = static_cast<const uint8_t*>(packet);
+    std::lock_guard<std::mutex> lock(g->mu);
+    auto bad = [&]() {
+        ++g->n_bad;
+        return DCBF_ERR_INVALID_ARG;
+    };
+    if (length < 8 || p[0] != 0x53 || p[1] != 0x04 || p[2] != 2 || p[3] != 6) return bad();
+    const size_t n_items = (static_cast<size_t>(p[6]) << 8) | p[7];
+    if (length < 8 + 8 * n_items) return bad();
+    long long heap_cnt = -1, heap_size = -1, heap_offset = -1, payload_len = -1, timestamp = -1, feng_id = -1,
+              frequency = -1, raw_addr = -1;
+    bool descriptor = false;
+    for (size_t i = 0; i < n_items; ++i) {
+        unsigned long long w = 0;
+        for (int b = 0; b < 8; ++b) w = (w << 8) | p[8 + 8 * i + b];
+        const bool immediate = (w >> 63) != 0;
+        const unsigned id = static_cast<unsigned>((w >> 48) & 0x7fffu);
+        const long long v = static_cast<long long>(w & 0xffffffffffffull);
+        switch (id) {
+            case 0x0001: heap_cnt = v; break;
+            case 0x0002: heap_size = v; break;
+            case 0x0003: heap_offset = v; break;
+            case 0x0004: payload_len = v; break;
+            case 0x0005: descriptor = true; break;
+            case 0x1600: if (immediate) timestamp = v; break;
+            case 0x4101: if (immediate) feng_id = v; break;
+            case 0x4103: if (immediate) frequency = v; break;
+            case 0x4300: if (!immediate) raw_addr = v; break;
+            default: break;  // other items (stream control, engine-specific immediates) do not concern the layout
+        }
+    }
+    const size_t header = 8 + 8 * n_items;
+    if (heap_cnt < 0 || heap_offset < 0 || payload_len < 0 || static_cast<size_t>(payload_len) != length - header) return bad();
+    if (descriptor) return DCBF_ERR_UNSUPPORTED;  // descriptor heaps carry no data
+    if (timestamp >= 0) {  // first packet of a heap (or a sender that repeats the pointers): remember the heap's place
+        if (feng_id < 0) feng_id = default_feng_id;
+        if (g->heap_keys.find(static_cast<unsigned long long>(heap_cnt)) == g->heap_keys.end()) {
+            g->heap_key_order.push_back(static_cast<unsigned long long>(heap_cnt));
+            if (g->heap_key_order.size() > 4096) {
+                g->heap_keys.erase(g->heap_key_order.front());
+                g->heap_key_order.pop_front();
+            }
+        }
+        g->heap_keys[static_cast<unsigned long long>(heap_cnt)] = {timestamp, static_cast<int>(feng_id)};
+        if (g->expect_frequency >= 0 && frequency >= 0 && frequency != g->expect_frequency) {
+            g->heap_keys[static_cast<unsigned long long>(heap_cnt)].feng_id = -2;  // another engine's sub-band
+            return DCBF_ERR_UNSUPPORTED;
+        }
+    } else {
+        const auto it = g->heap_keys.find(static_cast<unsigned long long>(heap_cnt));
+        if (it == g->heap_keys.end()) {  // overtook its heap's first packet: cannot be placed
+            ++g->n_late;
+            return DCBF_ERR_UNSUPPORTED;
+        }
+        timestamp = it->second.timestamp;
+        feng_id = it->second.feng_id;
+        if (feng_id == -2) return DCBF_ERR_UNSUPPORTED;
+    }
+    if (raw_addr < 0) raw_addr = 0;  // the payload of an F-engine heap is the feng_raw item alone
+    if ((heap_size >= 0 && static_cast<size_t>(heap_size) != g->heap_bytes) || raw_addr != 0 ||
+        static_cast<size_t>(heap_offset) + static_cast<size_t>(payload_len) > g->heap_bytes)
+        return bad();
+    int slot = 0, cell = 0;
+    if (int e = locate(g, timestamp, static_cast<int>(feng_id), &slot, &cell)) return e;
+    auto& c = g->chunks[slot];
+    if (c.present[cell]) {
+        ++g->n_duplicate;
+        return DCBF_OK;
+    }
+    memcpy(c.data + static_cast<size_t>(cell) * g->heap_bytes + heap_offset, p + header, static_cast<size_t>(payload_len));
+    c.received[cell] += static_cast<uint32_t>(payload_len);
+    if (c.received[cell] >= g->heap_bytes) mark_present(g, slot, cell);
+    return DCBF_OK;
+}
+
+int dcbf_ingest_set_frequency(dcbf_ingest_t ingest, long long first_channel) {
+    auto* g = static_cast<Ingest*>(ingest);
+    if (!g) return DCBF_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(g->mu);
+    g->expect_frequency = first_channel;
     return DCBF_OK;
 }
 

@@ -185,7 +185,8 @@ int dcbf_host_plan_destroy(dcbf_host_plan_t plan);
  * heaps are placed by (timestamp, feng_id) in any arrival order; n_chunks/2 chunks can be receiving at once, the
  * rest hold finished chunks until released.  A chunk is finished when all its heaps have arrived, or when newer
  * heaps push the window past it (missing heaps are zero-filled and reported).  No network code: the receive loop
- * calls dcbf_ingest_heap (copy) or dcbf_ingest_heap_ptr + dcbf_ingest_heap_done (write in place).
+ * calls dcbf_ingest_packet (raw SPEAD packets), dcbf_ingest_heap (copy of a complete heap) or
+ * dcbf_ingest_heap_ptr + dcbf_ingest_heap_done (write in place).
  * timestamp_step = ADC samples between consecutive heaps of one antenna; pinned = 0 uses ordinary memory (no GPU
  * needed, for tests).  Thread-safe.  dcbf_ingest_heap returns DCBF_ERR_UNSUPPORTED for a heap that was dropped
  * (too old, duplicate of a closed chunk, or no free chunk because the consumer is behind). */
@@ -195,6 +196,15 @@ int dcbf_ingest_create(dcbf_ingest_t* ingest, int n_chunks, int n_batches, int n
 int dcbf_ingest_heap(dcbf_ingest_t ingest, long long timestamp, int feng_id, const void* payload);
 int dcbf_ingest_heap_ptr(dcbf_ingest_t ingest, long long timestamp, int feng_id, void** dst);
 int dcbf_ingest_heap_done(dcbf_ingest_t ingest, long long timestamp, int feng_id);
+/* One SPEAD-64-48 packet as received from the network (the wire format of fgpu_send_prototype.py:18,55-60 and of the
+ * MeerKAT F-engines): its payload is written straight to its place in the chunk (heap offset item 0x0003), the heap
+ * counts as arrived once all its bytes have.  timestamp 0x1600 and feng_id 0x4101 are taken from the packet, or, for
+ * packets that do not repeat the item pointers, from the heap's first packet (a packet that overtakes it is dropped);
+ * default_feng_id is used when the sender has no 0x4101 item (the prototype: one sender = one antenna), -1 = none.
+ * Descriptor heaps and heaps of another sub-band (dcbf_ingest_set_frequency, item 0x4103) return
+ * DCBF_ERR_UNSUPPORTED; malformed packets DCBF_ERR_INVALID_ARG and count in n_bad. */
+int dcbf_ingest_packet(dcbf_ingest_t ingest, const void* packet, size_t length, int default_feng_id);
+int dcbf_ingest_set_frequency(dcbf_ingest_t ingest, long long first_channel);
 /* Next finished chunk in time order: returns 1 and sets *samples (the `samples` argument of dcbf_host_plan_run),
  * *first_timestamp, *n_missing and present[n_batches * n_ants] (each may be NULL); 0 if none is ready; flush != 0
  * also hands out chunks that are still incomplete (end of stream).  Give the chunk back with dcbf_ingest_release. */

@@ -222,3 +222,72 @@ def test_ingest_ring_assembles_heaps_in_any_order():
         np.testing.assert_array_equal(present, exp_present)
         np.testing.assert_array_equal(samples, want)
     ing.close()
+
+
+def _spead_packet(heap_cnt, heap_size, heap_offset, payload, items):
+    """One SPEAD-64-48 packet: header, the four standard immediates, then ``items`` = [(id, immediate?, value)].
+    Layout per the SPEAD specification as spead2's Flavour(4, 64, 48) emits it (fgpu_send_prototype.py:18)."""
+    import struct
+
+    ptrs = [(0x0001, True, heap_cnt), (0x0002, True, heap_size), (0x0003, True, heap_offset),
+            (0x0004, True, len(payload))] + list(items)
+    out = bytes([0x53, 0x04, 2, 6, 0, 0]) + struct.pack(">H", len(ptrs))
+    for ident, immediate, value in ptrs:
+        out += struct.pack(">Q", (int(immediate) << 63) | (ident << 48) | (value & 0xFFFFFFFFFFFF))
+    return out + bytes(payload)
+
+
+def test_ingest_accepts_raw_spead_packets():
+    """dcbf_ingest_packet: heaps arrive as SPEAD-64-48 packets (timestamp 0x1600, feng_id 0x4101, frequency 0x4103,
+    feng_raw 0x4300), several packets per heap, interleaved between antennas; only the first packet of a heap
+    carries the item pointers (spead2's default).  The chunk comes out identical to heap-wise ingest."""
+    from dpdk_dc_sand_b200 import _capi
+
+    B, A, C_, T, step = 2, 3, 4, 16, 4096
+    heap_bytes = C_ * T * 4
+    ing = _capi.Ingest(4, B, A, C_, T, step, pinned=False)
+    ing.set_frequency(8)
+    rng = np.random.default_rng(5)
+    truth = rng.integers(0, 256, (B, A, C_, T, 2, 2), dtype=np.uint8)
+    pkt_payload = 96  # heap_bytes = 256 -> packets of 96, 96, 64 bytes
+    streams = []
+    for b in range(B):
+        for a in range(A):
+            raw = truth[b, a].tobytes()
+            cnt = (b * A + a) * 7 + 3
+            pkts = []
+            for off in range(0, heap_bytes, pkt_payload):
+                first = off == 0
+                items = [(0x1600, True, b * step), (0x4101, True, a), (0x4103, True, 8), (0x4300, False, 0)] if first else []
+                pkts.append(_spead_packet(cnt, heap_bytes, off, raw[off:off + pkt_payload], items))
+            streams.append(pkts)
+    # a heap of another sub-band, a descriptor heap and garbage: refused without touching the chunk
+    other = _spead_packet(999, heap_bytes, 0, bytes(heap_bytes), [(0x1600, True, 0), (0x4101, True, 0), (0x4103, True, 12),
+                                                                  (0x4300, False, 0)])
+    assert not ing.packet(other)
+    assert not ing.packet(_spead_packet(1000, 0, 0, b"", [(0x0005, False, 0)]))
+    with pytest.raises(ValueError):
+        ing.packet(b"\x53\x04\x02\x06\x00\x00\x00\x09short")
+    assert ing.stats()["bad"] == 1
+    # round-robin over the heaps (packets of different antennas interleave), later packets of two heaps swapped
+    rounds = [[s[i] for s in streams if i < len(s)] for i in range(3)]
+    rounds[1], rounds[2] = rounds[2], rounds[1]
+    assert ing.pop() is None
+    for r in rounds:
+        for pkt in r:
+            assert ing.packet(pkt)
+    got = ing.pop()
+    assert got is not None
+    samples, ts, present = got
+    assert ts == 0 and present.all()
+    np.testing.assert_array_equal(samples, truth)
+    ing.release(samples)
+    # a packet that overtakes its heap's first packet cannot be placed; a sender without feng_id uses the default
+    late = _spead_packet(5000, heap_bytes, 96, bytes(96), [])
+    assert not ing.packet(late)
+    solo = _spead_packet(5001, heap_bytes, 0, bytes(range(256)), [(0x1600, True, 2 * step), (0x4300, False, 0)])
+    assert ing.packet(solo, default_feng_id=1)
+    samples, ts, present = ing.pop(flush=True)
+    assert ts == 2 * step and present.sum() == 1 and present[0, 1]
+    np.testing.assert_array_equal(samples[0, 1].reshape(-1), np.arange(256, dtype=np.uint8))
+    ing.close()
