@@ -77,9 +77,8 @@ constexpr int kOutStageBytes = 4 * 2 * kOutBoxBytes;    // 4 epilogue warps x 2 
 constexpr int kTmemCols = 512;
 
 constexpr int kSmemData = kAopStages * kAopStageBytes + kBopBufs * kBopBufBytes + kRawStages * kRawStageBytes + kOutStageBytes;
-constexpr int kGainTabBytes = 64 * 8;  // q8: (gain, clip level) of the <= 64 beams of a single N tile
 constexpr int kCtlBytes = 640;  // 320 B of mbarriers + Control
-constexpr int kSmemBytes = 1024 /*alignment slack*/ + kSmemData + kCtlBytes + kGainTabBytes;
+constexpr int kSmemBytes = 1024 /*alignment slack*/ + kSmemData + kCtlBytes;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 enum Role { kRoleProducer = 1, kRoleMma = 2, kRoleEpilogue = 3, kRoleConvert = 4, kRoleCoeff = 5 };
@@ -109,6 +108,7 @@ struct FusedParams {
     int ub;          // batches sharing one coefficient set: B, or 1 with time-varying steering
     int raw_stages;  // depth of the raw TMA ring: kRawStages + extra stages placed behind the B tiles
     int raw_extra_off;  // byte offset of the first extra stage inside each 64 KiB B buffer
+    uint32_t inv_a;     // floor(2^32 / A) + 1: e / A == umulhi(e, inv_a) for every entry index of an N tile
     float dt_hi[DCBF_MAX_TV_BATCHES], dt_lo[DCBF_MAX_TV_BATCHES];  // per-batch time offset (s) as a float pair
     double chan_centre;      // absolute index of local channel 0, minus N/2
     double turns_per_delay;  // -1 / (N * Ts): half-turns of phase per (second of delay x channel offset)
@@ -207,15 +207,14 @@ __device__ __forceinline__ void advance_model(float base, float rate, float dt_h
 // one FFMA then scales and rounds: adding 1.5*2^23 leaves the two's-complement int8 in the low mantissa byte,
 // round-half-even), three byte permutes pack the word.  kCount also counts clipped values.
 template <bool kCount>
-__device__ __forceinline__ uint32_t quantise4(const uint32_t (&r)[32], int j, float2 g0, float2 g1, int* clipped) {
+__device__ __forceinline__ uint32_t quantise4(const uint32_t (&r)[32], int j, float gain, float limit, int* clipped) {
     uint32_t m[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float2 g = i < 2 ? g0 : g1;  // (gain, 127 / gain)
         const float v = __uint_as_float(r[4 * j + i]);
-        const float cl = fminf(fmaxf(v, -g.y), g.y);
+        const float cl = fminf(fmaxf(v, -limit), limit);
         if (kCount) *clipped += (cl != v);
-        m[i] = __float_as_uint(fmaf(cl, g.x, 12582912.0f));
+        m[i] = __float_as_uint(fmaf(cl, gain, 12582912.0f));
     }
     return __byte_perm(__byte_perm(m[0], m[1], 0x0040u), __byte_perm(m[2], m[3], 0x0040u), 0x5410u);
 }
@@ -289,12 +288,14 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         for (int i = threadIdx.x; i < kBopBufs * kBopBufBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async_smem();
     }
-    const uint32_t gain_tab_cta = smem_base + kSmemData + kCtlBytes;
-    if (kQ8 && prm.q8_wide && threadIdx.x < 64) {  // one table for the CTA (single N tile); padding beams: gain 0
-        const int m = threadIdx.x;
-        const float gi = m < prm.M ? __ldg(prm.gains + m) : 0.f;
-        st_shared_v2(gain_tab_cta + m * 8u, __float_as_uint(gi),
-                     __float_as_uint(m >= prm.M ? 3.0e38f : gi > 0.f ? 127.0f / gi : 0.f));
+    if (kQ8 && warp == 0) {
+        // q8: the per-beam gains ride on the coefficients as gain[m] / max|gain| (in [-1, 1], so the fp16 hi+lo split
+        // keeps its precision); the epilogue then scales every column by the same max|gain| and clips at 127 / max|gain|
+        float g = 0.f;
+        for (int m = lane; m < prm.M; m += 32) g = fmaxf(g, fabsf(__ldg(prm.gains + m)));
+#pragma unroll
+        for (int o = 16; o; o >>= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, o));
+        if (lane == 0) ctl->q8_gmax = g;
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
     if (warp == kProducerWarp && lane == 0) prefetch_tensormap(&tm_in);
@@ -453,7 +454,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         // =================================== epilogue ===================================
         const int q = warp & 3;  // TMEM lane quarter this warp may read
         const uint32_t ost = ost_base + static_cast<uint32_t>(q) * (2 * kOutBoxBytes);
-        const uint32_t gain_tab = ost + kOutBoxBytes;  // q8 only: its four 1 KiB boxes live in the first half
+        const float q8_gain = kQ8 ? ctl->q8_gmax : 0.f, q8_limit = q8_gain > 0.f ? 127.0f / q8_gain : 0.f;
         constexpr bool merged = kMerged;  // a specialisation: the extra 32 registers must not weigh on the wide-tile build
         const uint32_t acc_cols = static_cast<uint32_t>(merged ? 2 * nt : nt);  // TMEM columns per (buffer, pol)
         // 32 accumulator columns of this thread's row; merged tiles keep the hi and lo coefficient parts in two
@@ -575,19 +576,6 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k)
             for (int it = 0; it < prm.nt_count && ok; ++it) {
                 const int n0 = it * nt;
-                if (kQ8 && !prm.q8_wide && (prm.nt_count > 1 || k == 0)) {
-                    // per-warp table of (gain, clip level = 127 / gain) for the 64 beams an N tile can hold, kept
-                    // in the unused part of this warp's staging area; padding beams: gain 0, never "clipped"
-                    __syncwarp();
-#pragma unroll
-                    for (int i = lane; i < 64; i += 32) {
-                        const int m = (n0 >> 1) + i;
-                        const float gi = m < M ? __ldg(prm.gains + m) : 0.f;
-                        st_shared_v2(gain_tab + static_cast<uint32_t>(i) * 8u, __float_as_uint(gi),
-                                     __float_as_uint(m >= M ? 3.0e38f : gi > 0.f ? 127.0f / gi : 0.f));
-                    }
-                    __syncwarp();
-                }
                 for (int b = 0; b < B && ok; ++b)
                     for (int h = 0; h < prm.ht_count && ok; ++h, ++unit) {
                         const uint32_t ab = unit % kAccBufs;
@@ -606,35 +594,55 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                 for (int p = 0; p < kPols && row0 < T; ++p, ++box) {
                                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kPols + p) * acc_cols;
                                     const uint32_t sb = ost + (box & 1u) * kOutBoxBytes;
+                                    unsigned long long tp0 = 0, tp1 = 0, tp2 = 0;
+                                    if (kProf && prof_lane) tp0 = global_ns();
                                     bulk_wait_group_read<1>();  // (issuing lane) the store that last read this box is done
                                     __syncwarp();
+                                    if (kProf && prof_lane) tp1 = global_ns();
                                     // 32 columns of row `lane` -> 16-byte chunks c0/16 and c0/16 + 1, XOR-swizzled by the
                                     // row's 128-byte group
                                     auto put32 = [&](const uint32_t (&r)[32], int c0) {
                                         uint32_t w[8];
 #pragma unroll
-                                        for (int j = 0; j < 8; ++j) {
-                                            const float4 gg = ld_shared_f4(gain_tab_cta + static_cast<uint32_t>((c0 >> 1) + 2 * j) * 8u);
-                                            const float2 g0 = make_float2(gg.x, gg.y), g1 = make_float2(gg.z, gg.w);
-                                            w[j] = prm.saturated ? quantise4<true>(r, j, g0, g1, &clipped)
-                                                                 : quantise4<false>(r, j, g0, g1, &clipped);
-                                        }
+                                        for (int j = 0; j < 8; ++j)
+                                            w[j] = prm.saturated ? quantise4<true>(r, j, q8_gain, q8_limit, &clipped)
+                                                                 : quantise4<false>(r, j, q8_gain, q8_limit, &clipped);
                                         const uint32_t a0 = static_cast<uint32_t>(lane * nt + c0);
                                         const uint32_t a1 = a0 + 16u;
                                         st_shared_v4(sb + (a0 ^ (((a0 >> 7) & cmask) << 4)), w[0], w[1], w[2], w[3]);
                                         st_shared_v4(sb + (a1 ^ (((a1 >> 7) & cmask) << 4)), w[4], w[5], w[6], w[7]);
                                     };
-                                    for (int cb = 0; cb < nt; cb += 32) {
-                                        uint32_t r[32];
-                                        ld32(taddr + cb, r);
-                                        tmem_wait_ld();
-                                        put32(r, cb);
+                                    if constexpr (merged) {
+                                        for (int cb = 0; cb < nt; cb += 32) {
+                                            uint32_t r[32];
+                                            ld32(taddr + cb, r);
+                                            tmem_wait_ld();
+                                            put32(r, cb);
+                                        }
+                                    } else {  // the next 32 columns are on their way from TMEM while these are quantised
+                                        uint32_t r0[32], r1[32];
+                                        tmem_ld_32x32b_x32(taddr, r0);
+                                        for (int cb = 0; cb < nt; cb += 64) {
+                                            tmem_wait_ld();
+                                            if (cb + 32 < nt) tmem_ld_32x32b_x32(taddr + cb + 32, r1);
+                                            put32(r0, cb);
+                                            if (cb + 32 < nt) {
+                                                tmem_wait_ld();
+                                                if (cb + 64 < nt) tmem_ld_32x32b_x32(taddr + cb + 64, r0);
+                                                put32(r1, cb + 32);
+                                            }
+                                        }
                                     }
+                                    if (kProf && prof_lane) tp2 = global_ns();
                                     fence_proxy_async_smem();
                                     __syncwarp();
                                     if (elect_one()) {
                                         tma_store_3d(&tm_out, sb, 0, row0, (b * kPols + p) * C + c);
                                         bulk_commit_group();
+                                    }
+                                    if (kProf && prof_lane) {  // slot 1: bulk-store read wait, slot 2: TMEM + quantise + stores | fence + issue
+                                        ctl->wait_ns[kRoleEpilogue][1] += tp1 - tp0;
+                                        ctl->wait_ns[kRoleEpilogue][2] += (tp2 - tp1) | ((global_ns() - tp2) << 32);
                                     }
                                 }
                                 tc_fence_before();
@@ -642,14 +650,20 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                 if (lane == 0) mbar_arrive(bar(kAccEmpty + ab));
                                 continue;
                             }
-                            auto emit_block = [&](const uint32_t (&r)[32], int cb, int plane, uint32_t sb) {
+                            auto emit_block = [&](uint32_t (&r)[32], int cb, int plane, uint32_t sb) {
                                 uint32_t w[8];
+                                // columns past the tile / the last beam hold other accumulators' values: they are never
+                                // stored, and must not count as clipped either
+                                const int valid = min(nt, N2 - n0) - cb;
+                                if (valid < 32) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float4 gg = ld_shared_f4(gain_tab + static_cast<uint32_t>((cb >> 1) + 2 * j) * 8u);
-                                    w[j] = prm.saturated ? quantise4<true>(r, j, make_float2(gg.x, gg.y), make_float2(gg.z, gg.w), &clipped)
-                                                         : quantise4<false>(r, j, make_float2(gg.x, gg.y), make_float2(gg.z, gg.w), &clipped);
+                                    for (int i = 0; i < 32; ++i)
+                                        if (i >= valid) r[i] = 0u;
                                 }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    w[j] = prm.saturated ? quantise4<true>(r, j, q8_gain, q8_limit, &clipped)
+                                                         : quantise4<false>(r, j, q8_gain, q8_limit, &clipped);
                                 if (prm.tma_store) {
                                     const uint32_t dst = sb + lane * 32;  // [32 rows][32 B], 32B swizzle
                                     const uint32_t x = static_cast<uint32_t>((lane >> 2) & 1) << 4;
@@ -967,6 +981,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             const float s_hi = static_cast<float>(scale), s_lo = static_cast<float>(scale - static_cast<double>(s_hi));
             float dt_hi = 0.f, dt_lo = 0.f;
             const float* w_tile = nullptr;
+            const float* g_tile = nullptr;
+            const float q8_inv_gmax = kQ8 && ctl->q8_gmax > 0.f ? 1.0f / ctl->q8_gmax : 0.f;
             // one (beam, antenna) entry -> four 32-bit words of the B tile at d0 (row 2m) and d1 (row 2m+1)
             auto emit = [&](const Dv& dv, uint32_t d0, int e) {
                 float r, small, sn, cs;
@@ -983,6 +999,11 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     const float w = __ldg(w_tile + e);
                     cs *= w;
                     sn *= w;
+                }
+                if constexpr (kQ8) {  // requantisation gain of this entry's beam, relative to the largest one
+                    const float g = __ldg(g_tile + __umulhi(static_cast<uint32_t>(e), prm.inv_a)) * q8_inv_gmax;
+                    cs *= g;
+                    sn *= g;
                 }
                 // fp16 hi + fp16 residual of (cos, sin)
                 const uint32_t hi = pack_half2(cs, sn);
@@ -1012,6 +1033,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 const int m0 = it * mt;
                 const int entries = min(mt, M - m0) * A;
                 w_tile = prm.weights ? prm.weights + static_cast<size_t>(m0) * A : nullptr;  // entry e <-> [m0 + e / A][e % A]
+                if (kQ8) g_tile = prm.gains + m0;
                 bool waited = false;
                 const uint32_t buf = bop_base + bb * kBopBufBytes;
                 int ml = ml_first, a = a_first;
@@ -1167,6 +1189,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     pick_n_tiling(A, M, p.parts, &p.kb_count, &p.nt, &p.nt_count);
     if (p.nt < 16) return DCBF_ERR_UNSUPPORTED;  // more than 128 k-blocks (4096 antennas)
     p.slab_count = (A + kSlabAnts - 1) / kSlabAnts;
+    p.inv_a = static_cast<uint32_t>((1ull << 32) / static_cast<unsigned>(A)) + 1u;
     p.ht_count = (T + kTileT - 1) / kTileT;
     p.chan_centre = static_cast<double>(first_chan) - static_cast<double>(N) / 2.0;
     p.turns_per_delay = -1.0 / (static_cast<double>(N) * sample_period);

@@ -1,28 +1,40 @@
 """Developer probe: same-box A/B of dcbf_fused (C3) across several builds of libdcbf.so.
 
-    python tools/ab_fused.py lib1.so lib2.so ...      (interleaved rounds, CUDA events, 20 launches each)
+    python tools/ab_fused.py [--q8] lib1.so lib2.so ...      (interleaved rounds, CUDA events, 20 launches each)
 """
 import ctypes as C
 import sys
 
 import torch
 
+Q8 = "--q8" in sys.argv
+if Q8:
+    sys.argv.remove("--q8")
 A, Cc, T, M, B = 64, 4096, 256, 64, 1
 dev = torch.device("cuda", 0)
 x = torch.randint(0, 256, (B, A, Cc, T, 2, 2), dtype=torch.uint8, device=dev)
 dv = torch.rand((Cc, M, A, 4), dtype=torch.float32, device=dev) * 1e-8
 out = torch.empty((B, 2, Cc, T // 16, 16, 2 * M), dtype=torch.float32, device=dev)
+out8 = torch.empty((B, 2, Cc, T // 16, 16, 2 * M), dtype=torch.int8, device=dev)
+gains = torch.full((M,), 0.01, dtype=torch.float32, device=dev)
+sat = torch.zeros(1, dtype=torch.int64, device=dev)
 libs = []
 for path in sys.argv[1:]:
     lib = C.CDLL(path)
     lib.dcbf_fused.restype = C.c_int
     lib.dcbf_fused.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_double, C.c_uint, C.c_void_p]
+    lib.dcbf_fused_q8.restype = C.c_int
+    lib.dcbf_fused_q8.argtypes = [C.c_void_p] * 5 + [C.c_int] * 7 + [C.c_double, C.c_void_p, C.c_uint, C.c_void_p]
     libs.append((path, lib))
 
 
 def run(lib, n):
     for _ in range(n):
-        st = lib.dcbf_fused(x.data_ptr(), dv.data_ptr(), out.data_ptr(), B, A, Cc, Cc, T, M, 0, 1 / 1712e6, 0, None)
+        if Q8:
+            st = lib.dcbf_fused_q8(x.data_ptr(), dv.data_ptr(), gains.data_ptr(), out8.data_ptr(), sat.data_ptr(), B, A, Cc, Cc,
+                                   T, M, 0, 1 / 1712e6, None, 0, None)
+        else:
+            st = lib.dcbf_fused(x.data_ptr(), dv.data_ptr(), out.data_ptr(), B, A, Cc, Cc, T, M, 0, 1 / 1712e6, 0, None)
         assert st == 0, st
 
 
