@@ -331,6 +331,12 @@ def run_ours(args, wl) -> None:
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1 and not args.no_numa_bind:  # host staging buffers of the e2e leg next to this rank's GPU
+        from dpdk_dc_sand_b200 import sharding
+
+        numa = sharding.bind_to_device_numa(local)
+        sys.stderr.write(f"[bench] rank {rank}: numa binding: {numa}\n")
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
@@ -612,6 +618,7 @@ def main() -> None:
     ap.add_argument("--no-q8", action="store_true", help="skip the int8-output extension measurement")
     ap.add_argument("--no-secondary", action="store_true", help="skip the extra c2 (BASELINE configs[1]) measurement")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: leave the rank's CPU affinity alone")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

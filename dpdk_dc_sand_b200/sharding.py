@@ -53,6 +53,23 @@ def plan(n_channels: int, world: Optional[int] = None, rank: Optional[int] = Non
     return ChannelShard(rank, world, n_channels, n_channels // world)
 
 
+def bind_to_device_numa(device_index: int) -> Optional[str]:
+    """Pin the calling thread (and, by first touch, the page-locked buffers it allocates afterwards) to the CPUs
+    NVML reports as local to GPU ``device_index``.  One process per GPU: without this all ranks' host staging
+    buffers tend to land on one socket and the host-buffer path (``dcbf_host_plan_*``) shares one memory controller
+    and one inter-socket link.  Returns a short description, or None if NVML or the cpuset does not allow it."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        cpus = sorted(os.sched_getaffinity(0))
+        return f"gpu {device_index}: {len(cpus)} cpus {cpus[0]}..{cpus[-1]}"
+    except Exception:  # noqa: BLE001 - affinity is an optimisation, never a requirement
+        return None
+
+
 def local_samples(samples, shard: ChannelShard):
     """``(B, A, N, T, P, 2)`` full-band voltages -> this rank's contiguous ``(B, A, C, T, P, 2)`` block.
 
