@@ -428,8 +428,6 @@ int launch_beamform_tc(const uint8_t* reordered, const float* coeffs, float* bea
     p.items = units * p.nt_count * p.hg_count;
     p.signed_in = (flags & DCBF_FLAG_SIGNED_INPUT) ? 1 : 0;
     p.mma_warps = p.nt <= 64 ? 2 : 1;
-    static const int forced = [] { const char* e = getenv("DCBF_DEBUG_TC_MMA_WARPS"); return e ? atoi(e) : 0; }();
-    if (forced == 1 || forced == 2) p.mma_warps = forced;
     if (int e = get_status_block(&p.status)) return e;
 
     EncodeTiledFn encode = nullptr;

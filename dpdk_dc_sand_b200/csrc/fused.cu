@@ -1222,8 +1222,6 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
         const int spare = (kBopBufBytes - used) / kRawStageBytes;
         p.raw_extra_off = used;
         p.raw_stages = kRawStages + 2 * std::min(spare, (kMaxRawStages - kRawStages) / 2);
-        static const int forced = [] { const char* e = getenv("DCBF_DEBUG_RAW_STAGES"); return e ? atoi(e) : 0; }();
-        if (forced >= 1 && forced <= p.raw_stages) p.raw_stages = forced;
     }
     p.tma_store = !(flags & DCBF_FLAG_DEBUG_DIRECT_EPILOGUE) && (M % (q8 ? 8 : 2) == 0) && (p.nt_count == 1 || p.nt % 32 == 0);
     if (static_cast<long long>(B) * kPols * C > 0x7fffffffLL) return DCBF_ERR_UNSUPPORTED;

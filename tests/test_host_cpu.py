@@ -291,3 +291,17 @@ def test_ingest_accepts_raw_spead_packets():
     assert ts == 2 * step and present.sum() == 1 and present[0, 1]
     np.testing.assert_array_equal(samples[0, 1].reshape(-1), np.arange(256, dtype=np.uint8))
     ing.close()
+
+
+def test_numa_binding_helper_is_optional():
+    """sharding.bind_to_device_numa is an optimisation for one-process-per-GPU hosts: without NVML / a GPU it reports
+    None and leaves the process alone."""
+    import os
+
+    from dpdk_dc_sand_b200 import sharding
+
+    before = os.sched_getaffinity(0)
+    out = sharding.bind_to_device_numa(0)
+    assert out is None or isinstance(out, str)
+    if out is None:
+        assert os.sched_getaffinity(0) == before
