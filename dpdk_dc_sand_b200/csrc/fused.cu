@@ -308,6 +308,10 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     const int A = prm.A, C = prm.C, T = prm.T, M = prm.M, B = prm.B;
     const int N2 = 2 * M;
     const int nt = prm.nt, parts = prm.parts;
+    // Scheduling unit: a channel; with K-streamed B tiles a (channel, N tile) pair = unit / nt_count, unit % nt_count
+    // (a channel of many beams takes long enough that whole channels balance badly over the CTAs)
+    const uint32_t n_units = kStream ? static_cast<uint32_t>(C) * static_cast<uint32_t>(prm.nt_count) : static_cast<uint32_t>(C);
+    const int it_count = kStream ? 1 : prm.nt_count;  // N tiles iterated INSIDE one unit
     const uint32_t part_bytes = static_cast<uint32_t>(nt * 128);            // one part of a k-block: [nt rows][128 B]
     const uint32_t bop_kb_bytes = static_cast<uint32_t>(parts) * part_bytes;  // one k-block: [part][nt rows][128 B]
     // profiling: lane 0 of each role's first warp accounts blocked time per barrier class (slot) and role span
@@ -326,12 +330,13 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         // slab order inside a (channel, N tile, batch): time tile outer, antenna slab inner; kStream: slab outer
         // (every B k-block is then used for both time tiles before it is released)
         const int n_inner = kStream ? prm.ht_count : prm.slab_count, n_outer = kStream ? prm.slab_count : prm.ht_count;
-        for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k)
-            for (int it = 0; it < prm.nt_count && ok; ++it)
+        for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k)
+            for (int it = 0; it < it_count && ok; ++it)
                 for (int b = 0; b < B && ok; ++b)
                     for (int o = 0; o < n_outer && ok; ++o)
                         for (int i = 0; i < n_inner; ++i) {
                             const int h = kStream ? i : o, s = kStream ? o : i;
+                            const int c = static_cast<int>(kStream ? w / static_cast<uint32_t>(prm.nt_count) : w);
                             ok = mbar_wait<kProf>(bar(kRawEmpty + rs), ph ^ 1u, ctl, prm.status, kRoleProducer, kRawEmpty + rs, ps + 0);
                             if (!ok) break;
                             if (elect_one()) {
@@ -357,8 +362,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             // (channel, N tile, batch) unit are open at once (ht x 2 x nt TMEM columns), slabs outer, time tiles inner
             const uint32_t pol = warp == kMmaWarp ? 0u : 1u;
             uint32_t kstep = 0;
-            for (uint32_t k = 0; ok && sched_get(ctl, k) < C; ++k)
-                for (int itb = 0; itb < prm.nt_count * B && ok; ++itb, ++unit) {
+            for (uint32_t k = 0; ok && sched_get(ctl, k) < n_units; ++k)
+                for (int b = 0; b < B && ok; ++b, ++unit) {
                     ok = mbar_wait<kProf>(bar(kAccEmpty), (unit & 1u) ^ 1u, ctl, prm.status, kRoleMma, kAccEmpty, ps + 1);
                     if (!ok) break;
                     tc_fence_after();
@@ -403,7 +408,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     __syncwarp();
                 }
         } else
-        for (uint32_t k = 0; ok && sched_get(ctl, k) < C; ++k)
+        for (uint32_t k = 0; ok && sched_get(ctl, k) < n_units; ++k)
             for (int isb = 0; isb < prm.nt_count * prm.sb_count && ok; ++isb, ++step) {  // (N tile, coefficient set)
                 const uint32_t bb = step % kBopBufs;
                 ok = mbar_wait<kProf>(bar(kBopFull + bb), (step / kBopBufs) & 1u, ctl, prm.status, kRoleMma, kBopFull + bb, ps + 0);
@@ -559,8 +564,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         };
         if constexpr (kStream) {
             // all (time tile, pol) accumulators of a (channel, N tile, batch) unit complete together
-            for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k)
-                for (int it = 0; it < prm.nt_count && ok; ++it)
+            for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
+                const uint32_t c = w / static_cast<uint32_t>(prm.nt_count);
+                const int it = static_cast<int>(w - c * static_cast<uint32_t>(prm.nt_count));
                     for (int b = 0; b < B && ok; ++b, ++unit) {
                         ok = mbar_wait<kProf>(bar(kAccFull), unit & 1u, ctl, prm.status, kRoleEpilogue, kAccFull, ps + 0);
                         if (!ok) break;
@@ -572,8 +578,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar(kAccEmpty));
                     }
+            }
         } else
-        for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k)
+        for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < n_units; ++k)
             for (int it = 0; it < prm.nt_count && ok; ++it) {
                 const int n0 = it * nt;
                 for (int b = 0; b < B && ok; ++b)
@@ -720,8 +727,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         const uint32_t sw = static_cast<uint32_t>((t >> 1) & 3);
         uint32_t slab = 0, rs = 0, rph = 0;
         bool ok = true;
-        for (uint32_t k = 0; ok && sched_get(ctl, k) < C; ++k)
-            for (int it = 0; it < prm.nt_count && ok; ++it)
+        for (uint32_t k = 0; ok && sched_get(ctl, k) < n_units; ++k)
+            for (int it = 0; it < it_count && ok; ++it)
                 for (int bh = 0; bh < B * prm.ht_count && ok; ++bh)
                     for (int s = 0; s < prm.slab_count; ++s, ++slab) {
                         const uint32_t as = slab % kAopStages;
@@ -795,11 +802,14 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 bulk_prefetch_l2(p + o, static_cast<uint32_t>(min(bytes - o, static_cast<size_t>(65536))));
         };
         auto sch_publish = [&](int id) {
-            if (id >= C) {
+            if (static_cast<uint32_t>(id) >= n_units) {
                 id = kChanSentinel;
                 sch_end = true;
-            } else if (sch_n > 0) {
-                warm_l2(id, 0);  // about one channel before the register loads get there
+            } else if (sch_n > 0) {  // about one unit before the register loads get there
+                if (kStream)
+                    warm_l2(id / prm.nt_count, (id % prm.nt_count) * (nt >> 1));
+                else
+                    warm_l2(id, 0);
             }
             ctl->chan_ring[sch_n & 7] = id;
             __threadfence_block();
@@ -832,15 +842,17 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             const int wl = warp - kCoeffWarp0;
             const int mt = nt >> 1;
             uint32_t nk = 0;
-            int nc = sched_get(ctl, 0), nit = 0, nb = 0, nkb = 0;
+            int nw = sched_get(ctl, 0), nb = 0, nkb = 0;  // load cursor: unit, batch, k-block
             float2 nxt[kPer];
             auto issue_loads = [&]() {
+                const int nc = nw / prm.nt_count, nit = nw - nc * prm.nt_count;
                 const int m0 = nit * mt, mte = min(mt, M - m0), a = kKbAnts * nkb + lane;
 #pragma unroll
                 for (int u = 0; u < kPer; ++u) {
                     const int m = wl + kCoeffWarps * u;
                     float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (nc < C && m < mte && a < A) t4 = ldg_nc_f4(prm.dv + (static_cast<size_t>(nc) * M + m0 + m) * A + a);
+                    if (static_cast<uint32_t>(nw) < n_units && m < mte && a < A)
+                        t4 = ldg_nc_f4(prm.dv + (static_cast<size_t>(nc) * M + m0 + m) * A + a);
                     nxt[u] = make_float2(t4.x, t4.z);
                 }
             };
@@ -849,31 +861,28 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     sch_flush();
                     if (sch_n <= static_cast<int>(nk) + 1) sch_request();
                 }
-                if (nc >= C) return;
+                if (static_cast<uint32_t>(nw) >= n_units) return;
                 if (++nkb < prm.kb_count) return;
                 nkb = 0;
                 if (++nb < B) return;
                 nb = 0;
-                if (++nit < prm.nt_count) {
-                    if (is_sched) warm_l2(nc, nit * mt);
-                    return;
-                }
-                nit = 0;
                 ++nk;
                 if (is_sched && sch_n <= static_cast<int>(nk)) {
                     sch_request();
                     sch_flush();
                 }
                 __syncwarp();
-                nc = sched_get(ctl, nk);
+                nw = sched_get(ctl, nk);
             };
             issue_loads();
             uint32_t kstep = 0;
             bool ok = true;
-            for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k) {
+            for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
+                const uint32_t c = w / static_cast<uint32_t>(prm.nt_count);
                 const double scale = (static_cast<double>(c) + prm.chan_centre) * prm.turns_per_delay;
                 const float s_hi = static_cast<float>(scale), s_lo = static_cast<float>(scale - static_cast<double>(s_hi));
-                for (int it = 0; it < prm.nt_count && ok; ++it) {
+                {
+                    const int it = static_cast<int>(w - c * static_cast<uint32_t>(prm.nt_count));
                     const int m0 = it * mt, mte = min(mt, M - m0);
                     const float* w_tile = prm.weights ? prm.weights + static_cast<size_t>(m0) * A : nullptr;
                     for (int bkb = 0; bkb < B * prm.kb_count && ok; ++bkb, ++kstep) {
@@ -976,7 +985,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
 
         uint32_t step = 0;
         bool ok = true;
-        for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < C; ++k) {
+        for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < n_units; ++k) {
             const double scale = (static_cast<double>(c) + prm.chan_centre) * prm.turns_per_delay;  // half-turns per second of delay
             const float s_hi = static_cast<float>(scale), s_lo = static_cast<float>(scale - static_cast<double>(s_hi));
             float dt_hi = 0.f, dt_lo = 0.f;
@@ -1285,7 +1294,8 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
         for (int i = 0; i < 14; ++i)
             DCBF_CUDA_TRY(cudaFuncSetAttribute(kKernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     }
-    const int grid = C < n_sms[dev] ? C : n_sms[dev];
+    const long long units = kstream ? static_cast<long long>(C) * p.nt_count : C;  // what the CTAs draw from the queue
+    const int grid = units < n_sms[dev] ? static_cast<int>(units) : n_sms[dev];
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
