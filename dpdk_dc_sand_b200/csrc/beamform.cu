@@ -5,7 +5,7 @@
 // Replaces kernel `run_complex_mult` (reference: beamformer/beamforming/complex_mult_kernel.py:11-100), which
 // launches 2A threads per output row that all compute the same 2M outputs with no operand reuse.  This is
 // the FALLBACK of the stand-alone MatrixMultiply op, for shapes whose rows the TMA descriptors of the tcgen05
-// kernel (beamform_tc.cu) cannot address (A % 8 != 0 or an odd beam count), and its cross-check
+// kernel (beamform_tc.cu) cannot address (odd beam counts: 8M-byte rows), and its cross-check
 // (DCBF_FLAG_DEBUG_CUDA_CORES): float32 operands, float32 accumulation in the reference's order (j ascending,
 // one accumulator per output) on the CUDA cores with a shared-memory tiled 64x64x32 scheme -- compute-bound at
 // ~30 TFLOP/s.  The production path is the fused tcgen05 kernel in fused.cu, which never materialises

@@ -20,7 +20,8 @@
 // elements (16 antennas) stream through a 2-slot B ring while both time tiles' accumulators stay open, and the
 // accumulators are double-buffered across items so the epilogue of one overlaps the MMAs of the next.
 //
-// Shapes the TMA descriptors cannot express (2A or 8M not a multiple of 16 bytes, i.e. A % 8 != 0 or M odd)
+// Antenna counts whose sample rows (2A bytes) are not a multiple of 16 bytes are fetched through an [8 samples x 2A]
+// view, eight small boxes per stage.  Odd beam counts (8M bytes per coefficient / output row not a multiple of 16)
 // stay on the float32 CUDA-core kernel in beamform.cu.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -52,6 +53,10 @@ constexpr int kWBoxBytes = 32 * 128;               // 32 k rows x 32 float32 col
 constexpr int kWStageBytes = (kNtMax / 32) * kWBoxBytes;
 constexpr int kXStages = 12;
 constexpr int kXStageBytes = kTileT * kKb;         // [t][32 bytes], 32B swizzle
+constexpr int kXSplitRowBytes = kKb + 16;          // split mode: a stage is 8 boxes [16 rows][48 B] (32 wanted bytes at a
+constexpr int kXSplitBoxBytes = 16 * kXSplitRowBytes;  // 2-byte-granular offset inside a 16-byte-aligned window)
+constexpr int kXSplitStageBytes = 8 * kXSplitBoxBytes;
+constexpr int kXSplitStages = kXStages * kXStageBytes / kXSplitStageBytes;
 constexpr int kAStages = 4;
 constexpr int kAStageBytes = kTileT * 64;          // [t][32 bf16], 64B swizzle
 constexpr int kOutBoxBytes = 32 * 128;             // 32 rows x 32 float32 columns, 128B swizzle
@@ -78,6 +83,7 @@ struct TcParams {
     int ht_count;     // ceil(T / 128)
     int hg_count;     // ceil(ht_count / 2)
     int signed_in;
+    int x_split;      // 2A is not a multiple of 16 bytes: X rows are fetched as 8 interleaved boxes (see launch_beamform_tc)
     int mma_warps;    // 2: one issuing warp per time tile of a group (narrow tiles are issue-bound); 1: wide tiles
 };
 
@@ -156,6 +162,7 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
     const uint32_t tmem_base = ctl->tmem_base;
 
     const int nt = prm.nt, kb_count = prm.kb_count;
+    const uint32_t x_stages = prm.x_split ? kXSplitStages : kXStages, x_pitch = prm.x_split ? kXSplitStageBytes : kXStageBytes;
     const uint32_t part_bytes = static_cast<uint32_t>(nt) * 64u;
     const long long items = prm.items, stride = gridDim.x;
     const int per_unit = prm.nt_count * prm.hg_count;
@@ -180,12 +187,18 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
                     ok = mbar_wait<false>(bar(kXEmpty + xs), ph ^ 1u, ctl, prm.status, kRoleXProducer, kXEmpty + xs);
                     if (!ok) break;
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(bar(kXFull + xs), kXStageBytes);
-                        tma_load_3d(x_base + xs * kXStageBytes, &tm_x, bar(kXFull + xs), s * kKb,
-                                    (hg * kGroupTiles + h) * kTileT, u);
+                        mbar_arrive_expect_tx(bar(kXFull + xs), x_pitch);
+                        if (!prm.x_split) {
+                            tma_load_3d(x_base + xs * x_pitch, &tm_x, bar(kXFull + xs), s * kKb, (hg * kGroupTiles + h) * kTileT, u);
+                        } else {  // rows of 8 samples: sample 8 r + i of the tile is bytes [i * 2A, (i + 1) * 2A) of row r
+                            // (the innermost TMA coordinate must be a multiple of 16 bytes: fetch the aligned 48-byte window)
+                            for (int i = 0; i < 8; ++i)
+                                tma_load_3d(x_base + xs * x_pitch + i * kXSplitBoxBytes, &tm_x, bar(kXFull + xs),
+                                            (i * prm.K2 + s * kKb) & ~15, (hg * kGroupTiles + h) * (kTileT / 8), u);
+                        }
                     }
                     __syncwarp();
-                    if (++xs == kXStages) xs = 0, ph ^= 1u;
+                    if (++xs == x_stages) xs = 0, ph ^= 1u;
                 }
         }
     } else if (warp == kWProducerWarp) {
@@ -301,6 +314,14 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
         const float bias = prm.signed_in ? 8388736.0f : 8388608.0f;  // 2^23 (+ 128 after the ^0x80 re-bias of i8)
         const uint32_t flip = prm.signed_in ? 0x80808080u : 0u;
         const uint32_t sw_in = static_cast<uint32_t>((t >> 2) & 1), sw_out = static_cast<uint32_t>((t >> 1) & 3);
+        // the two 16-byte halves of this thread's row inside a stage.  Split mode: sample t = 8 r + i is row r of box i,
+        // its 32 bytes start (i * 2A) % 16 bytes into the row's 48-byte window: nine 4-byte loads and a funnel shift.
+        // TMA destinations must be 128-byte aligned, so the boxes cannot be skewed against the banks and the eight
+        // lanes of a quarter-warp (eight boxes, same row) collide -- the price of an antenna count TMA cannot address.
+        const uint32_t src0 = static_cast<uint32_t>(t * 32) + ((0u ^ sw_in) << 4), src1 = static_cast<uint32_t>(t * 32) + ((1u ^ sw_in) << 4);
+        const uint32_t split_off = static_cast<uint32_t>((t & 7) * prm.K2) & 15u;
+        const uint32_t split_src = static_cast<uint32_t>((t & 7) * kXSplitBoxBytes + (t >> 3) * kXSplitRowBytes) + (split_off & ~3u);
+        const uint32_t split_shift = (split_off & 2u) * 8u;
         uint32_t xs = 0, xph = 0, as = 0, aph = 0;
         for (long long item = blockIdx.x; item < items && ok; item += stride) {
             int u, it, hg, hn;
@@ -310,15 +331,24 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
                                        prm.status, kRoleConvert);
                 if (!ok) break;
                 // antennas beyond A and samples beyond T were zero-filled by the TMA box: byte 0 -> value 0 (u8),
-                // and 0 ^ 0x80 - 128 -> 0 (i8), so the operand padding needs no special case
-                const uint32_t src = x_base + xs * kXStageBytes + t * 32;
+                // and 0 ^ 0x80 - 128 -> 0 (i8), so the operand padding needs no special case (split mode: the bytes
+                // past 2A belong to the next sample, but they only ever meet the zero-filled rows k >= 2A of W)
+                const uint32_t src = x_base + xs * x_pitch;
                 uint32_t w[8];
                 {
-                    uint32_t c0[4], c1[4];
-                    ld_shared_v4(src + ((0u ^ sw_in) << 4), c0);
-                    ld_shared_v4(src + ((1u ^ sw_in) << 4), c1);
+                    if (!prm.x_split) {
+                        uint32_t c0[4], c1[4];
+                        ld_shared_v4(src + src0, c0);
+                        ld_shared_v4(src + src1, c1);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) w[i] = c0[i] ^ flip, w[4 + i] = c1[i] ^ flip;
+                        for (int i = 0; i < 4; ++i) w[i] = c0[i] ^ flip, w[4 + i] = c1[i] ^ flip;
+                    } else {
+                        uint32_t c[9];
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) c[i] = ld_shared_u32(src + split_src + 4u * i);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) w[i] = __funnelshift_r(c[i], c[i + 1], split_shift) ^ flip;
+                    }
                 }
                 const uint32_t dst = a_base + as * kAStageBytes + t * 64;
 #pragma unroll
@@ -332,7 +362,7 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
                     mbar_arrive(bar(kAFull + as));
                     mbar_arrive(bar(kXEmpty + xs));
                 }
-                if (++xs == kXStages) xs = 0, xph ^= 1u;
+                if (++xs == x_stages) xs = 0, xph ^= 1u;
                 if (++as == kAStages) as = 0, aph ^= 1u;
             }
         }
@@ -410,7 +440,8 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
 }  // namespace
 
 bool beamform_tc_supported(const void* reordered, const void* coeffs, const void* beams, int A, int M) {
-    return A % 8 == 0 && M % 2 == 0 && aligned16(reordered) && aligned16(coeffs) && aligned16(beams);
+    (void)A;  // any antenna count: rows that TMA cannot address one by one are fetched eight at a time
+    return M % 2 == 0 && aligned16(reordered) && aligned16(coeffs) && aligned16(beams);
 }
 
 int launch_beamform_tc(const uint8_t* reordered, const float* coeffs, float* beams, int B, int C, int T, int A, int M,
@@ -428,13 +459,25 @@ int launch_beamform_tc(const uint8_t* reordered, const float* coeffs, float* bea
     p.items = units * p.nt_count * p.hg_count;
     p.signed_in = (flags & DCBF_FLAG_SIGNED_INPUT) ? 1 : 0;
     p.mma_warps = p.nt <= 64 ? 2 : 1;
+    p.x_split = (p.K2 % 16) != 0;
     if (int e = get_status_block(&p.status)) return e;
 
     EncodeTiledFn encode = nullptr;
     if (int e = get_encode_fn(&encode)) return e;
     alignas(64) CUtensorMap tm_x, tm_w, tm_out;
     const cuuint32_t estr[3] = {1, 1, 1};
-    {
+    if (p.x_split) {
+        // 2A bytes per sample is not a multiple of 16, which a tensor map needs of every stride: view the voltages as
+        // [units][T / 8][8 x 2A] (stride 16 A) and fetch a [128 samples][32 B] stage as 8 boxes [16 rows][32 B], box i
+        // = samples 8 r + i at byte offset i * 2A + k rounded down to 16 (48-byte rows, no swizzle).
+        const cuuint64_t dims[3] = {static_cast<cuuint64_t>(8 * p.K2), static_cast<cuuint64_t>(T / 8), static_cast<cuuint64_t>(units)};
+        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(8 * p.K2), static_cast<cuuint64_t>(T) * p.K2};
+        const cuuint32_t box[3] = {kXSplitRowBytes, kTileT / 8, 1};
+        const CUresult r = encode(&tm_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(reordered), dims, strides, box,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return record_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(reordered, split)");
+    } else {
         // voltages as bytes [units][T][2A]; box [1][128][32], 32B swizzle
         const cuuint64_t dims[3] = {static_cast<cuuint64_t>(p.K2), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(units)};
         const cuuint64_t strides[2] = {static_cast<cuuint64_t>(p.K2), static_cast<cuuint64_t>(T) * p.K2};

@@ -38,7 +38,7 @@ int launch_coeffs(const float* delay_vals, float* coeffs, int B, int P, int C, i
                   double sample_period, const double* batch_dt_s, const float* beam_weights, cudaStream_t s);
 int launch_beamform(const uint8_t* reordered, const float* coeffs, float* beams, int B, int C, int T, int A, int M,
                     unsigned flags, cudaStream_t s);
-// tcgen05 version (beamform_tc.cu) for shapes its TMA descriptors can express: A % 8 == 0, M even
+// tcgen05 version (beamform_tc.cu) for shapes its TMA descriptors can express: even beam count
 bool beamform_tc_supported(const void* reordered, const void* coeffs, const void* beams, int A, int M);
 int launch_beamform_tc(const uint8_t* reordered, const float* coeffs, float* beams, int B, int C, int T, int A, int M,
                        unsigned flags, cudaStream_t s);

@@ -15,11 +15,13 @@ SHAPES = [  # B, C, T, A, M, signed
     (1, 3, 128, 16, 16, False), (2, 3, 64, 64, 16, False), (1, 5, 256, 64, 64, False), (1, 2, 384, 80, 32, True),
     (1, 2, 256, 8, 2, False), (1, 3, 640, 72, 6, False), (1, 2, 256, 136, 130, False), (1, 300, 256, 64, 64, False),
     (1, 2, 48, 24, 70, True),
+    # antenna counts whose rows are not a multiple of 16 bytes (eight-box fetch)
+    (1, 3, 256, 197, 256, False), (2, 3, 64, 4, 2, False), (1, 5, 384, 79, 2, True), (1, 2, 48, 23, 4, False), (1, 300, 256, 84, 16, False),
 ]
 
 
 CFG = {"c2": (64, 1024, 256, 16), "c3": (64, 4096, 256, 64), "c4/8": (80, 4096, 256, 32), "c2x8": (64, 8192, 256, 16),
-       "c4": (80, 32768, 256, 32)}
+       "c4": (80, 32768, 256, 32), "c5/8": (197, 512, 256, 256)}
 
 
 def once(name):
@@ -41,7 +43,12 @@ def main():
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev).manual_seed(11)
     bad = 0
-    for (B, C, T, A, M, signed) in SHAPES:
+    shapes = SHAPES
+    if "--shape" in sys.argv:  # --shape B C T A M signed(0/1)
+        i = sys.argv.index("--shape")
+        v = [int(x) for x in sys.argv[i + 1:i + 7]]
+        shapes = [(v[0], v[1], v[2], v[3], v[4], bool(v[5]))]
+    for (B, C, T, A, M, signed) in shapes:
         re = torch.randint(0, 256, (B, 2, C, T // 16, 16, A, 2), dtype=torch.uint8, device=dev, generator=g)
         co = torch.randn((B, 2, C, 2 * A, 2 * M), dtype=torch.float32, device=dev, generator=g)
         co *= torch.exp2(torch.randint(-20, 20, co.shape, device=dev, generator=g).float())  # wide dynamic range
