@@ -1111,7 +1111,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     }
 }
 
-constexpr int kSchedSlots = 64;  // concurrent launches per device that can share the pool without interfering
+constexpr int kLiveSlots = 64;   // launches in flight at once on one device that can share the pool without interfering
+constexpr int kSchedSlots = 2 * kLiveSlots;  // the second half belongs to launches captured into CUDA graphs, which keep
+                                             // their slot for every replay and must not meet a live launch on it
 using KernelFn = void (*)(const FusedParams, const CUtensorMap, const CUtensorMap);
 // index = 6 * q8 + 2 * variant (0 plain, 1 profiling, 2 time-varying) + merged; [12], [13] = K-streamed B (plain, profiling)
 KernelFn const kKernels[14] = {
@@ -1235,8 +1237,13 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     p.tma_store = !(flags & DCBF_FLAG_DEBUG_DIRECT_EPILOGUE) && (M % (q8 ? 8 : 2) == 0) && (p.nt_count == 1 || p.nt % 32 == 0);
     if (static_cast<long long>(B) * kPols * C > 0x7fffffffLL) return DCBF_ERR_UNSUPPORTED;
     if (int e = get_status_block(&p.status)) return e;
-    static std::atomic<unsigned> ticket{0};
-    p.sched = p.status + 4 + 2 * (ticket.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
+    static std::atomic<unsigned> ticket{0}, captured_ticket{0};
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    DCBF_CUDA_TRY(cudaStreamIsCapturing(s, &capturing));
+    const unsigned slot = capturing == cudaStreamCaptureStatusActive
+                              ? kLiveSlots + captured_ticket.fetch_add(1, std::memory_order_relaxed) % kLiveSlots
+                              : ticket.fetch_add(1, std::memory_order_relaxed) % kLiveSlots;
+    p.sched = p.status + 4 + 2 * slot;
     p.prof = g_prof_dev;
 
     EncodeTiledFn encode = nullptr;

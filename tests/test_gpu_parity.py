@@ -685,3 +685,42 @@ def test_native_library_is_loaded():
     with open("/proc/self/maps") as fh:
         assert any("libdcbf.so" in line for line in fh)
     assert os.path.basename(_capi.lib_path()) == "libdcbf.so"
+
+
+def test_fused_launches_can_be_captured_in_a_cuda_graph(dropin):
+    """The C ABI only enqueues (no allocation or synchronisation after the first call on a device), so a sequence of
+    launches can be captured once and replayed: graph replays, interleaved with live launches on another stream,
+    reproduce the eager results bit for bit (captured launches keep a channel-queue slot of their own)."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m, n = 1, 64, 300, 128, 16, 1024
+    g = torch.Generator(device="cuda").manual_seed(17)
+    xs = [torch.randint(0, 256, (b, a, c, t, 2, 2), dtype=torch.uint8, device="cuda", generator=g) for _ in range(3)]
+    dv = torch.from_numpy(orc.make_delay_vals_random(c, m, a, seed=5)).cuda()
+    outs = [torch.empty((b, 2, c, t // 16, 16, 2 * m), dtype=torch.float32, device="cuda") for _ in range(3)]
+    want = []
+    for x, o in zip(xs, outs):  # eager pass (also performs the one-time allocations)
+        _capi.fused(x, dv, o, b, a, c, n, t, m, 0, TS)
+        torch.cuda.synchronize()
+        want.append(o.clone())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        st = torch.cuda.current_stream()
+        for x, o in zip(xs, outs):
+            _capi.fused(x, dv, o, b, a, c, n, t, m, 0, TS, 0, st)
+    side = torch.cuda.Stream()
+    live = torch.empty_like(outs[0])
+    for rep in range(3):
+        for o in outs:
+            o.fill_(float("nan"))
+        torch.cuda.synchronize()
+        graph.replay()
+        for _ in range(4):  # live launches racing the replay
+            _capi.fused(xs[0], dv, live, b, a, c, n, t, m, 0, TS, 0, side)
+        torch.cuda.synchronize()
+        _capi.fused_status()
+        for o, w in zip(outs, want):
+            assert torch.equal(o, w), rep
+        assert torch.equal(live, want[0])
