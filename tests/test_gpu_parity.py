@@ -724,3 +724,48 @@ def test_fused_launches_can_be_captured_in_a_cuda_graph(dropin):
         for o, w in zip(outs, want):
             assert torch.equal(o, w), rep
         assert torch.equal(live, want[0])
+
+
+def test_headline_size_fused_equals_three_kernel_chain_and_is_linear(dropin):
+    """Size-independent properties at the size the BASELINE metric is quoted on (C3: 64 antennas x 4096 channels x
+    256 samples, 64 beams): (1) the fused kernel agrees with the chain reorder -> float64 coefficients -> tcgen05
+    contraction, four different kernels and two different coefficient arithmetics, to 0.05 absolute (the 2^-10 budget
+    is ~8 here);  (2) the contraction is linear in the voltages;  (3) the reorder is an exact permutation (its byte
+    histogram and a strided probe of elements survive)."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m = 1, 64, 4096, 256, 64
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(23)
+    x = torch.randint(0, 256, (b, a, c, t, 2, 2), dtype=torch.uint8, device=dev, generator=g)
+    dv = torch.zeros((c, m, a, 4), dtype=torch.float32, device=dev)
+    dv[..., 0] = (torch.rand((c, m, a), device=dev, generator=g) * 32 - 16) * TS
+    dv[..., 2] = (torch.rand((c, m, a), device=dev, generator=g) * 2 - 1) * math.pi
+    fused = torch.empty((b, 2, c, t // 16, 16, 2 * m), dtype=torch.float32, device=dev)
+    _capi.fused(x, dv, fused, b, a, c, c, t, m, 0, TS)
+    re = torch.empty((b, 2, c, t // 16, 16, a, 2), dtype=torch.uint8, device=dev)
+    co = torch.empty((b, 2, c, 2 * a, 2 * m), dtype=torch.float32, device=dev)
+    chain = torch.empty_like(fused)
+    _capi.reorder(x, re, b, a, c, t)
+    _capi.coeffs(dv, co, b, 2, c, c, a, m, 0, TS)
+    _capi.beamform(re, co, chain, b, c, t, a, m)
+    torch.cuda.synchronize()
+    _capi.fused_status()
+    assert (fused - chain).abs().max().item() <= 0.05
+    # reorder: (b, a, c, t, p, x) -> (b, p, c, t//16, t%16, a, x), probed on a strided subset, plus the histogram
+    probe = x[:, ::7, ::513, ::5].permute(0, 4, 2, 3, 1, 5)
+    got = re.reshape(b, 2, c, t, a, 2)[:, :, ::513, ::5, ::7]
+    assert torch.equal(got, probe)
+    assert torch.equal(torch.bincount(x.reshape(-1).int(), minlength=256), torch.bincount(re.reshape(-1).int(), minlength=256))
+    del co, chain
+    hi, lo = re >> 4, re & 15
+    co = torch.randn((b, 2, c, 2 * a, 2 * m), dtype=torch.float32, device=dev, generator=g)
+    o, o_hi, o_lo = torch.empty_like(fused), torch.empty_like(fused), torch.empty_like(fused)
+    _capi.beamform(re, co, o, b, c, t, a, m)
+    _capi.beamform(hi, co, o_hi, b, c, t, a, m)
+    _capi.beamform(lo, co, o_lo, b, c, t, a, m)
+    torch.cuda.synchronize()
+    _capi.fused_status()
+    assert (16 * o_hi + o_lo - o).abs().max().item() <= 0.05
