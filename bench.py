@@ -331,6 +331,11 @@ def run_ours(args, wl) -> None:
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
+    if world > 1:  # NCCL prints its version banner to fd 1: park stdout on stderr until the JSON line is due
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
     numa = None
     if world > 1 and not args.no_numa_bind:  # host staging buffers of the e2e leg next to this rank's GPU
         from dpdk_dc_sand_b200 import sharding
@@ -548,6 +553,42 @@ def run_ours(args, wl) -> None:
             del h_out8
         del h_in, h_dv, h_out
 
+    gather = None
+    if world > 1 and not args.no_gather:
+        # the path's only (optional) collective, outside the compute timing: every rank's beams to rank 0 over NCCL
+        from dpdk_dc_sand_b200 import sharding
+
+        shard = sharding.plan(n_total, world=world, rank=rank)
+        _capi.fused(samples, dv, beams, B, A, C, n_total, T, M, rank, SAMPLE_PERIOD, flags)
+        torch.cuda.synchronize()
+        local_sum = beams.double().sum()
+        total = local_sum.clone()
+        dist.all_reduce(total)
+        times = []
+        full = None
+        for _ in range(2):
+            del full
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            full = sharding.gather_beams(beams, shard, dst=0)
+            e1.record()
+            torch.cuda.synchronize()
+            t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+            times.append(float(t_ms.item()))
+        ok = True
+        if rank == 0:
+            ok = tuple(full.shape)[2] == n_total and abs(float(full.double().sum().item()) - float(total.item())) <= 1e-6 * abs(float(total.item())) + 1e-3 \
+                and torch.equal(full[:, :, :C], beams)
+        del full
+        torch.cuda.empty_cache()
+        gbytes = (world - 1) * beams.numel() * 4
+        gather = {"ms": min(times), "bytes_received_by_rank0": gbytes, "GBps": gbytes / (min(times) / 1e3) / 1e9,
+                  "checksum_ok": bool(ok), "api": "sharding.gather_beams (torch.distributed gather, nccl)",
+                  "note": "optional; not part of value / e2e"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -593,13 +634,17 @@ def run_ours(args, wl) -> None:
         "beam_gsamples_per_s": world * B * 2 * C * T * M / sec_per_step / 1e9,
         "algorithmic_GBps": world * alg_bytes / sec_per_step / 1e9,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "sustained": sustained, "streaming": streaming, "q8_output": q8, "other_workloads": secondary,
+        "sustained": sustained, "streaming": streaming, "q8_output": q8, "other_workloads": secondary, "gather": gather,
         "pcie": {"note": "e2e is bounded by the host link: pinned copies measured on this pool (tools/bench_standalone.py) "
                          "reach 55.5 GB/s H2D, 57.3 GB/s D2H alone and 49.9 GB/s each way when both directions run "
                          "at once; the e2e step moves h2d_bytes_per_step up and d2h_bytes_per_step down",
                  "e2e_d2h_GBps": (e2e["d2h_bytes_per_step"] / (e2e["ms_per_step"] / 1e3) / 1e9) if e2e else None},
     }
-    print(json.dumps(line))
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -619,6 +664,7 @@ def main() -> None:
     ap.add_argument("--no-secondary", action="store_true", help="skip the extra c2 (BASELINE configs[1]) measurement")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: leave the rank's CPU affinity alone")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip timing the optional beam-output gather to rank 0")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
