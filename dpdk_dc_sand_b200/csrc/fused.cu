@@ -283,9 +283,13 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         (void)kNumBars;
     }
     // B tiles start as zeros: padding rows (k >= 2A, n >= 2M) are never written afterwards.
+    // (only the part of each 64 KiB buffer the tiles occupy: the tail, if any, holds extra raw stages)
     {
-        uint4* z = reinterpret_cast<uint4*>(smem_gen);
-        for (int i = threadIdx.x; i < kBopBufs * kBopBufBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+        const int used16 = kStream ? kBopBufBytes / 16 : prm.raw_extra_off / 16;  // 16-byte units per buffer
+        for (int buf = 0; buf < kBopBufs; ++buf) {
+            uint4* z = reinterpret_cast<uint4*>(smem_gen + buf * kBopBufBytes);
+            for (int i = threadIdx.x; i < used16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+        }
         fence_proxy_async_smem();
     }
     if (kQ8 && warp == 0) {
