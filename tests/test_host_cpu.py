@@ -331,3 +331,44 @@ def test_bench_reference_arm_prints_one_contract_line():
     ours = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"],
                           capture_output=True, text=True, timeout=600, env=env)
     assert ours.returncode != 0 and "CUDA" in (ours.stderr + ours.stdout)
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/dcbf.h is the drop-in boundary: it must compile as C99 (no C++ in any signature) and a C program
+    must link against libdcbf.so and call the entry points that need no GPU."""
+    import shutil
+    import subprocess
+
+    from dpdk_dc_sand_b200 import _capi
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    _capi.load()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "dpdk_dc_sand_b200", "lib")
+    src = tmp_path / "smoke.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "dcbf.h"
+int main(void) {
+    int kb = 0, nt = 0, ntc = 0;
+    if (dcbf_version() != DCBF_VERSION) return 1;
+    if (strlen(dcbf_strerror(DCBF_ERR_TIMEOUT)) == 0) return 2;
+    if (dcbf_fused_bytes(1, 64, 4096, 256, 64) != 1610612736LL) return 3;
+    dcbf_fused_tiling(64, 64, 0, &kb, &nt, &ntc);
+    if (kb != 2 || nt != 128 || ntc != 1) return 4;
+    if (dcbf_reorder(NULL, NULL, 1, 1, 1, 16, NULL) != DCBF_ERR_INVALID_ARG) return 5;
+    dcbf_ingest_t ing = NULL;
+    if (dcbf_ingest_create(&ing, 2, 1, 2, 2, 16, 1024, 0) != DCBF_OK) return 6;
+    if (dcbf_ingest_destroy(ing) != DCBF_OK) return 7;
+    printf("ok\n");
+    return 0;
+}
+''')
+    exe = tmp_path / "smoke"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src), "-L", lib_dir,
+                    "-ldcbf", "-Wl,-rpath," + lib_dir, "-o", str(exe)], check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout, out.stderr)
