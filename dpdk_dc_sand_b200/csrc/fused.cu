@@ -1202,7 +1202,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     p.parts = (flags & DCBF_FLAG_FP16_COEFF) ? 1 : 2;
     p.signed_in = (flags & DCBF_FLAG_SIGNED_INPUT) ? 1 : 0;
     pick_n_tiling(A, M, p.parts, &p.kb_count, &p.nt, &p.nt_count);
-    if (p.nt < 16) return DCBF_ERR_UNSUPPORTED;  // more than 128 k-blocks (4096 antennas)
+    const bool no_whole_tiles = p.nt < 16;  // > 512 antennas (hi+lo): not even a 16-column tile set fits a 64 KiB buffer
     p.slab_count = (A + kSlabAnts - 1) / kSlabAnts;
     p.inv_a = static_cast<uint32_t>((1ull << 32) / static_cast<unsigned>(A)) + 1u;
     p.ht_count = (T + kTileT - 1) / kTileT;
@@ -1222,7 +1222,9 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     }
     // Many antennas x beams: a whole B tile set no longer fits 64 KiB with a useful width (the voltages would be
     // re-converted for every narrow N tile).  Stream B by 32-antenna k-blocks instead: N tiles of up to 128 columns.
-    const bool kstream = p.nt_count > 1 && !q8 && !batch_dt_s && p.ht_count <= 2 && !(flags & DCBF_FLAG_DEBUG_NO_KSTREAM);
+    const bool kstream = (p.nt_count > 1 || no_whole_tiles) && !q8 && !batch_dt_s && p.ht_count <= 2 &&
+                         !(flags & DCBF_FLAG_DEBUG_NO_KSTREAM);
+    if (no_whole_tiles && !kstream) return DCBF_ERR_UNSUPPORTED;  // (the k-block ring itself has no antenna limit)
     if (kstream) {
         const int n_pad = ((2 * M + 15) / 16) * 16;
         p.nt_count = (n_pad + 127) / 128;

@@ -240,6 +240,7 @@ def test_op_sequence_reference_inputs(dropin, n_ants):
 
 FUSED_CASES = [
     # B, A, C, T, M, N, xeng_id, signed, fp16_coeff
+    (1, 600, 2, 128, 8, 64, 0, False, False),     # more antennas than any whole B tile set holds: k-block ring only
     (1, 4, 64, 256, 4, 64, 0, False, False),      # BASELINE configs[0]
     (1, 64, 24, 256, 16, 1024, 0, False, False),  # configs[1] geometry, a slice of channels
     (1, 64, 10, 256, 64, 4096, 5, False, False),  # configs[2] geometry, xeng 5 of 8... (C=10 slice)
