@@ -10,6 +10,9 @@ import torch
 Q8 = "--q8" in sys.argv
 if Q8:
     sys.argv.remove("--q8")
+LONG = "--long" in sys.argv  # 3000 launches of run-in per measurement: the board is then at its power cap
+if LONG:
+    sys.argv.remove("--long")
 A, Cc, T, M, B = 64, 4096, 256, 64, 1
 dev = torch.device("cuda", 0)
 x = torch.randint(0, 256, (B, A, Cc, T, 2, 2), dtype=torch.uint8, device=dev)
@@ -43,9 +46,12 @@ for path, lib in libs:
 torch.cuda.synchronize()
 for rnd in range(4):
     for path, lib in libs:
+        n = 200 if LONG else 20
+        if LONG:
+            run(lib, 3000)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        run(lib, 20)
+        run(lib, n)
         e1.record()
         torch.cuda.synchronize()
-        print(f"round {rnd} {path.split('/')[-1]:28s} {e0.elapsed_time(e1) / 20 * 1e3:7.1f} us")
+        print(f"round {rnd} {path.split('/')[-1]:28s} {e0.elapsed_time(e1) / n * 1e3:7.1f} us")
