@@ -162,7 +162,10 @@ int dcbf_fused_status(int* role, int* barrier, int* block);
  * The buffer must hold 24 * (number of SMs) entries. */
 void dcbf_debug_set_profile_buffer(unsigned long long* dev_ptr);
 
-/* The tiling dcbf_fused will use for (n_ants, n_beams, flags): k-blocks of 32 antennas, N tiles of *nt columns. */
+/* The whole-tile-set tiling of dcbf_fused for (n_ants, n_beams, flags): k-blocks of 32 antennas, N tiles of *nt
+ * columns such that one tile set (all k-blocks, hi+lo) fits a 64 KiB buffer.  When that needs more than one N tile
+ * (*nt_count > 1) and n_samples <= 256 without int8 output or per-heap times, the kernel streams B by k-blocks
+ * instead and uses N tiles of up to 128 columns (ceil(2 n_beams / 128) of them). */
 void dcbf_fused_tiling(int n_ants, int n_beams, unsigned flags, int* kb_count, int* nt, int* nt_count);
 
 /* ---- host-buffer entry point (what a caller holding HOST arrays binds to) --------------------------------
