@@ -50,7 +50,9 @@ typedef void* dcbf_stream_t; /* cudaStream_t */
 typedef enum dcbf_status {
     DCBF_OK = 0,
     DCBF_ERR_INVALID_ARG = -1, /* null pointer, non-positive dimension, T % 16 != 0, misaligned pointer */
-    DCBF_ERR_UNSUPPORTED = -2, /* shape outside what the kernels were built for */
+    DCBF_ERR_UNSUPPORTED = -2, /* shape outside what the kernels were built for: dcbf_fused with more than 512 antennas
+                                  (1024 with DCBF_FLAG_FP16_COEFF) AND more than 256 samples, int8 output or per-heap
+                                  times; more than DCBF_MAX_TV_BATCHES heaps with per-heap times; index overflow */
     DCBF_ERR_CUDA = -3,        /* a CUDA runtime call failed; see dcbf_last_cuda_error() */
     DCBF_ERR_NO_DEVICE = -4,   /* no sm_100 device is current */
     DCBF_ERR_TIMEOUT = -5      /* in-kernel watchdog fired (pipeline dead-lock guard) */

@@ -1,0 +1,84 @@
+"""Randomised shape sweep of the C ABI against float64 references (developer aid; the committed parity tests are
+tests/test_gpu_parity.py).
+
+    python tools/fuzz_gpu.py [n_cases] [seed]
+
+Every case draws (B, A, C, T, M, flags) and checks: dcbf_fused against the oracle pipeline (2^-10 sum|x| budget; the
+observed error is printed), dcbf_reorder bit-exact, dcbf_beamform (tcgen05 or CUDA cores, whichever the shape takes)
+against a float64 matmul, and the in-kernel watchdog status.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dpdk_dc_sand_b200 import _capi  # noqa: E402
+from oracle import beamform_oracle as orc  # noqa: E402
+
+TS = orc.SAMPLE_PERIOD
+
+
+def main():
+    n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    rng = np.random.default_rng(seed)
+    dev = torch.device("cuda", 0)
+    worst_f, worst_b, bad = 0.0, 0.0, 0
+    for case in range(n_cases):
+        B = int(rng.integers(1, 4))
+        A = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 23, 31, 32, 33, 48, 63, 64, 65, 79, 80, 96, 100, 130, 197, 256, 300, 520]))
+        M = int(rng.choice([1, 2, 3, 4, 5, 8, 15, 16, 17, 32, 33, 63, 64, 65, 100, 128, 130, 256]))
+        T = 16 * int(rng.choice([1, 2, 3, 4, 7, 8, 9, 16, 17, 24]))
+        while B * A * T * M > 3e6:  # keep the float64 oracle fast
+            M = max(1, M // 2)
+        C = int(rng.integers(1, 6)) if A * M > 4000 else int(rng.integers(1, 40))
+        signed = bool(rng.integers(0, 2))
+        fp16 = bool(rng.integers(0, 4) == 0)
+        n_total = C * int(rng.integers(1, 4))
+        xid = int(rng.integers(0, n_total // C))
+        x = orc.make_samples(B, A, C, T, seed=case)
+        dv = orc.make_delay_vals_random(C, M, A, seed=1000 + case)
+        dx, ddv = torch.from_numpy(x).to(dev), torch.from_numpy(dv).to(dev)
+        out = torch.full((B, 2, C, T // 16, 16, 2 * M), float("nan"), dtype=torch.float32, device=dev)
+        flags = (_capi.FLAG_SIGNED_INPUT if signed else 0) | (_capi.FLAG_FP16_COEFF if fp16 else 0)
+        tag = f"case {case}: B{B} A{A} C{C} T{T} M{M} N{n_total} x{xid} signed={signed:d} fp16={fp16:d}"
+        try:
+            _capi.fused(dx, ddv, out, B, A, C, n_total, T, M, xid, TS, flags)
+            torch.cuda.synchronize()
+            _capi.fused_status()
+        except Exception as e:  # noqa: BLE001
+            expected = A > 512 and T > 256 and "unsupported" in str(e)  # the one refused region (see dcbf.h)
+            print(tag, "refused as documented" if expected else f"EXCEPTION {e}", flush=True)
+            bad += not expected
+            continue
+        ref = orc.beamform_pipeline(x, dv, n_total, xid, TS, signed_input=signed)
+        budget = 2.0 ** -10 * orc.beamform_abs_bound(orc.reorder(x), signed_input=signed)[..., None]
+        got = out.cpu().numpy()
+        ratio = float(np.max(np.abs(got - ref) / np.maximum(budget, 1e-30))) if not np.isnan(got).any() else float("inf")
+        worst_f = max(worst_f, ratio)
+        # stand-alone ops
+        re = torch.empty((B, 2, C, T // 16, 16, A, 2), dtype=torch.uint8, device=dev)
+        _capi.reorder(dx, re, B, A, C, T)
+        ok_re = bool(np.array_equal(re.cpu().numpy(), orc.reorder(x)))
+        co = torch.randn((B, 2, C, 2 * A, 2 * M), dtype=torch.float32, device=dev)
+        ob = torch.full_like(out, float("nan"))
+        _capi.beamform(re, co, ob, B, C, T, A, M, _capi.FLAG_SIGNED_INPUT if signed else 0)
+        torch.cuda.synchronize()
+        _capi.fused_status()
+        xr = (re.view(torch.int8) if signed else re).double().reshape(B, 2, C, T, 2 * A)
+        refb = torch.matmul(xr, co.double())
+        scale = torch.matmul(xr.abs(), co.double().abs()) + 1e-30
+        eb = float(((ob.reshape(B, 2, C, T, 2 * M).double() - refb).abs() / scale).max()) if not torch.isnan(ob).any() else float("inf")
+        worst_b = max(worst_b, eb)
+        ok = ratio <= 1.0 and ok_re and eb < 4e-6
+        bad += not ok
+        if not ok or case % 20 == 0:
+            print(tag, f"fused err/budget {ratio:.2e} reorder {'ok' if ok_re else 'BAD'} beamform {eb:.2e} {'ok' if ok else 'FAIL'}", flush=True)
+    print(f"{n_cases} cases, {bad} failed; worst fused err/budget {worst_f:.2e}, worst beamform err/sum|x||w| {worst_b:.2e}")
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
