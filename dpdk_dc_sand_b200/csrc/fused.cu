@@ -108,7 +108,7 @@ struct FusedParams {
     int ub;          // batches sharing one coefficient set: B, or 1 with time-varying steering
     int raw_stages;  // depth of the raw TMA ring: kRawStages + extra stages placed behind the B tiles
     int raw_extra_off;  // byte offset of the first extra stage inside each 64 KiB B buffer
-    uint32_t inv_a;     // floor(2^32 / A) + 1: e / A == umulhi(e, inv_a) for every entry index of an N tile
+    uint32_t inv_a;     // floor(2^32 / A) + 1: e / A == umulhi(e, inv_a) for every entry index of an N tile (A >= 2)
     float dt_hi[DCBF_MAX_TV_BATCHES], dt_lo[DCBF_MAX_TV_BATCHES];  // per-batch time offset (s) as a float pair
     double chan_centre;      // absolute index of local channel 0, minus N/2
     double turns_per_delay;  // -1 / (N * Ts): half-turns of phase per (second of delay x channel offset)
@@ -1014,7 +1014,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     sn *= w;
                 }
                 if constexpr (kQ8) {  // requantisation gain of this entry's beam, relative to the largest one
-                    const float g = __ldg(g_tile + __umulhi(static_cast<uint32_t>(e), prm.inv_a)) * q8_inv_gmax;
+                    const float g = __ldg(g_tile + (A == 1 ? static_cast<uint32_t>(e) : __umulhi(static_cast<uint32_t>(e), prm.inv_a))) * q8_inv_gmax;
                     cs *= g;
                     sn *= g;
                 }

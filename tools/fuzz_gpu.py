@@ -43,9 +43,29 @@ def main():
         dx, ddv = torch.from_numpy(x).to(dev), torch.from_numpy(dv).to(dev)
         out = torch.full((B, 2, C, T // 16, 16, 2 * M), float("nan"), dtype=torch.float32, device=dev)
         flags = (_capi.FLAG_SIGNED_INPUT if signed else 0) | (_capi.FLAG_FP16_COEFF if fp16 else 0)
-        tag = f"case {case}: B{B} A{A} C{C} T{T} M{M} N{n_total} x{xid} signed={signed:d} fp16={fp16:d}"
+        mode = ["plain", "plain", "tv", "weights", "q8", "tv+weights+q8"][int(rng.integers(0, 6))]
+        if A > 512 and mode != "plain":
+            mode = "plain"
+        batch_dt = list(rng.uniform(-2.0, 2.0, B)) if "tv" in mode else None
+        weights = rng.uniform(0.0, 1.5, (M, A)).astype(np.float32) if "weights" in mode else None
+        if batch_dt is not None:  # rates that move the phase by a few turns over the +-2 s
+            dv[..., 1] = rng.uniform(-1e-10, 1e-10, dv.shape[:-1])
+            dv[..., 3] = rng.uniform(-1.0, 1.0, dv.shape[:-1])
+            ddv = torch.from_numpy(dv).to(dev)
+        tag = f"case {case}: B{B} A{A} C{C} T{T} M{M} N{n_total} x{xid} signed={signed:d} fp16={fp16:d} {mode}"
+        ref = orc.beamform_pipeline(x, dv, n_total, xid, TS, signed_input=signed, batch_dt=batch_dt, weights=weights)
+        gains = out8 = sat = None
+        if "q8" in mode:
+            gains = (rng.uniform(0.5, 3.0, M) * 100.0 / max(np.abs(ref).max(), 1e-9)).astype(np.float32)
+            out8 = torch.full(out.shape, 77, dtype=torch.int8, device=dev)
+            sat = torch.zeros(1, dtype=torch.int64, device=dev)
         try:
-            _capi.fused(dx, ddv, out, B, A, C, n_total, T, M, xid, TS, flags)
+            if mode == "plain":
+                _capi.fused(dx, ddv, out, B, A, C, n_total, T, M, xid, TS, flags)
+            else:
+                _capi.fused_ex(dx, ddv, None if out8 is not None else out, B, A, C, n_total, T, M, xid, TS, flags,
+                               batch_dt=batch_dt, weights=None if weights is None else torch.from_numpy(weights).to(dev),
+                               gains=None if gains is None else torch.from_numpy(gains).to(dev), beams_q8=out8, saturated=sat)
             torch.cuda.synchronize()
             _capi.fused_status()
         except Exception as e:  # noqa: BLE001
@@ -53,10 +73,19 @@ def main():
             print(tag, "refused as documented" if expected else f"EXCEPTION {e}", flush=True)
             bad += not expected
             continue
-        ref = orc.beamform_pipeline(x, dv, n_total, xid, TS, signed_input=signed)
         budget = 2.0 ** -10 * orc.beamform_abs_bound(orc.reorder(x), signed_input=signed)[..., None]
-        got = out.cpu().numpy()
-        ratio = float(np.max(np.abs(got - ref) / np.maximum(budget, 1e-30))) if not np.isnan(got).any() else float("inf")
+        if weights is not None:
+            budget = budget * 1.5
+        if out8 is not None:  # int8 output: at most one step from the float64 requantisation, same clip count
+            want, want_clipped = orc.requantise(ref, gains)
+            diff = np.abs(out8.cpu().numpy().astype(np.int32) - want.astype(np.int32))
+            frac = np.count_nonzero(diff) / diff.size
+            ratio = 0.0 if diff.max() <= 1 and frac <= (5e-2 if fp16 else 2e-3) and abs(int(sat.item()) - want_clipped) <= 2 + 0.05 * want_clipped else float("inf")
+            if ratio:
+                print(f"  q8 detail: max diff {diff.max()}, fraction differing {frac:.2e}, clipped {int(sat.item())} vs {want_clipped}", flush=True)
+        else:
+            got = out.cpu().numpy()
+            ratio = float(np.max(np.abs(got - ref) / np.maximum(budget, 1e-30))) if not np.isnan(got).any() else float("inf")
         worst_f = max(worst_f, ratio)
         # stand-alone ops
         re = torch.empty((B, 2, C, T // 16, 16, A, 2), dtype=torch.uint8, device=dev)
