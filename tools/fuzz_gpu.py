@@ -1,7 +1,7 @@
 """Randomised shape sweep of the C ABI against float64 references (developer aid; the committed parity tests are
 tests/test_gpu_parity.py).
 
-    python tools/fuzz_gpu.py [n_cases] [seed]
+    python tools/fuzz_gpu.py [n_cases] [seed] [--many-channels]
 
 Every case draws (B, A, C, T, M, flags) and checks: dcbf_fused against the oracle pipeline (2^-10 sum|x| budget; the
 observed error is printed), dcbf_reorder bit-exact, dcbf_beamform (tcgen05 or CUDA cores, whichever the shape takes)
@@ -23,6 +23,7 @@ TS = orc.SAMPLE_PERIOD
 def main():
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    many_channels = "--many-channels" in sys.argv
     rng = np.random.default_rng(seed)
     dev = torch.device("cuda", 0)
     worst_f, worst_b, bad = 0.0, 0.0, 0
@@ -34,6 +35,9 @@ def main():
         while B * A * T * M > 3e6:  # keep the float64 oracle fast
             M = max(1, M // 2)
         C = int(rng.integers(1, 6)) if A * M > 4000 else int(rng.integers(1, 40))
+        if many_channels:  # more work units than SMs: the persistent loops wrap, every ring changes phase many times
+            A, M, T = min(A, 33), min(M, 17), min(T, 64)
+            C = int(rng.integers(150, 900))
         signed = bool(rng.integers(0, 2))
         fp16 = bool(rng.integers(0, 4) == 0)
         n_total = C * int(rng.integers(1, 4))
@@ -101,10 +105,26 @@ def main():
         scale = torch.matmul(xr.abs(), co.double().abs()) + 1e-30
         eb = float(((ob.reshape(B, 2, C, T, 2 * M).double() - refb).abs() / scale).max()) if not torch.isnan(ob).any() else float("inf")
         worst_b = max(worst_b, eb)
-        ok = ratio <= 1.0 and ok_re and eb < 4e-6
+        # stand-alone coefficients (float64 evaluation; same per-heap times / weights as the fused call)
+        cg = torch.full((B, 2, C, 2 * A, 2 * M), float("nan"), dtype=torch.float32, device=dev)
+        _capi.coeffs(ddv, cg, B, 2, C, n_total, A, M, xid, TS, batch_dt=batch_dt,
+                     weights=None if weights is None else torch.from_numpy(weights).to(dev))
+        cref = orc.steering_coeffs(dv, B, 2, C, n_total, A, M, xid, TS, out_dtype=np.float64, batch_dt=batch_dt, weights=weights)
+        ec = float(np.abs(cg.cpu().numpy().astype(np.float64) - cref).max())
+        # host-buffer plan with a random chunking: bit-equal to the device path (plain mode only)
+        ok_plan = True
+        if mode == "plain":
+            plan = _capi.HostPlan(B, A, C, n_total, T, M, xid, TS, flags, chunk_chans=int(rng.integers(1, C + 1)),
+                                  n_slots=int(rng.integers(2, 5)))
+            h_out = np.empty(out.shape, np.float32)
+            plan.run(x, dv, h_out)
+            plan.close()
+            ok_plan = bool(np.array_equal(h_out, out.cpu().numpy()))
+        ok = ratio <= 1.0 and ok_re and eb < 4e-6 and ec <= 2.5e-6 and ok_plan
         bad += not ok
         if not ok or case % 20 == 0:
-            print(tag, f"fused err/budget {ratio:.2e} reorder {'ok' if ok_re else 'BAD'} beamform {eb:.2e} {'ok' if ok else 'FAIL'}", flush=True)
+            print(tag, f"fused err/budget {ratio:.2e} reorder {'ok' if ok_re else 'BAD'} beamform {eb:.2e} coeffs {ec:.1e} "
+                       f"plan {'ok' if ok_plan else 'BAD'} {'ok' if ok else 'FAIL'}", flush=True)
     print(f"{n_cases} cases, {bad} failed; worst fused err/budget {worst_f:.2e}, worst beamform err/sum|x||w| {worst_b:.2e}")
     sys.exit(1 if bad else 0)
 
