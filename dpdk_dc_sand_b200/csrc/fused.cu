@@ -104,6 +104,7 @@ struct FusedParams {
     int tma_store;   // 1: epilogue through shared memory + TMA tensor stores; 0: st.global from registers
     int merged;      // hi and lo coefficient rows form ONE N = 2 nt tile per MMA (nt <= 64); the epilogue adds the halves
     int q8_wide;     // q8 only: the N tile is the whole output row (32 / 64 / 128 bytes): one box per 32 rows
+    int hg_count;    // kStream: groups of <= 2 time tiles per (channel, N tile)
     int sb_count;    // coefficient sets per (channel, N tile): 1, or B with time-varying steering
     int ub;          // batches sharing one coefficient set: B, or 1 with time-varying steering
     int raw_stages;  // depth of the raw TMA ring: kRawStages + extra stages placed behind the B tiles
@@ -312,10 +313,18 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     const int A = prm.A, C = prm.C, T = prm.T, M = prm.M, B = prm.B;
     const int N2 = 2 * M;
     const int nt = prm.nt, parts = prm.parts;
-    // Scheduling unit: a channel; with K-streamed B tiles a (channel, N tile) pair = unit / nt_count, unit % nt_count
-    // (a channel of many beams takes long enough that whole channels balance badly over the CTAs)
-    const uint32_t n_units = kStream ? static_cast<uint32_t>(C) * static_cast<uint32_t>(prm.nt_count) : static_cast<uint32_t>(C);
+    // Scheduling unit: a channel; with K-streamed B tiles a (channel, N tile, group of <= 2 time tiles) triple
+    // (a channel of many beams takes long enough that whole channels balance badly over the CTAs; two time tiles are
+    // what the TMEM accumulators of one unit hold)
+    const uint32_t per_chan = kStream ? static_cast<uint32_t>(prm.nt_count * prm.hg_count) : 1u;
+    const uint32_t n_units = static_cast<uint32_t>(C) * per_chan;
     const int it_count = kStream ? 1 : prm.nt_count;  // N tiles iterated INSIDE one unit
+    // kStream: unit -> channel, N tile, first time tile and number of time tiles of the group
+    auto unit_decode = [&](uint32_t w, uint32_t* uc, int* uit, int* uh0, int* uhn) {
+        const uint32_t c_ = w / per_chan, r_ = w - c_ * per_chan;
+        const int it_ = static_cast<int>(r_) / prm.hg_count, hg_ = static_cast<int>(r_) - it_ * prm.hg_count;
+        *uc = c_, *uit = it_, *uh0 = 2 * hg_, *uhn = min(2, prm.ht_count - 2 * hg_);
+    };
     const uint32_t part_bytes = static_cast<uint32_t>(nt * 128);            // one part of a k-block: [nt rows][128 B]
     const uint32_t bop_kb_bytes = static_cast<uint32_t>(parts) * part_bytes;  // one k-block: [part][nt rows][128 B]
     // profiling: lane 0 of each role's first warp accounts blocked time per barrier class (slot) and role span
@@ -333,14 +342,18 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         bool ok = true;
         // slab order inside a (channel, N tile, batch): time tile outer, antenna slab inner; kStream: slab outer
         // (every B k-block is then used for both time tiles before it is released)
-        const int n_inner = kStream ? prm.ht_count : prm.slab_count, n_outer = kStream ? prm.slab_count : prm.ht_count;
-        for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k)
+        const int n_outer = kStream ? prm.slab_count : prm.ht_count;
+        for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
+            uint32_t uc = w;
+            int uit = 0, uh0 = 0, uhn = 0;
+            if (kStream) unit_decode(w, &uc, &uit, &uh0, &uhn);
+            const int n_inner = kStream ? uhn : prm.slab_count;
             for (int it = 0; it < it_count && ok; ++it)
                 for (int b = 0; b < B && ok; ++b)
                     for (int o = 0; o < n_outer && ok; ++o)
                         for (int i = 0; i < n_inner; ++i) {
-                            const int h = kStream ? i : o, s = kStream ? o : i;
-                            const int c = static_cast<int>(kStream ? w / static_cast<uint32_t>(prm.nt_count) : w);
+                            const int h = kStream ? uh0 + i : o, s = kStream ? o : i;
+                            const int c = static_cast<int>(uc);
                             ok = mbar_wait<kProf>(bar(kRawEmpty + rs), ph ^ 1u, ctl, prm.status, kRoleProducer, kRawEmpty + rs, ps + 0);
                             if (!ok) break;
                             if (elect_one()) {
@@ -350,6 +363,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                             __syncwarp();
                             if (++rs == raw_stages) rs = 0, ph ^= 1u;
                         }
+        }
     } else if (warp == kMmaWarp || warp == kMmaWarp2) {
         // =================================== MMA issuer ===================================
         // merged: the lo rows follow the hi rows in the B tile, so one N = 2 nt MMA replaces two N = nt MMAs and the
@@ -366,7 +380,10 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             // (channel, N tile, batch) unit are open at once (ht x 2 x nt TMEM columns), slabs outer, time tiles inner
             const uint32_t pol = warp == kMmaWarp ? 0u : 1u;
             uint32_t kstep = 0;
-            for (uint32_t k = 0; ok && sched_get(ctl, k) < n_units; ++k)
+            for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
+                uint32_t uc;
+                int uit, uh0, uhn;
+                unit_decode(w, &uc, &uit, &uh0, &uhn);
                 for (int b = 0; b < B && ok; ++b, ++unit) {
                     ok = mbar_wait<kProf>(bar(kAccEmpty), (unit & 1u) ^ 1u, ctl, prm.status, kRoleMma, kAccEmpty, ps + 1);
                     if (!ok) break;
@@ -378,7 +395,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         const int n_ants = min(kSlabAnts, A - s * kSlabAnts);
                         const int k_steps = (n_ants + 7) >> 3;
                         const uint32_t b_lo = b_lo0 + slot * (kBopSlotBytes >> 4) + static_cast<uint32_t>(s & 1) * 4u;
-                        for (int h = 0; h < prm.ht_count && ok; ++h, ++slab) {
+                        for (int h = 0; h < uhn && ok; ++h, ++slab) {
                             const uint32_t as = slab % kAopStages;
                             ok = mbar_wait<kProf>(bar(kAopFull + as), (slab / kAopStages) & 1u, ctl, prm.status, kRoleMma, kAopFull + as, ps + 2);
                             if (!ok) break;
@@ -411,6 +428,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     if (ok && elect_one()) umma_commit(bar(kAccFull));
                     __syncwarp();
                 }
+            }
         } else
         for (uint32_t k = 0; ok && sched_get(ctl, k) < n_units; ++k)
             for (int isb = 0; isb < prm.nt_count * prm.sb_count && ok; ++isb, ++step) {  // (N tile, coefficient set)
@@ -569,15 +587,16 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         if constexpr (kStream) {
             // all (time tile, pol) accumulators of a (channel, N tile, batch) unit complete together
             for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
-                const uint32_t c = w / static_cast<uint32_t>(prm.nt_count);
-                const int it = static_cast<int>(w - c * static_cast<uint32_t>(prm.nt_count));
+                uint32_t c;
+                int it, uh0, uhn;
+                unit_decode(w, &c, &it, &uh0, &uhn);
                     for (int b = 0; b < B && ok; ++b, ++unit) {
                         ok = mbar_wait<kProf>(bar(kAccFull), unit & 1u, ctl, prm.status, kRoleEpilogue, kAccFull, ps + 0);
                         if (!ok) break;
                         tc_fence_after();
-                        for (int h = 0; h < prm.ht_count; ++h)
+                        for (int h = 0; h < uhn; ++h)
                             for (int p = 0; p < kPols; ++p)
-                                store_tile_f32((static_cast<uint32_t>(h) * kPols + p) * static_cast<uint32_t>(nt), b, p, c, h * kTileT, it * nt);
+                                store_tile_f32((static_cast<uint32_t>(h) * kPols + p) * static_cast<uint32_t>(nt), b, p, c, (uh0 + h) * kTileT, it * nt);
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar(kAccEmpty));
@@ -731,9 +750,15 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         const uint32_t sw = static_cast<uint32_t>((t >> 1) & 3);
         uint32_t slab = 0, rs = 0, rph = 0;
         bool ok = true;
-        for (uint32_t k = 0; ok && sched_get(ctl, k) < n_units; ++k)
+        for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
+            int tiles = prm.ht_count;  // time tiles per (unit, N tile, batch)
+            if (kStream) {
+                uint32_t uc;
+                int uit, uh0;
+                unit_decode(w, &uc, &uit, &uh0, &tiles);
+            }
             for (int it = 0; it < it_count && ok; ++it)
-                for (int bh = 0; bh < B * prm.ht_count && ok; ++bh)
+                for (int bh = 0; bh < B * tiles && ok; ++bh)
                     for (int s = 0; s < prm.slab_count; ++s, ++slab) {
                         const uint32_t as = slab % kAopStages;
                         ok = mbar_wait2<kProf>(bar(kRawFull + rs), rph, kRawFull + rs, bar(kAopEmpty + as),
@@ -772,6 +797,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         if (kProf && prof_lane)  // slot 2: (LDS + convert + STS) | (fence + arrive) << 32
                             ctl->wait_ns[kRoleConvert][2] += (tc1 - tc0) | ((global_ns() - tc1) << 32);
                     }
+        }
     } else if (warp < kCoeffWarp0 + kCoeffWarps) {
         // =================================== steering coefficients ===================================
         // delay_vals[c][m0 .. m0+mt) is one contiguous run of (beam, antenna) entries: the 256 threads walk it
@@ -811,7 +837,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 sch_end = true;
             } else if (sch_n > 0) {  // about one unit before the register loads get there
                 if (kStream)
-                    warm_l2(id / prm.nt_count, (id % prm.nt_count) * (nt >> 1));
+                    warm_l2(id / static_cast<int>(per_chan), ((id % static_cast<int>(per_chan)) / prm.hg_count) * (nt >> 1));
                 else
                     warm_l2(id, 0);
             }
@@ -849,7 +875,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             int nw = sched_get(ctl, 0), nb = 0, nkb = 0;  // load cursor: unit, batch, k-block
             float2 nxt[kPer];
             auto issue_loads = [&]() {
-                const int nc = nw / prm.nt_count, nit = nw - nc * prm.nt_count;
+                const int nc = nw / static_cast<int>(per_chan), nit = (nw - nc * static_cast<int>(per_chan)) / prm.hg_count;
                 const int m0 = nit * mt, mte = min(mt, M - m0), a = kKbAnts * nkb + lane;
 #pragma unroll
                 for (int u = 0; u < kPer; ++u) {
@@ -882,11 +908,12 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             uint32_t kstep = 0;
             bool ok = true;
             for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
-                const uint32_t c = w / static_cast<uint32_t>(prm.nt_count);
+                uint32_t c;
+                int it, uh0, uhn;
+                unit_decode(w, &c, &it, &uh0, &uhn);
                 const double scale = (static_cast<double>(c) + prm.chan_centre) * prm.turns_per_delay;
                 const float s_hi = static_cast<float>(scale), s_lo = static_cast<float>(scale - static_cast<double>(s_hi));
                 {
-                    const int it = static_cast<int>(w - c * static_cast<uint32_t>(prm.nt_count));
                     const int m0 = it * mt, mte = min(mt, M - m0);
                     const float* w_tile = prm.weights ? prm.weights + static_cast<size_t>(m0) * A : nullptr;
                     for (int bkb = 0; bkb < B * prm.kb_count && ok; ++bkb, ++kstep) {
@@ -1222,8 +1249,8 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     }
     // Many antennas x beams: a whole B tile set no longer fits 64 KiB with a useful width (the voltages would be
     // re-converted for every narrow N tile).  Stream B by 32-antenna k-blocks instead: N tiles of up to 128 columns.
-    const bool kstream = (p.nt_count > 1 || no_whole_tiles) && !q8 && !batch_dt_s && p.ht_count <= 2 &&
-                         !(flags & DCBF_FLAG_DEBUG_NO_KSTREAM);
+    const bool kstream = (p.nt_count > 1 || no_whole_tiles) && !q8 && !batch_dt_s && !(flags & DCBF_FLAG_DEBUG_NO_KSTREAM);
+    p.hg_count = (p.ht_count + 1) / 2;
     if (no_whole_tiles && !kstream) return DCBF_ERR_UNSUPPORTED;  // (the k-block ring itself has no antenna limit)
     if (kstream) {
         const int n_pad = ((2 * M + 15) / 16) * 16;
@@ -1307,7 +1334,8 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
         for (int i = 0; i < 14; ++i)
             DCBF_CUDA_TRY(cudaFuncSetAttribute(kKernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     }
-    const long long units = kstream ? static_cast<long long>(C) * p.nt_count : C;  // what the CTAs draw from the queue
+    const long long units = kstream ? static_cast<long long>(C) * p.nt_count * p.hg_count : C;
+    if (units > 0x7ffffff0LL) return DCBF_ERR_UNSUPPORTED;  // what the CTAs draw from the queue
     const int grid = units < n_sms[dev] ? static_cast<int>(units) : n_sms[dev];
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);

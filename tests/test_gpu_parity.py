@@ -241,6 +241,7 @@ def test_op_sequence_reference_inputs(dropin, n_ants):
 FUSED_CASES = [
     # B, A, C, T, M, N, xeng_id, signed, fp16_coeff
     (1, 600, 2, 128, 8, 64, 0, False, False),     # more antennas than any whole B tile set holds: k-block ring only
+    (1, 600, 2, 400, 8, 64, 1, True, False),      # ... and more than two time tiles: the ring is re-streamed per pair
     (1, 4, 64, 256, 4, 64, 0, False, False),      # BASELINE configs[0]
     (1, 64, 24, 256, 16, 1024, 0, False, False),  # configs[1] geometry, a slice of channels
     (1, 64, 10, 256, 64, 4096, 5, False, False),  # configs[2] geometry, xeng 5 of 8... (C=10 slice)
@@ -558,8 +559,9 @@ def test_concurrent_launches_on_several_streams_do_not_share_the_channel_queue(d
 
 
 @pytest.mark.parametrize("case", [(1, 197, 3, 256, 256, 4096, 1), (2, 45, 4, 128, 131, 512, 0), (3, 64, 2, 48, 80, 256, 2),
-                                  (1, 33, 150, 16, 70, 4096, 5)],
-                         ids=["C5_geometry", "odd_beams_direct_epilogue_2_heaps", "3_heaps_partial_tile", "150_channels"])
+                                  (1, 33, 150, 16, 70, 4096, 5), (2, 45, 3, 640, 131, 512, 1)],
+                         ids=["C5_geometry", "odd_beams_direct_epilogue_2_heaps", "3_heaps_partial_tile", "150_channels",
+                              "five_time_tiles"])
 def test_k_streamed_b_tiles_match_whole_tile_sets(dropin, case):
     """Many antennas x beams switch the fused kernel to K-streamed B tiles (a ring of 32-antenna k-blocks, N tiles up
     to 128 columns, all time-tile accumulators open at once).  Same result as the whole-tile-set mode
