@@ -873,7 +873,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             const int mt = nt >> 1;
             uint32_t nk = 0;
             int nw = sched_get(ctl, 0), nb = 0, nkb = 0;  // load cursor: unit, batch, k-block
-            float2 nxt[kPer];
+            Dv nxt[kPer];  // static: (delay_s, phase_rad); kTv: all four fields
             auto issue_loads = [&]() {
                 const int nc = nw / static_cast<int>(per_chan), nit = (nw - nc * static_cast<int>(per_chan)) / prm.hg_count;
                 const int m0 = nit * mt, mte = min(mt, M - m0), a = kKbAnts * nkb + lane;
@@ -883,7 +883,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (static_cast<uint32_t>(nw) < n_units && m < mte && a < A)
                         t4 = ldg_nc_f4(prm.dv + (static_cast<size_t>(nc) * M + m0 + m) * A + a);
-                    nxt[u] = make_float2(t4.x, t4.z);
+                    if constexpr (kTv) nxt[u] = t4;
+                    else nxt[u] = make_float2(t4.x, t4.z);
                 }
             };
             auto advance_cursor = [&]() {
@@ -919,7 +920,12 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     for (int bkb = 0; bkb < B * prm.kb_count && ok; ++bkb, ++kstep) {
                         const int kb = bkb % prm.kb_count;
                         const uint32_t slot = kstep % kBopSlots;
-                        float2 v[kPer];
+                        float dt_hi = 0.f, dt_lo = 0.f;
+                        if constexpr (kTv) {  // per-heap time: this step's coefficients belong to batch bkb / kb_count
+                            dt_hi = prm.dt_hi[bkb / prm.kb_count];
+                            dt_lo = prm.dt_lo[bkb / prm.kb_count];
+                        }
+                        Dv v[kPer];
 #pragma unroll
                         for (int u = 0; u < kPer; ++u) v[u] = nxt[u];
                         advance_cursor();
@@ -939,7 +945,14 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                 const int m = wl + kCoeffWarps * u;
                                 if (m < mte) {
                                     float r, small, sn, cs;
-                                    steer_phase<false>(v[u].x, 0.f, v[u].y, 0.f, s_hi, s_lo, scale, &r, &small);
+                                    if constexpr (kTv) {
+                                        float d_hi, d_lo, ph_hi, ph_lo;
+                                        advance_model(v[u].x, v[u].y, dt_hi, dt_lo, &d_hi, &d_lo);
+                                        advance_model(v[u].z, v[u].w, dt_hi, dt_lo, &ph_hi, &ph_lo);
+                                        steer_phase<true>(d_hi, d_lo, ph_hi, ph_lo, s_hi, s_lo, scale, &r, &small);
+                                    } else {
+                                        steer_phase<false>(v[u].x, 0.f, v[u].y, 0.f, s_hi, s_lo, scale, &r, &small);
+                                    }
                                     sincospi_reduced(r, small, &sn, &cs);
                                     if (w_tile) {
                                         const float w = __ldg(w_tile + static_cast<size_t>(m) * A + a);
@@ -1146,8 +1159,10 @@ constexpr int kLiveSlots = 64;   // launches in flight at once on one device tha
 constexpr int kSchedSlots = 2 * kLiveSlots;  // the second half belongs to launches captured into CUDA graphs, which keep
                                              // their slot for every replay and must not meet a live launch on it
 using KernelFn = void (*)(const FusedParams, const CUtensorMap, const CUtensorMap);
-// index = 6 * q8 + 2 * variant (0 plain, 1 profiling, 2 time-varying) + merged; [12], [13] = K-streamed B (plain, profiling)
-KernelFn const kKernels[14] = {
+// index = 6 * q8 + 2 * variant (0 plain, 1 profiling, 2 time-varying) + merged; [12] .. [14] = K-streamed B (plain,
+// profiling, time-varying)
+constexpr int kNumKernels = 15;
+KernelFn const kKernels[kNumKernels] = {
     fused_beamform_kernel<false, false, false, false, false>, fused_beamform_kernel<false, false, false, true, false>,
     fused_beamform_kernel<true, false, false, false, false>,  fused_beamform_kernel<true, false, false, true, false>,
     fused_beamform_kernel<false, true, false, false, false>,  fused_beamform_kernel<false, true, false, true, false>,
@@ -1155,6 +1170,7 @@ KernelFn const kKernels[14] = {
     fused_beamform_kernel<true, false, true, false, false>,   fused_beamform_kernel<true, false, true, true, false>,
     fused_beamform_kernel<false, true, true, false, false>,   fused_beamform_kernel<false, true, true, true, false>,
     fused_beamform_kernel<false, false, false, false, true>,  fused_beamform_kernel<true, false, false, false, true>,
+    fused_beamform_kernel<false, true, false, false, true>,
 };
 
 int* g_status_dev[64] = {};  // per-device: 4-int status block + kSchedSlots x {next, done} channel counters
@@ -1249,7 +1265,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     }
     // Many antennas x beams: a whole B tile set no longer fits 64 KiB with a useful width (the voltages would be
     // re-converted for every narrow N tile).  Stream B by 32-antenna k-blocks instead: N tiles of up to 128 columns.
-    const bool kstream = (p.nt_count > 1 || no_whole_tiles) && !q8 && !batch_dt_s && !(flags & DCBF_FLAG_DEBUG_NO_KSTREAM);
+    const bool kstream = (p.nt_count > 1 || no_whole_tiles) && !q8 && !(flags & DCBF_FLAG_DEBUG_NO_KSTREAM);
     p.hg_count = (p.ht_count + 1) / 2;
     if (no_whole_tiles && !kstream) return DCBF_ERR_UNSUPPORTED;  // (the k-block ring itself has no antenna limit)
     if (kstream) {
@@ -1331,7 +1347,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     DCBF_CUDA_TRY(cudaGetDevice(&dev));
     if (!n_sms[dev]) {
         DCBF_CUDA_TRY(cudaDeviceGetAttribute(&n_sms[dev], cudaDevAttrMultiProcessorCount, dev));
-        for (int i = 0; i < 14; ++i)
+        for (int i = 0; i < kNumKernels; ++i)
             DCBF_CUDA_TRY(cudaFuncSetAttribute(kKernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     }
     const long long units = kstream ? static_cast<long long>(C) * p.nt_count * p.hg_count : C;
@@ -1350,7 +1366,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     // (int8 output, variant, merged) specialisation; variant: 0 plain, 1 profiling, 2 time-varying steering (the
     // profiler has no time-varying build)
     const int variant = batch_dt_s ? 2 : p.prof ? 1 : 0;
-    auto kernel = kstream ? kKernels[12 + (p.prof ? 1 : 0)] : kKernels[(q8 ? 6 : 0) + 2 * variant + (p.merged ? 1 : 0)];
+    auto kernel = kstream ? kKernels[batch_dt_s ? 14 : 12 + (p.prof ? 1 : 0)] : kKernels[(q8 ? 6 : 0) + 2 * variant + (p.merged ? 1 : 0)];
     DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, p, tm_in, tm_out));
     DCBF_CHECK_LAUNCH("fused_beamform_kernel");
     return DCBF_OK;

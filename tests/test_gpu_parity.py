@@ -373,6 +373,31 @@ def test_time_varying_steering(dropin):
     np.testing.assert_array_equal(res[0], res[1])
 
 
+def test_time_varying_steering_with_many_antennas_and_beams(dropin):
+    """Per-heap times in the K-streamed mode (a shape whose B tile sets need several N tiles, heaps of three time
+    tiles): inside the budget against the float64 oracle and equal, to float32 rounding, to the whole-tile-set mode."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m, n, xid = 3, 100, 3, 384, 100, 512, 1
+    assert _capi.fused_tiling(a, m)[2] > 1
+    times = [0.0, 2.5, -3.75]
+    x = orc.make_samples(b, a, c, t, seed=43)
+    dv = _tv_delay_vals(c, m, a, seed=44)
+    ref = orc.beamform_pipeline(x, dv, n, xid, TS, batch_dt=times)
+    dx, ddv = torch.from_numpy(x).cuda(), torch.from_numpy(dv).cuda()
+    outs = []
+    for flags in (0, _capi.FLAG_DEBUG_NO_KSTREAM):
+        out = torch.full(ref.shape, float("nan"), dtype=torch.float32, device="cuda")
+        _capi.fused(dx, ddv, out, b, a, c, n, t, m, xid, TS, flags, batch_dt=times)
+        torch.cuda.synchronize()
+        _capi.fused_status()
+        outs.append(out.cpu().numpy().astype(np.float64))
+        assert np.all(np.abs(outs[-1] - ref) <= 2.0 ** -8 * _budget(x) + 1e-3)
+    np.testing.assert_allclose(outs[0], outs[1], rtol=0, atol=float(_budget(x).max()) * 2.0 ** -6)
+
+
 @pytest.mark.parametrize("case", [(1, 64, 7, 256, 16, 1024, 0, False), (2, 23, 3, 48, 3, 256, 1, True),
                                   (1, 80, 4, 256, 32, 32768, 3, False), (1, 4, 9, 128, 8, 64, 0, False),
                                   (1, 1, 21, 128, 15, 21, 0, False)],
