@@ -122,7 +122,7 @@ def main():
             ok_plan = bool(np.array_equal(h_out, out.cpu().numpy()))
         ok = ratio <= 1.0 and ok_re and eb < 4e-6 and ec <= 2.5e-6 and ok_plan
         bad += not ok
-        if not ok or case % 20 == 0:
+        if not ok or case % 20 == 0 or A > 512:
             print(tag, f"fused err/budget {ratio:.2e} reorder {'ok' if ok_re else 'BAD'} beamform {eb:.2e} coeffs {ec:.1e} "
                        f"plan {'ok' if ok_plan else 'BAD'} {'ok' if ok else 'FAIL'}", flush=True)
     print(f"{n_cases} cases, {bad} failed; worst fused err/budget {worst_f:.2e}, worst beamform err/sum|x||w| {worst_b:.2e}")
