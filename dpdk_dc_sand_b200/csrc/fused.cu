@@ -595,8 +595,55 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         if (!ok) break;
                         tc_fence_after();
                         for (int h = 0; h < uhn; ++h)
-                            for (int p = 0; p < kPols; ++p)
-                                store_tile_f32((static_cast<uint32_t>(h) * kPols + p) * static_cast<uint32_t>(nt), b, p, c, (uh0 + h) * kTileT, it * nt);
+                            for (int p = 0; p < kPols; ++p) {
+                                const uint32_t col0 = (static_cast<uint32_t>(h) * kPols + p) * static_cast<uint32_t>(nt);
+                                if constexpr (kQ8) {
+                                    // requantised output, 32-column blocks through four rotating 1 KiB boxes (as below)
+                                    const int row0 = (uh0 + h) * kTileT + 32 * q, n0 = it * nt;
+                                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + col0;
+                                    const int plane = (b * kPols + p) * C + static_cast<int>(c);
+                                    for (int cb = 0; cb < nt && row0 < T && n0 + cb < N2; cb += 32, ++box) {
+                                        uint32_t r[32], w[8];
+                                        tmem_ld_32x32b_x32(taddr + cb, r);
+                                        bulk_wait_group_read<3>();  // (issuing lane) the box used four blocks ago is free
+                                        __syncwarp();
+                                        tmem_wait_ld();
+                                        const int valid = min(nt, N2 - n0) - cb;  // columns past the last beam: never stored, never "clipped"
+                                        if (valid < 32) {
+#pragma unroll
+                                            for (int i = 0; i < 32; ++i)
+                                                if (i >= valid) r[i] = 0u;
+                                        }
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j)
+                                            w[j] = prm.saturated ? quantise4<true>(r, j, q8_gain, q8_limit, &clipped)
+                                                                 : quantise4<false>(r, j, q8_gain, q8_limit, &clipped);
+                                        if (prm.tma_store) {
+                                            const uint32_t sb = ost + (box & 3u) * 1024u;
+                                            const uint32_t dst = sb + lane * 32;  // [32 rows][32 B], 32B swizzle
+                                            const uint32_t x = static_cast<uint32_t>((lane >> 2) & 1) << 4;
+                                            st_shared_v4(dst + x, w[0], w[1], w[2], w[3]);
+                                            st_shared_v4(dst + (x ^ 16u), w[4], w[5], w[6], w[7]);
+                                            fence_proxy_async_smem();
+                                            __syncwarp();
+                                            if (elect_one()) {
+                                                tma_store_3d(&tm_out, sb, n0 + cb, row0, plane);
+                                                bulk_commit_group();
+                                            }
+                                        } else if (row0 + lane < T) {  // ragged beam counts: 2-byte stores (row pitch 2M is even)
+                                            uint8_t* rowp = reinterpret_cast<uint8_t*>(prm.out_q8) +
+                                                            (static_cast<size_t>(plane) * T + row0 + lane) * static_cast<size_t>(N2) + n0 + cb;
+#pragma unroll
+                                            for (int j = 0; j < 16; ++j)
+                                                if (n0 + cb + 2 * j < N2)
+                                                    *reinterpret_cast<uint16_t*>(rowp + 2 * j) =
+                                                        static_cast<uint16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+                                        }
+                                    }
+                                } else {
+                                    store_tile_f32(col0, b, p, c, (uh0 + h) * kTileT, it * nt);
+                                }
+                            }
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar(kAccEmpty));
@@ -869,6 +916,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             // takes beams w, w + 8, ...: 8 beams per warp and step.  Coefficients are regenerated per batch in
             // this mode (the ring does not keep them).
             constexpr int kPer = 8;
+            const float ks_inv_gmax = kQ8 && ctl->q8_gmax > 0.f ? 1.0f / ctl->q8_gmax : 0.f;
             const int wl = warp - kCoeffWarp0;
             const int mt = nt >> 1;
             uint32_t nk = 0;
@@ -958,6 +1006,11 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                         const float w = __ldg(w_tile + static_cast<size_t>(m) * A + a);
                                         cs *= w;
                                         sn *= w;
+                                    }
+                                    if constexpr (kQ8) {  // requantisation gain of this beam, relative to the largest one
+                                        const float g = __ldg(prm.gains + m0 + m) * ks_inv_gmax;
+                                        cs *= g;
+                                        sn *= g;
                                     }
                                     const uint32_t hi = pack_half2(cs, sn);
                                     const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
@@ -1159,9 +1212,9 @@ constexpr int kLiveSlots = 64;   // launches in flight at once on one device tha
 constexpr int kSchedSlots = 2 * kLiveSlots;  // the second half belongs to launches captured into CUDA graphs, which keep
                                              // their slot for every replay and must not meet a live launch on it
 using KernelFn = void (*)(const FusedParams, const CUtensorMap, const CUtensorMap);
-// index = 6 * q8 + 2 * variant (0 plain, 1 profiling, 2 time-varying) + merged; [12] .. [14] = K-streamed B (plain,
-// profiling, time-varying)
-constexpr int kNumKernels = 15;
+// index = 6 * q8 + 2 * variant (0 plain, 1 profiling, 2 time-varying) + merged; [12] .. [16] = K-streamed B (plain,
+// profiling, time-varying, int8 output, int8 output + time-varying)
+constexpr int kNumKernels = 17;
 KernelFn const kKernels[kNumKernels] = {
     fused_beamform_kernel<false, false, false, false, false>, fused_beamform_kernel<false, false, false, true, false>,
     fused_beamform_kernel<true, false, false, false, false>,  fused_beamform_kernel<true, false, false, true, false>,
@@ -1171,6 +1224,7 @@ KernelFn const kKernels[kNumKernels] = {
     fused_beamform_kernel<false, true, true, false, false>,   fused_beamform_kernel<false, true, true, true, false>,
     fused_beamform_kernel<false, false, false, false, true>,  fused_beamform_kernel<true, false, false, false, true>,
     fused_beamform_kernel<false, true, false, false, true>,
+    fused_beamform_kernel<false, false, true, false, true>,   fused_beamform_kernel<false, true, true, false, true>,
 };
 
 int* g_status_dev[64] = {};  // per-device: 4-int status block + kSchedSlots x {next, done} channel counters
@@ -1265,7 +1319,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     }
     // Many antennas x beams: a whole B tile set no longer fits 64 KiB with a useful width (the voltages would be
     // re-converted for every narrow N tile).  Stream B by 32-antenna k-blocks instead: N tiles of up to 128 columns.
-    const bool kstream = (p.nt_count > 1 || no_whole_tiles) && !q8 && !(flags & DCBF_FLAG_DEBUG_NO_KSTREAM);
+    const bool kstream = (p.nt_count > 1 || no_whole_tiles) && !(flags & DCBF_FLAG_DEBUG_NO_KSTREAM);
     p.hg_count = (p.ht_count + 1) / 2;
     if (no_whole_tiles && !kstream) return DCBF_ERR_UNSUPPORTED;  // (the k-block ring itself has no antenna limit)
     if (kstream) {
@@ -1311,7 +1365,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return record_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(samples)");
     }
-    p.q8_wide = q8 && p.tma_store && p.nt_count == 1 && (p.nt == 32 || p.nt == 64 || p.nt == 128);
+    p.q8_wide = q8 && !kstream && p.tma_store && p.nt_count == 1 && (p.nt == 32 || p.nt == 64 || p.nt == 128);
     if (p.tma_store && q8) {
         // requantised beams as [B*2*C][T][2M] int8; box [1][32][32] with 32B swizzle, or -- when one N tile is the
         // whole row -- box [1][32][nt] with the swizzle span equal to the row length
@@ -1366,7 +1420,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     // (int8 output, variant, merged) specialisation; variant: 0 plain, 1 profiling, 2 time-varying steering (the
     // profiler has no time-varying build)
     const int variant = batch_dt_s ? 2 : p.prof ? 1 : 0;
-    auto kernel = kstream ? kKernels[batch_dt_s ? 14 : 12 + (p.prof ? 1 : 0)] : kKernels[(q8 ? 6 : 0) + 2 * variant + (p.merged ? 1 : 0)];
+    auto kernel = kstream ? kKernels[q8 ? (batch_dt_s ? 16 : 15) : batch_dt_s ? 14 : 12 + (p.prof ? 1 : 0)] : kKernels[(q8 ? 6 : 0) + 2 * variant + (p.merged ? 1 : 0)];
     DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, p, tm_in, tm_out));
     DCBF_CHECK_LAUNCH("fused_beamform_kernel");
     return DCBF_OK;

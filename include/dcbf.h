@@ -50,9 +50,8 @@ typedef void* dcbf_stream_t; /* cudaStream_t */
 typedef enum dcbf_status {
     DCBF_OK = 0,
     DCBF_ERR_INVALID_ARG = -1, /* null pointer, non-positive dimension, T % 16 != 0, misaligned pointer */
-    DCBF_ERR_UNSUPPORTED = -2, /* shape outside what the kernels were built for: int8 output with more than 512 antennas
-                                  (1024 with DCBF_FLAG_FP16_COEFF); more than DCBF_MAX_TV_BATCHES heaps with per-heap
-                                  times; index overflow */
+    DCBF_ERR_UNSUPPORTED = -2, /* shape outside what the kernels were built for: more than DCBF_MAX_TV_BATCHES heaps
+                                  with per-heap times; index overflow */
     DCBF_ERR_CUDA = -3,        /* a CUDA runtime call failed; see dcbf_last_cuda_error() */
     DCBF_ERR_NO_DEVICE = -4,   /* no sm_100 device is current */
     DCBF_ERR_TIMEOUT = -5      /* in-kernel watchdog fired (pipeline dead-lock guard) */
@@ -166,7 +165,7 @@ void dcbf_debug_set_profile_buffer(unsigned long long* dev_ptr);
 
 /* The whole-tile-set tiling of dcbf_fused for (n_ants, n_beams, flags): k-blocks of 32 antennas, N tiles of *nt
  * columns such that one tile set (all k-blocks, hi+lo) fits a 64 KiB buffer.  When that needs more than one N tile
- * (*nt_count > 1), without int8 output, the kernel streams B by k-blocks instead and uses N tiles
+ * (*nt_count > 1) the kernel streams B by k-blocks instead and uses N tiles
  * of up to 128 columns (ceil(2 n_beams / 128) of them), two 128-sample time tiles at a time. */
 void dcbf_fused_tiling(int n_ants, int n_beams, unsigned flags, int* kb_count, int* nt, int* nt_count);
 

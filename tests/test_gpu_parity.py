@@ -400,8 +400,10 @@ def test_time_varying_steering_with_many_antennas_and_beams(dropin):
 
 @pytest.mark.parametrize("case", [(1, 64, 7, 256, 16, 1024, 0, False), (2, 23, 3, 48, 3, 256, 1, True),
                                   (1, 80, 4, 256, 32, 32768, 3, False), (1, 4, 9, 128, 8, 64, 0, False),
-                                  (1, 1, 21, 128, 15, 21, 0, False)],
-                         ids=["M16_tma", "M3_ragged_signed", "M32_A80", "M8_16cols", "single_antenna"])
+                                  (1, 1, 21, 128, 15, 21, 0, False), (2, 100, 3, 384, 100, 512, 1, False),
+                                  (1, 600, 2, 128, 5, 64, 0, True)],
+                         ids=["M16_tma", "M3_ragged_signed", "M32_A80", "M8_16cols", "single_antenna", "k_streamed",
+                              "k_streamed_600_antennas_odd_beams"])
 def test_fused_q8_requantised_output(dropin, case):
     """Next-row feature: int8 beams = clip(rint(beam * gain[m]), -127, 127) in the fused epilogue.
     Against the float64 oracle: never more than one quantisation step away, practically always equal (the only
