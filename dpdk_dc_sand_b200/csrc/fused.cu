@@ -922,15 +922,25 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             uint32_t nk = 0;
             int nw = sched_get(ctl, 0), nb = 0, nkb = 0;  // load cursor: unit, batch, k-block
             Dv nxt[kPer];  // static: (delay_s, phase_rad); kTv: all four fields
+            // the cursor's unit, decoded once per unit (the divisions would otherwise sit in every k-block step)
+            const float4* n_src = prm.dv;  // delay_vals of (channel, first beam of the N tile)
+            int n_mte = 0;                 // beams in the N tile; 0 past the last unit
+            auto cursor_decode = [&]() {
+                n_mte = 0;
+                if (static_cast<uint32_t>(nw) < n_units) {
+                    const int nc = nw / static_cast<int>(per_chan), nit = (nw - nc * static_cast<int>(per_chan)) / prm.hg_count;
+                    n_mte = min(mt, M - nit * mt);
+                    n_src = prm.dv + (static_cast<size_t>(nc) * M + nit * mt) * A;
+                }
+            };
+            cursor_decode();
             auto issue_loads = [&]() {
-                const int nc = nw / static_cast<int>(per_chan), nit = (nw - nc * static_cast<int>(per_chan)) / prm.hg_count;
-                const int m0 = nit * mt, mte = min(mt, M - m0), a = kKbAnts * nkb + lane;
+                const int a = kKbAnts * nkb + lane;
 #pragma unroll
                 for (int u = 0; u < kPer; ++u) {
                     const int m = wl + kCoeffWarps * u;
                     float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (static_cast<uint32_t>(nw) < n_units && m < mte && a < A)
-                        t4 = ldg_nc_f4(prm.dv + (static_cast<size_t>(nc) * M + m0 + m) * A + a);
+                    if (m < n_mte && a < A) t4 = ldg_nc_f4(n_src + static_cast<size_t>(m) * A + a);
                     if constexpr (kTv) nxt[u] = t4;
                     else nxt[u] = make_float2(t4.x, t4.z);
                 }
@@ -952,6 +962,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 }
                 __syncwarp();
                 nw = sched_get(ctl, nk);
+                cursor_decode();
             };
             issue_loads();
             uint32_t kstep = 0;
