@@ -33,7 +33,11 @@
 // <= 64 columns run hi and lo as ONE N = 2 nt MMA (kMerged).
 //
 // Template specialisations: kProf (per-role blocked-time accounting, tools/prof_roles.py), kTv (per-heap delay /
-// phase rates, dcbf_fused_tv), kQ8 (int8 requantised output, dcbf_fused_q8), kMerged.
+// phase rates, dcbf_fused_tv), kQ8 (int8 requantised output, dcbf_fused_q8), kMerged, and kStream: when one B tile
+// set would need several N tiles (many antennas x beams) or does not fit at all (> 512 antennas), B is streamed
+// through a ring of 32-antenna k-blocks instead, with N tiles of up to 128 columns, two time tiles (all four
+// (time tile, pol) accumulators) per unit, and (channel, N tile, time-tile pair) units drawn from the queue.
+// Raw ring: 4 stages of their own plus, for narrow N tiles, up to 4 more in the unused tail of the B buffers.
 #include <cuda.h>
 
 #include <atomic>
