@@ -38,7 +38,7 @@ __device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
 
 __global__ void __launch_bounds__(kThreads)
 reorder_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int A, int C, int T, int tile_t,
-               int n_tiles) {
+               int n_tiles, uint32_t inv_a /* floor(2^32 / A) + 1 for A >= 2: e / A == umulhi(e, inv_a), e < 2^17 */) {
     extern __shared__ __align__(16) uint32_t raw[];  // [A][tile_t] words, row a rotated by 4 * (a / 8)
 
     const long long blk = blockIdx.x;
@@ -66,17 +66,25 @@ reorder_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int A,
     const size_t base0 = ((static_cast<size_t>(b) * kPols * C + c) * static_cast<size_t>(T) + t0) * A * 2;
     uint4* dst0 = reinterpret_cast<uint4*>(out + base0);
     uint4* dst1 = reinterpret_cast<uint4*>(out + base0 + static_cast<size_t>(C) * T * A * 2);  // pol 1 plane
+    const bool groups_of_8 = (A & 7) == 0;  // a chunk is then 8 antennas of ONE sample: one base address, constant stride
     for (int i = threadIdx.x; i < n_chunk; i += kThreads) {
         const int e = i << 3;
-        int t = e / A;
+        // e / A (ncu: the gather was bound by its own integer arithmetic, not by memory)
+        int t = inv_a ? static_cast<int>(__umulhi(static_cast<uint32_t>(e), inv_a)) : e;
         int a = e - t * A;
         uint32_t w[8];
+        if (groups_of_8) {
+            const uint32_t* src = raw + a * tile_t + ((t + 4 * (a >> 3)) & mask);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            w[j] = raw[a * tile_t + ((t + 4 * (a >> 3)) & mask)];
-            if (++a == A) {
-                a = 0;
-                ++t;
+            for (int j = 0; j < 8; ++j) w[j] = src[j * tile_t];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                w[j] = raw[a * tile_t + ((t + 4 * (a >> 3)) & mask)];
+                if (++a == A) {
+                    a = 0;
+                    ++t;
+                }
             }
         }
         uint4 v0, v1;  // low / high 16 bits of two words = pol 0 / pol 1 (re, im) of two elements
@@ -112,8 +120,10 @@ int launch_reorder(const uint8_t* samples, uint8_t* reordered, int B, int A, int
     if (smem > 48 * 1024)
         DCBF_CUDA_TRY(cudaFuncSetAttribute(reorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem)));
+    // e / A for the element indices of a tile (e < tile_t * A <= 51200) through one multiply; A = 1: e / 1 = e
+    const uint32_t inv_a = A == 1 ? 0u : static_cast<uint32_t>((1ull << 32) / static_cast<unsigned>(A)) + 1u;
     reorder_kernel<<<static_cast<unsigned>(n_blocks), kThreads, smem, s>>>(samples, reordered, A, C, T, tile_t,
-                                                                           n_tiles);
+                                                                           n_tiles, inv_a);
     DCBF_CHECK_LAUNCH("reorder_kernel");
     return DCBF_OK;
 }
