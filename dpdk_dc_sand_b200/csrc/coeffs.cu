@@ -69,10 +69,20 @@ coeffs_kernel(const float4* __restrict__ delay_vals, float* __restrict__ coeffs,
     const int reps = times.n > 0 ? n_pols : n_batches * n_pols;  // (batch, pol) replicas per set
     for (int g = 0; g < n_groups; ++g) {
         // phase 1: lanes along ant
-        for (int mi = warp; mi < kTile; mi += kThreads / 32) {
+        // all four loads of this thread first (ncu: the dependent load -> float64 chain -> next load sequence left
+        // the warps waiting on long_scoreboard most of the time)
+        float4 dvs[kTile / (kThreads / 32)];
+#pragma unroll
+        for (int r = 0; r < kTile / (kThreads / 32); ++r) {
+            const int m = m0 + warp + r * (kThreads / 32), a = a0 + lane;
+            dvs[r] = (m < M && a < A) ? __ldg(delay_vals + (static_cast<size_t>(c) * M + m) * A + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < kTile / (kThreads / 32); ++r) {
+            const int mi = warp + r * (kThreads / 32);
             const int m = m0 + mi, a = a0 + lane;
             if (m < M && a < A) {
-                const float4 dv = __ldg(delay_vals + (static_cast<size_t>(c) * M + m) * A + a);
+                const float4 dv = dvs[r];
                 double delay = static_cast<double>(dv.x);
                 double phase = static_cast<double>(dv.z);
                 if (times.n > 0) {
