@@ -2,7 +2,7 @@
 there; run whole here they check 64-bit indexing and the multi-N-tile path at full size).  Each result is checked on a
 few sampled channels against the oracle.
 
-    python tools/bench_configs.py [c2 c3 c4 c5 ...]
+    python tests/probes/bench_configs.py [c2 c3 c4 c5 ...]
 """
 import json
 import os
@@ -11,7 +11,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from dpdk_dc_sand_b200 import _capi  # noqa: E402
 from oracle import beamform_oracle as orc  # noqa: E402
 
@@ -30,7 +30,7 @@ def main():
         del sys.argv[i:i + 2]
     names = sys.argv[1:] or ["c2", "c3", "c4", "c5"]
     peak = 6550.1
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "MEASURED_PEAKS.json")
     if os.path.exists(path):
         peak = float(json.load(open(path))["hbm_gbs"])
     dev = torch.device("cuda", 0)

@@ -1,8 +1,8 @@
 """Developer probe: a few extreme shapes (1 ... 4096 antennas, 1 ... 2000 beams, 16 ... 4096 samples) through dcbf_fused and
-dcbf_beamform against float64 references.    python tools/extreme_shapes.py
+dcbf_beamform against float64 references.    python tests/probes/extreme_shapes.py
 """
 import os, sys, numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from dpdk_dc_sand_b200 import _capi
 from oracle import beamform_oracle as orc
 TS = orc.SAMPLE_PERIOD

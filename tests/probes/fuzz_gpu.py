@@ -1,7 +1,7 @@
 """Randomised shape sweep of the C ABI against float64 references (developer aid; the committed parity tests are
 tests/test_gpu_parity.py).
 
-    python tools/fuzz_gpu.py [n_cases] [seed] [--many-channels]
+    python tests/probes/fuzz_gpu.py [n_cases] [seed] [--many-channels]
 
 Every case draws (B, A, C, T, M, flags) and checks: dcbf_fused against the oracle pipeline (2^-10 sum|x| budget; the
 observed error is printed), dcbf_reorder bit-exact, dcbf_beamform (tcgen05 or CUDA cores, whichever the shape takes)
@@ -13,7 +13,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from dpdk_dc_sand_b200 import _capi  # noqa: E402
 from oracle import beamform_oracle as orc  # noqa: E402
 
