@@ -271,18 +271,18 @@ def run_reference(args, wl) -> None:
 # --------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------
-def measure_secondary(name, steps, dev, rank, world, peak):
-    """Kernel-only figure of another BASELINE config on this GPU (inputs resident in HBM; `sets` input/output
-    sets are rotated so that consecutive launches never find their data in the 126 MB L2)."""
+def measure_share(A, C, T, M, B, n_total, xeng_id, steps, dev, peak, desc=None):
+    """Kernel-only figure of one (per-GPU share of a) configuration on this GPU: inputs resident in HBM, `sets`
+    input/output sets rotated so that consecutive launches never find their data in the 126 MB L2.  `C` channels of
+    a band of `n_total`, this GPU being X-engine `xeng_id` (reference: coeff_generator.py:53)."""
     import torch
 
     from dpdk_dc_sand_b200 import _capi
 
-    desc, A, C, T, M, B = WORKLOADS[name]
     alg = _capi.fused_bytes(B, A, C, T, M)
     sets = max(2, -(-(4 * 126_000_000) // alg))  # >= 4 x L2 in flight
     gen = torch.Generator(device=dev)
-    gen.manual_seed(77 + rank)
+    gen.manual_seed(77 + xeng_id)
     xs = [torch.randint(0, 256, (B, A, C, T, 2, 2), dtype=torch.uint8, device=dev, generator=gen) for _ in range(sets)]
     dvs = []
     for _ in range(sets):
@@ -293,25 +293,66 @@ def measure_secondary(name, steps, dev, rank, world, peak):
     outs = [torch.empty((B, 2, C, T // 16, 16, 2 * M), dtype=torch.float32, device=dev) for _ in range(sets)]
     stream = torch.cuda.Stream()
 
+    def enqueue(n, flags, st):
+        for i in range(n):
+            j = i % sets
+            _capi.fused(xs[j], dvs[j], outs[j], B, A, C, n_total, T, M, xeng_id, SAMPLE_PERIOD, flags, st)
+
     def run(n, flags):
+        """(device seconds per launch, host seconds spent issuing one launch) of n launches from the host."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record(stream)
-            for i in range(n):
-                j = i % sets
-                _capi.fused(xs[j], dvs[j], outs[j], B, A, C, C * world, T, M, rank, SAMPLE_PERIOD, flags, stream)
+            t0 = time.perf_counter()
+            enqueue(n, flags, stream)
+            t_host = (time.perf_counter() - t0) / n
             e1.record(stream)
         stream.synchronize()
+        return e0.elapsed_time(e1) / 1e3 / n, t_host
+
+    def run_graph(n, flags):
+        """Device seconds per launch of the same n launches captured once into a CUDA graph and replayed: what the
+        GPU needs when the host's per-launch cost (argument checks, two tensor-map encodes, the launch itself) is
+        off the critical path -- a launch of a small share is shorter than that cost."""
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            enqueue(n, flags, stream)
+        graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        del graph
         return e0.elapsed_time(e1) / 1e3 / n
 
     run(2 * sets, 0)
-    sec = run(steps, 0)
-    sec_stream = run(steps, _capi.FLAG_STREAMING)
+    sec, host_sec = run(steps, 0)
+    sec_stream, _ = run(steps, _capi.FLAG_STREAMING)
+    sec_graph = run_graph(steps, 0)
+    sec_graph_stream = run_graph(steps, _capi.FLAG_STREAMING)
     _capi.fused_status()
-    return {"workload": f"{name}: {desc}", "ms_per_step": sec * 1e3, "input_GBps": xs[0].numel() / sec / 1e9,
-            "beam_gsamples_per_s": B * 2 * C * T * M / sec / 1e9, "algorithmic_bytes_per_launch": alg,
-            "roofline_frac": alg / sec / 1e9 / peak, "streaming_ms_per_step": sec_stream * 1e3,
-            "streaming_roofline_frac": alg / sec_stream / 1e9 / peak, "l2": f"{sets} rotating input/output sets"}
+    out = {"ms_per_step": sec * 1e3, "input_GBps": xs[0].numel() / sec / 1e9,
+           "beam_gsamples_per_s": B * 2 * C * T * M / sec / 1e9, "algorithmic_bytes_per_launch": alg,
+           "roofline_frac": alg / sec / 1e9 / peak, "streaming_ms_per_step": sec_stream * 1e3,
+           "streaming_roofline_frac": alg / sec_stream / 1e9 / peak,
+           "host_us_per_launch": host_sec * 1e6,
+           "graph_ms_per_step": sec_graph * 1e3, "graph_roofline_frac": alg / sec_graph / 1e9 / peak,
+           "graph_streaming_ms_per_step": sec_graph_stream * 1e3,
+           "graph_streaming_roofline_frac": alg / sec_graph_stream / 1e9 / peak,
+           "l2": f"{sets} rotating input/output sets",
+           "geometry": {"n_ants": A, "n_chans_per_gpu": C, "n_chans_total": n_total, "n_samples": T, "n_beams": M,
+                        "n_batches": B, "xeng_id": xeng_id}}
+    if desc:
+        out = {"workload": desc, **out}
+    return out
+
+
+def measure_secondary(name, steps, dev, rank, world, peak):
+    """Kernel-only figure of another BASELINE config on this GPU (see measure_share)."""
+    desc, A, C, T, M, B = WORKLOADS[name]
+    return measure_share(A, C, T, M, B, C * world, rank, steps, dev, peak, desc=f"{name}: {desc}")
 
 
 def run_ours(args, wl) -> None:

@@ -112,6 +112,11 @@ struct FusedParams {
     int sb_count;    // coefficient sets per (channel, N tile): 1, or B with time-varying steering
     int ub;          // batches sharing one coefficient set: B, or 1 with time-varying steering
     int raw_stages;  // depth of the raw TMA ring: kRawStages + extra stages placed behind the B tiles
+    // whole-tile-set mode: the first n_whole channels are units of their own; each of the remaining C - n_whole
+    // channels is cut into `split` units along its list of tile_count accumulator tiles (N tile, batch, time tile), so
+    // that the last round of the persistent CTAs is a fraction of a channel instead of a whole one
+    int n_whole, split, tile_count;
+    int pdl_wait;    // 1: wait for the preceding kernel of the stream (griddepcontrol.wait) after the prologue
     int raw_extra_off;  // byte offset of the first extra stage inside each 64 KiB B buffer
     uint32_t inv_a;     // floor(2^32 / A) + 1: e / A == umulhi(e, inv_a) for every entry index of an N tile (A >= 2)
     float dt_hi[DCBF_MAX_TV_BATCHES], dt_lo[DCBF_MAX_TV_BATCHES];  // per-batch time offset (s) as a float pair
@@ -168,32 +173,43 @@ constexpr float kInvPiLo = static_cast<float>(kInvPi - static_cast<double>(kInvP
 // With kPair the delay and the phase are float pairs themselves (time-varying steering).
 // Delays beyond ~1e6 half-turns of phase (milliseconds; nothing physical) take the float64 path.
 template <bool kPair>
-__device__ __forceinline__ void steer_phase(float d_hi, float d_lo, float ph_hi, float ph_lo, float s_hi, float s_lo,
-                                            double scale, float* r, float* small) {
+__device__ __forceinline__ void steer_phase_f64(float d_hi, float d_lo, float ph_hi, float ph_lo, double scale, float* r,
+                                                float* small) {
+    const double dd = kPair ? static_cast<double>(d_hi) + static_cast<double>(d_lo) : static_cast<double>(d_hi);
+    const double pp = kPair ? static_cast<double>(ph_hi) + static_cast<double>(ph_lo) : static_cast<double>(ph_hi);
+    const double x = fma(dd, scale, pp * kInvPi);
+    const double xr = x - 2.0 * rint(0.5 * x);
+    *r = static_cast<float>(xr);
+    *small = static_cast<float>(xr - static_cast<double>(*r));
+}
+// The float-pair evaluation alone, branch-free; returns false when the operands are out of its range (the caller then
+// redoes the entry with steer_phase_f64).  Keeping the test out of the arithmetic lets a whole batch of entries be
+// scheduled as one straight-line region (their dependent FMA chains interleave).
+template <bool kPair>
+__device__ __forceinline__ bool steer_phase_fast(float d_hi, float d_lo, float ph_hi, float ph_lo, float s_hi, float s_lo,
+                                                 float* r, float* small) {
     const float p = d_hi * s_hi;
     const float u = ph_hi * kInvPiHi;
-    if (fabsf(p) < 1048576.0f && fabsf(u) < 1048576.0f) {
-        float e = fmaf(d_hi, s_hi, -p);       // exact residual of p
-        e = fmaf(d_hi, s_lo, e);
-        if (kPair) e = fmaf(d_lo, s_hi, e);
-        e += fmaf(ph_hi, kInvPiHi, -u);       // exact residual of u
-        e = fmaf(ph_hi, kInvPiLo, e);
-        if (kPair) e = fmaf(ph_lo, kInvPiHi, e);
-        const float qf = fmaf(p, 0.5f, 12582912.0f) - 12582912.0f;  // rint(p / 2)
-        const float r0 = fmaf(qf, -2.0f, p);                         // p mod 2 in [-1, 1], exact
-        const float s1 = r0 + u;
-        const float bb = s1 - r0;
-        const float err = (r0 - (s1 - bb)) + (u - bb);               // rounding error of s1 (two-sum)
-        *r = s1;
-        *small = e + err;
-    } else {
-        const double dd = kPair ? static_cast<double>(d_hi) + static_cast<double>(d_lo) : static_cast<double>(d_hi);
-        const double pp = kPair ? static_cast<double>(ph_hi) + static_cast<double>(ph_lo) : static_cast<double>(ph_hi);
-        const double x = fma(dd, scale, pp * kInvPi);
-        const double xr = x - 2.0 * rint(0.5 * x);
-        *r = static_cast<float>(xr);
-        *small = static_cast<float>(xr - static_cast<double>(*r));
-    }
+    float e = fmaf(d_hi, s_hi, -p);       // exact residual of p
+    e = fmaf(d_hi, s_lo, e);
+    if (kPair) e = fmaf(d_lo, s_hi, e);
+    e += fmaf(ph_hi, kInvPiHi, -u);       // exact residual of u
+    e = fmaf(ph_hi, kInvPiLo, e);
+    if (kPair) e = fmaf(ph_lo, kInvPiHi, e);
+    const float qf = fmaf(p, 0.5f, 12582912.0f) - 12582912.0f;  // rint(p / 2)
+    const float r0 = fmaf(qf, -2.0f, p);                         // p mod 2 in [-1, 1], exact
+    const float s1 = r0 + u;
+    const float bb = s1 - r0;
+    const float err = (r0 - (s1 - bb)) + (u - bb);               // rounding error of s1 (two-sum)
+    *r = s1;
+    *small = e + err;
+    return fabsf(p) < 1048576.0f && fabsf(u) < 1048576.0f;
+}
+template <bool kPair>
+__device__ __forceinline__ void steer_phase(float d_hi, float d_lo, float ph_hi, float ph_lo, float s_hi, float s_lo,
+                                            double scale, float* r, float* small) {
+    if (!steer_phase_fast<kPair>(d_hi, d_lo, ph_hi, ph_lo, s_hi, s_lo, r, small))
+        steer_phase_f64<kPair>(d_hi, d_lo, ph_hi, ph_lo, scale, r, small);
 }
 
 // base + rate * dt as a float pair (dt = dt_hi + dt_lo): the model value at a heap's timestamp
@@ -297,6 +313,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         }
         fence_proxy_async_smem();
     }
+    // Programmatic dependent launch, default mode: everything above overlapped the tail of the preceding kernel of
+    // the stream; from here on global memory is touched, so wait until that kernel has completed and flushed.
+    if (prm.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (kQ8 && warp == 0) {
         // q8: the per-beam gains ride on the coefficients as gain[m] / max|gain| (in [-1, 1], so the fp16 hi+lo split
         // keeps its precision); the epilogue then scales every column by the same max|gain| and clips at 127 / max|gain|
@@ -321,8 +340,21 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     // (a channel of many beams takes long enough that whole channels balance badly over the CTAs; two time tiles are
     // what the TMEM accumulators of one unit hold)
     const uint32_t per_chan = kStream ? static_cast<uint32_t>(prm.nt_count * prm.hg_count) : 1u;
-    const uint32_t n_units = static_cast<uint32_t>(C) * per_chan;
-    const int it_count = kStream ? 1 : prm.nt_count;  // N tiles iterated INSIDE one unit
+    const uint32_t n_units = kStream ? static_cast<uint32_t>(C) * per_chan
+                                     : static_cast<uint32_t>(prm.n_whole + (C - prm.n_whole) * prm.split);
+    // whole-tile-set mode: unit -> channel and the range [j0, j1) of its accumulator tiles; tile j is
+    // (N tile j / (B ht), batch (j / ht) % B, time tile j % ht), the order every role walks them in
+    auto unit_range = [&](uint32_t w, uint32_t* uc, int* j0, int* j1) {
+        if (w < static_cast<uint32_t>(prm.n_whole)) {
+            *uc = w, *j0 = 0, *j1 = prm.tile_count;
+        } else {
+            const uint32_t r_ = w - static_cast<uint32_t>(prm.n_whole), c_ = r_ / static_cast<uint32_t>(prm.split);
+            const int s_ = static_cast<int>(r_ - c_ * static_cast<uint32_t>(prm.split));
+            *uc = static_cast<uint32_t>(prm.n_whole) + c_;
+            *j0 = s_ * prm.tile_count / prm.split, *j1 = (s_ + 1) * prm.tile_count / prm.split;
+        }
+    };
+    const int bh_count = prm.ub * prm.ht_count;  // accumulator tiles per coefficient set
     // kStream: unit -> channel, N tile, first time tile and number of time tiles of the group
     auto unit_decode = [&](uint32_t w, uint32_t* uc, int* uit, int* uh0, int* uhn) {
         const uint32_t c_ = w / per_chan, r_ = w - c_ * per_chan;
@@ -344,29 +376,42 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         // =================================== TMA producer ===================================
         uint32_t rs = 0, ph = 0;
         bool ok = true;
-        // slab order inside a (channel, N tile, batch): time tile outer, antenna slab inner; kStream: slab outer
-        // (every B k-block is then used for both time tiles before it is released)
-        const int n_outer = kStream ? prm.slab_count : prm.ht_count;
-        for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
-            uint32_t uc = w;
-            int uit = 0, uh0 = 0, uhn = 0;
-            if (kStream) unit_decode(w, &uc, &uit, &uh0, &uhn);
-            const int n_inner = kStream ? uhn : prm.slab_count;
-            for (int it = 0; it < it_count && ok; ++it)
+        // one raw slab: [16 antennas][128 samples] of (batch b, channel c) -> next ring stage
+        auto load_slab = [&](int h, int c, int s, int b) {
+            if (!mbar_wait<kProf>(bar(kRawEmpty + rs), ph ^ 1u, ctl, prm.status, kRoleProducer, kRawEmpty + rs, ps + 0)) return false;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bar(kRawFull + rs), kRawStageBytes);
+                tma_load_4d(raw_addr(rs), &tm_in, bar(kRawFull + rs), h * kTileT, c, s * kSlabAnts, b);
+            }
+            __syncwarp();
+            if (++rs == raw_stages) rs = 0, ph ^= 1u;
+            return true;
+        };
+        if constexpr (kStream) {
+            // slab outer, time tile inner (every B k-block is then used for both time tiles before it is released)
+            for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
+                uint32_t uc;
+                int uit, uh0, uhn;
+                unit_decode(w, &uc, &uit, &uh0, &uhn);
                 for (int b = 0; b < B && ok; ++b)
-                    for (int o = 0; o < n_outer && ok; ++o)
-                        for (int i = 0; i < n_inner; ++i) {
-                            const int h = kStream ? uh0 + i : o, s = kStream ? o : i;
-                            const int c = static_cast<int>(uc);
-                            ok = mbar_wait<kProf>(bar(kRawEmpty + rs), ph ^ 1u, ctl, prm.status, kRoleProducer, kRawEmpty + rs, ps + 0);
-                            if (!ok) break;
-                            if (elect_one()) {
-                                mbar_arrive_expect_tx(bar(kRawFull + rs), kRawStageBytes);
-                                tma_load_4d(raw_addr(rs), &tm_in, bar(kRawFull + rs), h * kTileT, c, s * kSlabAnts, b);
-                            }
-                            __syncwarp();
-                            if (++rs == raw_stages) rs = 0, ph ^= 1u;
-                        }
+                    for (int s = 0; s < prm.slab_count && ok; ++s)
+                        for (int i = 0; i < uhn && ok; ++i) ok = load_slab(uh0 + i, static_cast<int>(uc), s, b);
+            }
+        } else {
+            // per accumulator tile (N tile, batch, time tile): its antenna slabs
+            for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
+                uint32_t uc;
+                int j0, j1;
+                unit_range(w, &uc, &j0, &j1);
+                int bh = j0 % (B * prm.ht_count), b = bh / prm.ht_count, h = bh - b * prm.ht_count;
+                for (int j = j0; j < j1 && ok; ++j) {
+                    for (int s = 0; s < prm.slab_count && ok; ++s) ok = load_slab(h, static_cast<int>(uc), s, b);
+                    if (++h == prm.ht_count) {
+                        h = 0;
+                        if (++b == B) b = 0;
+                    }
+                }
+            }
         }
     } else if (warp == kMmaWarp || warp == kMmaWarp2) {
         // =================================== MMA issuer ===================================
@@ -434,11 +479,15 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 }
             }
         } else
-        for (uint32_t k = 0; ok && sched_get(ctl, k) < n_units; ++k)
-            for (int isb = 0; isb < prm.nt_count * prm.sb_count && ok; ++isb, ++step) {  // (N tile, coefficient set)
+        for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
+            uint32_t uc;
+            int j0, j1;
+            unit_range(w, &uc, &j0, &j1);
+            for (int j = j0; j < j1 && ok; ++step) {  // one (N tile, coefficient set) and the unit's tiles that use it
+                const int jend = min(j1, (j / bh_count + 1) * bh_count);
                 const uint32_t bb = step % kBopBufs;
                 ok = mbar_wait<kProf>(bar(kBopFull + bb), (step / kBopBufs) & 1u, ctl, prm.status, kRoleMma, kBopFull + bb, ps + 0);
-                for (int bh = 0; bh < prm.ub * prm.ht_count && ok; ++bh, ++unit) {
+                for (; j < jend && ok; ++j, ++unit) {
                     const uint32_t ab = unit % kAccBufs;
                     ok = mbar_wait<kProf>(bar(kAccEmpty + ab), ((unit / kAccBufs) & 1u) ^ 1u, ctl, prm.status, kRoleMma, kAccEmpty + ab, ps + 1);
                     if (!ok) break;
@@ -481,6 +530,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 if (ok && elect_one()) umma_commit(bar(kBopEmpty + bb));
                 __syncwarp();
             }
+        }
     } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + 4) {
         // =================================== epilogue ===================================
         const int q = warp & 3;  // TMEM lane quarter this warp may read
@@ -654,11 +704,19 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     }
             }
         } else
-        for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < n_units; ++k)
-            for (int it = 0; it < prm.nt_count && ok; ++it) {
-                const int n0 = it * nt;
-                for (int b = 0; b < B && ok; ++b)
-                    for (int h = 0; h < prm.ht_count && ok; ++h, ++unit) {
+        for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
+            uint32_t c;
+            int j0, j1;
+            unit_range(w, &c, &j0, &j1);
+            int jit = j0 / (B * prm.ht_count), jb = (j0 - jit * B * prm.ht_count) / prm.ht_count, jh = j0 % prm.ht_count;
+            {
+                {
+                    for (int j = j0; j < j1 && ok; ++j, ++unit) {
+                        const int n0 = jit * nt, b = jb, h = jh;  // this tile; then step the (N tile, batch, time tile) counters
+                        if (++jh == prm.ht_count) {
+                            jh = 0;
+                            if (++jb == B) jb = 0, ++jit;
+                        }
                         const uint32_t ab = unit % kAccBufs;
                         ok = mbar_wait<kProf>(bar(kAccFull + ab), (unit / kAccBufs) & 1u, ctl, prm.status, kRoleEpilogue, kAccFull + ab, ps + 0);
                         if (!ok) break;
@@ -785,7 +843,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar(kAccEmpty + ab));
                     }
+                }
             }
+        }
         bulk_wait_group_all();  // (issuing lane) staging memory and the stores themselves are done before exit
         if (kQ8 && prm.saturated) {
             clipped = __reduce_add_sync(0xffffffffu, clipped);
@@ -802,14 +862,20 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         uint32_t slab = 0, rs = 0, rph = 0;
         bool ok = true;
         for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
-            int tiles = prm.ht_count;  // time tiles per (unit, N tile, batch)
+            int tiles;  // (batch, time tile) pairs of the unit, each with slab_count slabs
             if (kStream) {
                 uint32_t uc;
                 int uit, uh0;
                 unit_decode(w, &uc, &uit, &uh0, &tiles);
+                tiles *= B;
+            } else {
+                uint32_t uc;
+                int j0, j1;
+                unit_range(w, &uc, &j0, &j1);
+                tiles = j1 - j0;
             }
-            for (int it = 0; it < it_count && ok; ++it)
-                for (int bh = 0; bh < B * tiles && ok; ++bh)
+            {
+                for (int bh = 0; bh < tiles && ok; ++bh)
                     for (int s = 0; s < prm.slab_count; ++s, ++slab) {
                         const uint32_t as = slab % kAopStages;
                         ok = mbar_wait2<kProf>(bar(kRawFull + rs), rph, kRawFull + rs, bar(kAopEmpty + as),
@@ -848,6 +914,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         if (kProf && prof_lane)  // slot 2: (LDS + convert + STS) | (fence + arrive) << 32
                             ctl->wait_ns[kRoleConvert][2] += (tc1 - tc0) | ((global_ns() - tc1) << 32);
                     }
+            }
         }
     } else if (warp < kCoeffWarp0 + kCoeffWarps) {
         // =================================== steering coefficients ===================================
@@ -860,6 +927,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         // kTv (time-varying steering): one coefficient set per heap, all four delay_vals fields are used.
         using Dv = typename std::conditional<kTv, float4, float2>::type;
         constexpr int kBatch = kTv ? 4 : 8;
+        constexpr int kIlp = kTv ? 2 : 4;  // entries evaluated together (bounded by the 96-register cap)
         constexpr int kStride = kCoeffWarps * 32;
         const int ctid = threadIdx.x - kCoeffWarp0 * 32;
         const int mt = nt >> 1;  // beams per N tile
@@ -887,10 +955,14 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 id = kChanSentinel;
                 sch_end = true;
             } else if (sch_n > 0) {  // about one unit before the register loads get there
-                if (kStream)
+                if (kStream) {
                     warm_l2(id / static_cast<int>(per_chan), ((id % static_cast<int>(per_chan)) / prm.hg_count) * (nt >> 1));
-                else
-                    warm_l2(id, 0);
+                } else {
+                    uint32_t uc;
+                    int j0, j1;
+                    unit_range(static_cast<uint32_t>(id), &uc, &j0, &j1);
+                    warm_l2(static_cast<int>(uc), (j0 / bh_count / sb_count) * mt);
+                }
             }
             ctl->chan_ring[sch_n & 7] = id;
             __threadfence_block();
@@ -1048,73 +1120,107 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 }
             }
         } else {
-        // cursor of the batch whose loads are in flight: (channel sequence index, N tile, coefficient set, entry)
+        // cursor of the batch whose loads are in flight: (unit sequence index, coefficient set of the unit, entry)
         uint32_t nk = 0;
-        int nc = sched_get(ctl, 0), nit = 0, nsb = 0, ne0 = ctid;
-        int n_entries = nc < C ? min(mt, M) * A : 0;
-        const float4* n_src = prm.dv + static_cast<size_t>(nc < C ? nc : 0) * M * A;
+        int nw = sched_get(ctl, 0), n_ch = 0, nisb = 0, nisb_last = 0, ne0 = ctid;
+        int n_entries = 0;
+        const float4* n_src = prm.dv;
         Dv nxt[kBatch];  // static: (delay_s, phase_rad), the two rate fields are ignored like the reference does
+        auto cursor_unit = [&]() {  // the cursor's unit -> channel and its range of (N tile, coefficient set) steps
+            if (static_cast<uint32_t>(nw) < n_units) {
+                uint32_t uc;
+                int j0, j1;
+                unit_range(static_cast<uint32_t>(nw), &uc, &j0, &j1);
+                n_ch = static_cast<int>(uc), nisb = j0 / bh_count, nisb_last = (j1 - 1) / bh_count;
+            }
+        };
+        auto cursor_set = [&]() {  // delay_vals of the cursor's (channel, N tile)
+            const int m0 = (nisb / sb_count) * mt;
+            n_entries = min(mt, M - m0) * A;
+            n_src = prm.dv + (static_cast<size_t>(n_ch) * M + m0) * A;
+        };
+        cursor_unit();
+        if (static_cast<uint32_t>(nw) < n_units) cursor_set();
         auto issue_loads = [&]() {
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
                 const int e = ne0 + u * kStride;
                 float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (nc < C && e < n_entries) t4 = ldg_nc_f4(n_src + e);
+                if (e < n_entries) t4 = ldg_nc_f4(n_src + e);
                 if constexpr (kTv) nxt[u] = t4;
                 else nxt[u] = make_float2(t4.x, t4.z);
             }
         };
         auto advance_cursor = [&]() {
-            if (is_sched) {  // publish what has come back, ask for the entry after the cursor's next channel
+            if (is_sched) {  // publish what has come back, ask for the entry after the cursor's next unit
                 sch_flush();
                 if (sch_n <= static_cast<int>(nk) + 1) sch_request();
             }
-            if (nc >= C) return;
+            if (static_cast<uint32_t>(nw) >= n_units) return;
             ne0 += kStride * kBatch;
             if (ne0 - ctid < n_entries) return;
             ne0 = ctid;
-            if (++nsb < sb_count) return;  // same delay_vals again for the next heap's coefficient set (L2 hits)
-            nsb = 0;
-            if (++nit == prm.nt_count) {  // the next channel's first N tile
-                nit = 0;
-                ++nk;
-                if (is_sched && sch_n <= static_cast<int>(nk)) {  // not published yet: do it now (rare)
-                    sch_request();
-                    sch_flush();
-                }
-                __syncwarp();
-                nc = sched_get(ctl, nk);
+            if (nisb < nisb_last) {
+                // the unit's next step: the same delay_vals again for the next heap's coefficient set (L2 hits), or
+                // the next N tile (warmed when its predecessor was started; warm the one after it)
+                ++nisb;
+                cursor_set();
+                if (is_sched && nisb % sb_count == 0 && nisb + sb_count <= nisb_last) warm_l2(n_ch, (nisb / sb_count + 1) * mt);
+                return;
             }
-            if (nc < C) {
-                const int m0 = nit * mt;
-                n_entries = min(mt, M - m0) * A;
-                n_src = prm.dv + (static_cast<size_t>(nc) * M + m0) * A;
-                // the channel's first N tile was warmed when the channel was published; warm the next one
-                if (is_sched && nit + 1 < prm.nt_count) warm_l2(nc, (nit + 1) * mt);
+            ++nk;
+            if (is_sched && sch_n <= static_cast<int>(nk)) {  // not published yet: do it now (rare)
+                sch_request();
+                sch_flush();
+            }
+            __syncwarp();
+            nw = sched_get(ctl, nk);
+            n_entries = 0;
+            cursor_unit();
+            if (static_cast<uint32_t>(nw) < n_units) {
+                cursor_set();
+                if (is_sched && nisb + sb_count <= nisb_last) warm_l2(n_ch, (nisb / sb_count + 1) * mt);
             }
         };
         issue_loads();
 
         uint32_t step = 0;
         bool ok = true;
-        for (uint32_t k = 0, c; ok && (c = sched_get(ctl, k)) < n_units; ++k) {
+        for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
+            uint32_t c;
+            int j0, j1;
+            unit_range(w, &c, &j0, &j1);
             const double scale = (static_cast<double>(c) + prm.chan_centre) * prm.turns_per_delay;  // half-turns per second of delay
             const float s_hi = static_cast<float>(scale), s_lo = static_cast<float>(scale - static_cast<double>(s_hi));
             float dt_hi = 0.f, dt_lo = 0.f;
             const float* w_tile = nullptr;
             const float* g_tile = nullptr;
             const float q8_inv_gmax = kQ8 && ctl->q8_gmax > 0.f ? 1.0f / ctl->q8_gmax : 0.f;
-            // one (beam, antenna) entry -> four 32-bit words of the B tile at d0 (row 2m) and d1 (row 2m+1)
-            auto emit = [&](const Dv& dv, uint32_t d0, int e) {
-                float r, small, sn, cs;
+            const bool two_parts = parts > 1;
+            // reduced phase (r, small) of one entry, float pairs only; false: out of range, redo in float64
+            auto phase_fast = [&](const Dv& dv, float* r, float* small) {
                 if constexpr (kTv) {
                     float d_hi, d_lo, ph_hi, ph_lo;
                     advance_model(dv.x, dv.y, dt_hi, dt_lo, &d_hi, &d_lo);
                     advance_model(dv.z, dv.w, dt_hi, dt_lo, &ph_hi, &ph_lo);
-                    steer_phase<true>(d_hi, d_lo, ph_hi, ph_lo, s_hi, s_lo, scale, &r, &small);
+                    return steer_phase_fast<true>(d_hi, d_lo, ph_hi, ph_lo, s_hi, s_lo, r, small);
                 } else {
-                    steer_phase<false>(dv.x, 0.f, dv.y, 0.f, s_hi, s_lo, scale, &r, &small);
+                    return steer_phase_fast<false>(dv.x, 0.f, dv.y, 0.f, s_hi, s_lo, r, small);
                 }
+            };
+            auto phase_f64 = [&](const Dv& dv, float* r, float* small) {
+                if constexpr (kTv) {
+                    float d_hi, d_lo, ph_hi, ph_lo;
+                    advance_model(dv.x, dv.y, dt_hi, dt_lo, &d_hi, &d_lo);
+                    advance_model(dv.z, dv.w, dt_hi, dt_lo, &ph_hi, &ph_lo);
+                    steer_phase_f64<true>(d_hi, d_lo, ph_hi, ph_lo, scale, r, small);
+                } else {
+                    steer_phase_f64<false>(dv.x, 0.f, dv.y, 0.f, scale, r, small);
+                }
+            };
+            // reduced phase of one (beam, antenna) entry -> four 32-bit words of the B tile at d0 (row 2m) and d1 (row 2m+1)
+            auto finish = [&](float r, float small, uint32_t d0, int e) {
+                float sn, cs;
                 sincospi_reduced(r, small, &sn, &cs);
                 if (w_tile) {  // ?beam-weights: real weight of this (beam, antenna); the table is tiny and stays in L1/L2
                     const float w = __ldg(w_tile + e);
@@ -1134,7 +1240,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 const uint32_t d1 = (d0 + 128u) ^ 16u;  // row + 1: swizzle phase (row & 7) | 1
                 st_shared_u32(d0, hi ^ 0x80000000u);
                 st_shared_u32(d1, __byte_perm(hi, 0u, 0x1032u));
-                if (parts > 1) {
+                if (two_parts) {
                     st_shared_u32(d0 + part_bytes, lo ^ 0x80000000u);
                     st_shared_u32(d1 + part_bytes, __byte_perm(lo, 0u, 0x1032u));
                 }
@@ -1144,7 +1250,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 return buf + static_cast<uint32_t>(a >> 5) * bop_kb_bytes + static_cast<uint32_t>(row) * 128u +
                        (static_cast<uint32_t>(((al >> 2) ^ (row & 7)) << 4) | static_cast<uint32_t>((al & 3) << 2));
             };
-            for (int isb = 0; isb < prm.nt_count * sb_count && ok; ++isb, ++step) {
+            for (int isb = j0 / bh_count, isb_last = (j1 - 1) / bh_count; isb <= isb_last && ok; ++isb, ++step) {
                 const int it = isb / sb_count, sb = isb - it * sb_count;
                 if constexpr (kTv) {
                     dt_hi = prm.dt_hi[sb];
@@ -1161,9 +1267,17 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 uint32_t d_fast = b_addr(buf, ml_first, a_first);
                 const uint32_t d_step = static_cast<uint32_t>(dm) * 256u;  // dm beams = 2 dm rows of 128 B
                 for (int e0 = ctid; e0 - ctid < entries; e0 += kStride * kBatch) {  // e0 - ctid is warp-uniform
+                    const unsigned long long tl0 = kProf && prof_lane ? global_ns() : 0ull;
                     Dv v[kBatch];
 #pragma unroll
                     for (int u = 0; u < kBatch; ++u) v[u] = nxt[u];
+                    if (kProf && prof_lane) {  // developer probe: time spent waiting for this batch's delay_vals to land
+                        float sink = 0.f;
+#pragma unroll
+                        for (int u = 0; u < kBatch; ++u) sink += v[u].x;
+                        asm volatile("" ::"f"(sink));
+                        ctl->wait_ns[kRoleCoeff][1] += global_ns() - tl0;
+                    }
                     advance_cursor();
                     issue_loads();
                     if (!waited) {
@@ -1171,15 +1285,17 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         waited = true;
                         if (!ok) break;
                     }
+                    // kIlp entries at a time in straight-line passes, so that their dependent chains interleave: reduced
+                    // phases (float pairs; the rare out-of-range entry is redone in float64), then sin/cos, fp16 split, stores
+                    uint32_t d0[kBatch];
                     if (fast_addr) {
 #pragma unroll
-                        for (int u = 0; u < kBatch; ++u)
-                            if (e0 + u * kStride < entries) emit(v[u], d_fast + static_cast<uint32_t>(u) * d_step, e0 + u * kStride);
+                        for (int u = 0; u < kBatch; ++u) d0[u] = d_fast + static_cast<uint32_t>(u) * d_step;
                         d_fast += kBatch * d_step;
                     } else {
 #pragma unroll
                         for (int u = 0; u < kBatch; ++u) {
-                            if (e0 + u * kStride < entries) emit(v[u], b_addr(buf, ml, a), e0 + u * kStride);
+                            d0[u] = b_addr(buf, ml, a);
                             ml += dm;
                             a += da;
                             if (a >= A) {
@@ -1188,11 +1304,32 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                             }
                         }
                     }
+                    const bool whole = (e0 - ctid) + kStride * kBatch <= entries;  // batch inside the tile (uniform over the role)
+#pragma unroll
+                    for (int g = 0; g < kBatch; g += kIlp) {
+                        float ph_r[kIlp], ph_s[kIlp];
+                        bool in_range = true;
+#pragma unroll
+                        for (int u = 0; u < kIlp; ++u) in_range &= phase_fast(v[g + u], &ph_r[u], &ph_s[u]);
+                        if (!in_range) {
+#pragma unroll
+                            for (int u = 0; u < kIlp; ++u) phase_f64(v[g + u], &ph_r[u], &ph_s[u]);
+                        }
+                        if (whole) {
+#pragma unroll
+                            for (int u = 0; u < kIlp; ++u) finish(ph_r[u], ph_s[u], d0[g + u], e0 + (g + u) * kStride);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < kIlp; ++u)
+                                if (e0 + (g + u) * kStride < entries) finish(ph_r[u], ph_s[u], d0[g + u], e0 + (g + u) * kStride);
+                        }
+                    }
                 }
                 if (!ok) break;
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(kBopFull + bb));
+                if (kProf && prof_lane && step == 0) ctl->wait_ns[kRoleCoeff][2] = global_ns() - role_t0;  // first set done
             }
         }
         }
@@ -1419,7 +1556,23 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
         for (int i = 0; i < kNumKernels; ++i)
             DCBF_CUDA_TRY(cudaFuncSetAttribute(kKernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     }
-    const long long units = kstream ? static_cast<long long>(C) * p.nt_count * p.hg_count : C;
+    // Whole-tile-set mode: C channels over G persistent CTAs leave a last round of R = C mod G channels in which
+    // G - R CTAs idle for a whole channel time (C3 cut over 8 GPUs: 512 channels = 3.46 per CTA, i.e. 4 rounds).  The
+    // last R channels are therefore cut into `split` units each along their accumulator tiles (the coefficients of a
+    // cut channel are generated once per piece, which is why only the tail is cut).
+    p.tile_count = p.nt_count * B * p.ht_count;
+    p.n_whole = C;
+    p.split = 1;
+    if (!kstream && !(flags & DCBF_FLAG_DEBUG_WHOLE_CHANNELS)) {
+        const int rem = C % n_sms[dev];
+        const int cut = rem ? std::min(p.tile_count, n_sms[dev] / rem) : 1;
+        if (cut > 1) {
+            p.n_whole = C - rem;
+            p.split = cut;
+        }
+    }
+    const long long units = kstream ? static_cast<long long>(C) * p.nt_count * p.hg_count
+                                    : static_cast<long long>(p.n_whole) + static_cast<long long>(C - p.n_whole) * p.split;
     if (units > 0x7ffffff0LL) return DCBF_ERR_UNSUPPORTED;  // what the CTAs draw from the queue
     const int grid = units < n_sms[dev] ? static_cast<int>(units) : n_sms[dev];
     cudaLaunchConfig_t cfg{};
@@ -1431,7 +1584,12 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (flags & DCBF_FLAG_STREAMING) ? 1 : 0;
+    // Every launch may start while the preceding kernel of the stream drains (programmatic dependent launch).  By
+    // default the kernel then waits for that kernel's completion (griddepcontrol.wait) right after its prologue, before
+    // it touches global memory: launch latency, barrier / TMEM set-up and the zeroing of the B tiles are off the
+    // critical path, nothing else changes.  DCBF_FLAG_STREAMING drops the wait (the caller promises independence).
+    cfg.numAttrs = (flags & DCBF_FLAG_DEBUG_NO_PDL) ? 0 : 1;
+    p.pdl_wait = (flags & DCBF_FLAG_STREAMING) ? 0 : 1;
     // (int8 output, variant, merged) specialisation; variant: 0 plain, 1 profiling, 2 time-varying steering (the
     // profiler has no time-varying build)
     const int variant = batch_dt_s ? 2 : p.prof ? 1 : 0;

@@ -69,6 +69,8 @@ typedef enum dcbf_status {
 #define DCBF_FLAG_DEBUG_NO_KSTREAM 0x200u /* dcbf_fused: keep whole B tile sets even when several N tiles are needed (cross-check) */
 #define DCBF_FLAG_DEBUG_CUDA_CORES 0x400u /* dcbf_beamform: float32 CUDA-core kernel even where the tcgen05 one applies (cross-check) */
 #define DCBF_FLAG_DEBUG_DIRECT_EPILOGUE 0x100u /* dcbf_fused: st.global from registers instead of TMA stores (cross-check) */
+#define DCBF_FLAG_DEBUG_WHOLE_CHANNELS 0x800u /* dcbf_fused: never cut the channels of the last scheduling round into pieces (cross-check) */
+#define DCBF_FLAG_DEBUG_NO_PDL 0x1000u /* dcbf_fused: plain stream-ordered launch (no programmatic dependent launch attribute) */
 
 int dcbf_version(void);
 const char* dcbf_strerror(int status);

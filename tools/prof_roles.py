@@ -10,7 +10,7 @@ from dpdk_dc_sand_b200 import _capi  # noqa: E402
 
 ROLES = {1: "producer", 2: "mma", 3: "epilogue", 4: "convert", 5: "coeff"}
 SLOTS = {1: ["raw_empty", "-", "-"], 2: ["bop_full", "acc_empty", "aop_full"], 3: ["acc_full", "store_wait", "tmem|sts+fence"],
-         4: ["raw_full", "aop_empty", "work|fence"], 5: ["bop_empty", "-", "-"]}
+         4: ["raw_full", "aop_empty", "work|fence"], 5: ["bop_empty", "data_wait", "first_set@"]}
 
 
 def main():
@@ -62,7 +62,7 @@ def main():
     for r, name in ROLES.items():
         span = p[:, r, 3]
         parts = ", ".join(f"{SLOTS[r][k]}={p[:, r, k].mean():7.1f}" for k in range(3) if SLOTS[r][k] != "-")
-        busy = span - p[:, r, :3].sum(axis=1)
+        busy = span - (p[:, r, :2].sum(axis=1) if r == 5 else p[:, r, :3].sum(axis=1))
         print(f"  {name:9s} span {span.mean():7.1f} (max {span.max():7.1f})  busy {busy.mean():7.1f}  blocked: {parts}")
 
 
