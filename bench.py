@@ -65,6 +65,19 @@ def _traffic(workload: str):
     return None
 
 
+def _verbatim_cpu():
+    """The reference's own CPU functions timed once in the authoring container (tools/time_verbatim_reference.py): they
+    need /root/reference, which does not exist on the GPU box, so the figure is context beside the live port timing."""
+    path = os.path.join(ROOT, "profiles", "r02_cpu_verbatim_reference.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        d = json.load(fh)
+    return {"source": "profiles/r02_cpu_verbatim_reference.json (authoring container, not this run)", "cores": d["cores"],
+            "what": d["what"], "unit": UNIT,
+            "cases": [{"case": c["case"], "value": c["input_GBps"], "total_s": c["total_s"]} for c in d["cases"]]}
+
+
 def _ncu_kernel_us(workload: str):
     """gpu__time_duration of one launch in the committed ncu capture (cold, serialised: context only)."""
     path = os.path.join(ROOT, "profiles", "fused_traffic.json")
@@ -238,6 +251,16 @@ def cpu_port_rate(n_ants, n_beams, n_samples, n_chans_total, sample_chans, repea
     return x.nbytes / best / 1e9, int(cores), times
 
 
+def bench_config(workload, wl, world):
+    """The `config` object of the JSON line: the same keys and values in both arms (ours / --impl reference)."""
+    desc, A, C, T, M, B = wl
+    alg = B * A * C * T * 4 + C * M * A * 16 + B * 2 * C * T * M * 8
+    return {"workload": f"{workload}: {desc} per GPU", "n_ants": A, "n_chans_per_gpu": C, "n_chans_total": C * world,
+            "n_samples": T, "n_beams": M, "n_batches": B,
+            "parallelism": f"channel-sharded x{world} (rank == xeng_id), no collective",
+            "l2": f"working set {alg / 2**20:.0f} MiB per step > 126 MB L2 (inputs larger than L2)"}
+
+
 def run_reference(args, wl) -> None:
     desc, A, C, T, M, B = wl
     rank = int(os.environ.get("RANK", "0"))
@@ -255,8 +278,7 @@ def run_reference(args, wl) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(timed), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "sample": f"{sample} of {C} channels per step",
-                   "n_ants": A, "n_beams": M, "n_samples": T},
+        "config": bench_config(args.workload, wl, args.gpus), "sample": f"{sample} of {C} channels per step",
         "beam_gsamples_per_s": B * 2 * sample * T * M / sec / 1e9,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} of {C} channels ({in_bytes} input bytes) per step, numpy float32 "
@@ -327,10 +349,19 @@ def measure_share(A, C, T, M, B, n_total, xeng_id, steps, dev, peak, desc=None):
         del graph
         return e0.elapsed_time(e1) / 1e3 / n
 
+    # a short idle before every timed burst: after a few tenths of a second of back-to-back launches the board sits at
+    # its power cap (the `sustained` figure of the headline shows by how much), and these figures are compared with the
+    # burst copy peak like the headline is
     run(2 * sets, 0)
+    time.sleep(0.25)
+    run(sets, 0)
     sec, host_sec = run(steps, 0)
+    time.sleep(0.25)
+    run(sets, _capi.FLAG_STREAMING)
     sec_stream, _ = run(steps, _capi.FLAG_STREAMING)
+    time.sleep(0.25)
     sec_graph = run_graph(steps, 0)
+    time.sleep(0.25)
     sec_graph_stream = run_graph(steps, _capi.FLAG_STREAMING)
     _capi.fused_status()
     out = {"ms_per_step": sec * 1e3, "input_GBps": xs[0].numel() / sec / 1e9,
@@ -346,6 +377,71 @@ def measure_share(A, C, T, M, B, n_total, xeng_id, steps, dev, peak, desc=None):
                         "n_batches": B, "xeng_id": xeng_id}}
     if desc:
         out = {"workload": desc, **out}
+    return out
+
+
+# The fixed bands of BASELINE.json configs[2..4], cut by frequency channel over the GPUs of one box
+# (reference: coeff_generator.py:53 `ch = c + C * xeng_id`, prebeamform_reorder_test.py:72): (n_ants, n_chans of the
+# whole band, n_samples, n_beams, the GPU counts the configuration is quoted for)
+BANDS = {
+    "c3": ("MeerKAT 4k mode: 64 antennas x 4096 channels x 256 samples, 64 beams", 64, 4096, 256, 64, (1, 2, 4, 8)),
+    "c4": ("MeerKAT+ 32k mode: 80 antennas x 32768 channels x 256 samples, 32 beams", 80, 32768, 256, 32, (8,)),
+    "c5": ("SKA-Mid scale: 197 antennas x 4096 channels x 256 samples, 256 beams", 197, 4096, 256, 256, (8,)),
+}
+_MODES = ("ms_per_step", "streaming_ms_per_step", "graph_ms_per_step", "graph_streaming_ms_per_step")
+
+
+def strong_scaling(world, rank, dev, peak, steps, dist=None, emulate=(2, 4, 8)):
+    """STRONG scaling: a fixed band cut over `world` GPUs (n_chans_per_gpu = n_chans / world, xeng_id = rank), the
+    partitioning BASELINE.json configs[2..4] name.  Every rank times its own share (one heap and 8 heaps per launch;
+    default launches, DCBF_FLAG_STREAMING, and both replayed from a CUDA graph); the slowest rank's time is reported.
+    `efficiency_vs_n1` = t(whole band on one GPU) / (world * t(share)), the whole band being timed in the same run.
+    With one GPU the per-GPU shares of 2, 4 and 8 GPUs are timed on it instead (`emulated_shares`: the shards exchange
+    nothing, so a share's kernel time does not depend on the other GPUs)."""
+    import torch
+
+    def timed(A, C, T, M, B, n_total, xid):
+        r = measure_share(A, C, T, M, B, n_total, xid, steps, dev, peak)
+        if world > 1:  # slowest rank, every mode
+            t = torch.tensor([r[k] for k in _MODES], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            for k, v in zip(_MODES, t.tolist()):
+                r[k] = v
+        alg = r["algorithmic_bytes_per_launch"]
+        for k in _MODES:
+            r[k.replace("ms_per_step", "roofline_frac")] = alg / (r[k] / 1e3) / 1e9 / peak
+        r.pop("input_GBps", None)
+        r.pop("beam_gsamples_per_s", None)
+        return r
+
+    out = {"note": strong_scaling.__doc__.split("\n\n")[0].replace("\n    ", " "), "n_gpus": world, "bands": {}}
+    for name, (desc, A, C, T, M, quoted) in BANDS.items():
+        if world > 1 and world not in quoted:
+            continue
+        band = {"workload": desc}
+        for B in (1, 8):
+            if B == 8 and name != "c3" and world == 1:
+                continue  # the whole C4 / C5 band with 8 heaps does not need timing on one GPU
+            key = f"b{B}"
+            whole = timed(A, C, T, M, B, C, 0) if (name == "c3" or B == 1) else None
+            band[key] = {"whole_band_on_one_gpu": whole}
+            if world > 1:
+                share = timed(A, C // world, T, M, B, C, rank)
+                if whole is not None:
+                    for k in _MODES:
+                        share[k.replace("ms_per_step", "efficiency_vs_n1")] = whole[k] / (world * share[k])
+                band[key]["share"] = share
+            else:
+                band[key]["emulated_shares"] = {}
+                for n in emulate:
+                    if n not in quoted:
+                        continue
+                    share = timed(A, C // n, T, M, B, C, n - 1)
+                    if whole is not None:
+                        for k in _MODES:
+                            share[k.replace("ms_per_step", "efficiency_vs_n1")] = whole[k] / (n * share[k])
+                    band[key]["emulated_shares"][f"n{n}"] = share
+        out["bands"][name] = band
     return out
 
 
@@ -565,13 +661,32 @@ def run_ours(args, wl) -> None:
             t = torch.tensor([e2e_sec], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_sec = float(t.item())
-        plan.close()
         # the host-path result must be the device-path result (same kernel, chunked): cheap identity check
         same = bool(torch.equal(h_out[:, :, : min(C, 8)], beams[:, :, : min(C, 8)].cpu()))
+        # the same with the delay model resident on the device (it changes at control-plane cadence, not per heap):
+        # per-step H2D = the voltages alone
+        plan.set_delay_vals(n_dv)
+        plan.run(n_in, None, n_out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            plan.run(n_in, None, n_out)
+        torch.cuda.synchronize()
+        r_sec = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([r_sec], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            r_sec = float(t.item())
+        same_r = bool(torch.equal(h_out[:, :, : min(C, 8)], beams[:, :, : min(C, 8)].cpu()))
+        plan.close()
         e2e = {"value": world * in_bytes / e2e_sec / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(in_bytes + dv.numel() * 4), "d2h_bytes_per_step": int(beams.numel() * 4),
                "ms_per_step": e2e_sec * 1e3, "steps": e2e_steps, "api": "dcbf_host_plan_run (pinned host arrays)",
-               "matches_device_path": same}
+               "matches_device_path": same,
+               "resident_delay_model": {"value": world * in_bytes / r_sec / 1e9, "unit": UNIT, "ms_per_step": r_sec * 1e3,
+                                        "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(beams.numel() * 4),
+                                        "api": "dcbf_host_plan_set_delay_vals once, then dcbf_host_plan_run(samples, NULL, beams)",
+                                        "matches_device_path": same_r}}
         if q8 is not None:
             h_out8 = torch.empty(beams.shape, dtype=torch.int8, pin_memory=True)
             n_out8 = h_out8.numpy()
@@ -588,9 +703,23 @@ def run_ours(args, wl) -> None:
                 t = torch.tensor([q_e2e], dtype=torch.float64, device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 q_e2e = float(t.item())
+            plan.set_delay_vals(n_dv)
+            plan.run_q8(n_in, None, n_out8)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                plan.run_q8(n_in, None, n_out8)
+            q_res = (time.perf_counter() - t0) / e2e_steps
+            if world > 1:
+                t = torch.tensor([q_res], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                q_res = float(t.item())
             plan.close()
             q8["e2e"] = {"value": world * in_bytes / q_e2e / 1e9, "unit": UNIT, "ms_per_step": q_e2e * 1e3,
-                         "h2d_bytes_per_step": int(in_bytes + dv.numel() * 4), "d2h_bytes_per_step": int(beams.numel())}
+                         "h2d_bytes_per_step": int(in_bytes + dv.numel() * 4), "d2h_bytes_per_step": int(beams.numel()),
+                         "resident_delay_model": {"value": world * in_bytes / q_res / 1e9, "unit": UNIT,
+                                                  "ms_per_step": q_res * 1e3, "h2d_bytes_per_step": int(in_bytes),
+                                                  "d2h_bytes_per_step": int(beams.numel())}}
             del h_out8
         del h_in, h_dv, h_out
 
@@ -630,15 +759,21 @@ def run_ours(args, wl) -> None:
                   "checksum_ok": bool(ok), "api": "sharding.gather_beams (torch.distributed gather, nccl)",
                   "note": "optional; not part of value / e2e"}
 
+    peak, peak_src = _peaks()
+    strong = None
+    if not args.no_strong and args.workload == "c3":
+        del samples, dv, beams
+        torch.cuda.empty_cache()
+        strong = strong_scaling(world, rank, dev, peak, max(args.steps, 30), dist if world > 1 else None)
+        samples = dv = beams = None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = _peaks()
     secondary = None
     if world == 1 and not args.no_secondary and args.workload == "c3":
-        del samples, dv, beams
         torch.cuda.empty_cache()
         secondary = {"c2": measure_secondary("c2", max(args.steps, 40), dev, rank, world, peak),
                      "c2_b8": measure_secondary("c2_b8", max(args.steps, 20), dev, rank, world, peak)}
@@ -647,10 +782,15 @@ def run_ours(args, wl) -> None:
     if q8 is not None:
         q8["roofline_frac"] = q8["algorithmic_GBps_per_gpu"] / peak
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": _traffic(args.workload), "kernel": "fused_beamform_kernel",
+                "traffic": _traffic(args.workload),
+                "traffic_source": "committed ncu capture (profiles/fused_traffic.json), not measured in this run",
+                "kernel": "fused_beamform_kernel",
+                "frac_sustained": (alg_bytes / (sustained["ms_per_step"] / 1e3) / 1e9 / peak) if sustained else None,
+                "sustained": sustained,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_us_mean": mean_launch_s * 1e6,
                 "launch_us_min": min(per_launch_ms) * 1e3, "launch_us_with_event_between_launches": statistics.mean(per_launch_ms) * 1e3,
-                "kernel_us_under_ncu": _ncu_kernel_us(args.workload), "peak_source": peak_src,
+                "kernel_us_under_ncu": _ncu_kernel_us(args.workload), "kernel_us_under_ncu_source": "committed ncu capture",
+                "peak_source": peak_src,
                 "tensor_tflops_real_expanded": B * 2 * C * T * 8 * A * M / mean_launch_s / 1e12}
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -666,16 +806,14 @@ def run_ours(args, wl) -> None:
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16",  # tcgen05 kind::f16 operands (u8 voltages exact, coefficients fp16 hi+lo pairs), f32 accumulate
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc} per GPU", "n_ants": A, "n_chans_per_gpu": C,
-                   "n_chans_total": n_total, "n_samples": T, "n_beams": M, "n_batches": B,
-                   "parallelism": f"channel-sharded x{world} (rank == xeng_id), no collective",
-                   "l2": f"working set {alg_bytes / 2**20:.0f} MiB per step > 126 MB L2 (inputs larger than L2)",
-                   "arithmetic": "u8 voltages exact in f16; coefficients as f16 " + ("single rounding" if args.fp16_coeff else "hi+lo pair (~2^-24)") + "; f32 accumulate in TMEM; f32 beams",
-                   "tiling": dict(zip(("kb_count", "nt", "nt_count"), _capi.fused_tiling(A, M, flags)))},
+        "config": bench_config(args.workload, wl, world),
+        "arithmetic": "u8 voltages exact in f16; coefficients as f16 " + ("single rounding" if args.fp16_coeff else "hi+lo pair (~2^-24)") + "; f32 accumulate in TMEM; f32 beams",
+        "tiling": dict(zip(("kb_count", "nt", "nt_count"), _capi.fused_tiling(A, M, flags))),
         "beam_gsamples_per_s": world * B * 2 * C * T * M / sec_per_step / 1e9,
         "algorithmic_GBps": world * alg_bytes / sec_per_step / 1e9,
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_verbatim": _verbatim_cpu(), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "sustained": sustained, "streaming": streaming, "q8_output": q8, "other_workloads": secondary, "gather": gather,
+        "strong_scaling": strong,
         "pcie": {"note": "e2e is bounded by the host link: pinned copies measured on this pool (tools/bench_standalone.py) "
                          "reach 55.5 GB/s H2D, 57.3 GB/s D2H alone and 49.9 GB/s each way when both directions run "
                          "at once; the e2e step moves h2d_bytes_per_step up and d2h_bytes_per_step down",
@@ -703,6 +841,7 @@ def main() -> None:
     ap.add_argument("--no-sustained", action="store_true", help="skip the power-capped sustained-load measurement")
     ap.add_argument("--no-q8", action="store_true", help="skip the int8-output extension measurement")
     ap.add_argument("--no-secondary", action="store_true", help="skip the extra c2 (BASELINE configs[1]) measurement")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (fixed bands cut over the GPUs)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: leave the rank's CPU affinity alone")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: skip timing the optional beam-output gather to rank 0")

@@ -52,12 +52,14 @@ SIGNATURES = {
                                 C.c_void_p]),
     "dcbf_fused_q8_bytes": (C.c_ulonglong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dcbf_fused_status": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dcbf_fused_status_poll": (C.c_int, []),
     "dcbf_debug_set_profile_buffer": (None, [C.c_void_p]),
     "dcbf_fused_tiling": (None, [C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                  C.POINTER(C.c_int)]),
     "dcbf_host_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_double, C.c_uint, C.c_int, C.c_int]),
     "dcbf_host_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcbf_host_plan_set_delay_vals": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dcbf_host_plan_set_gains": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dcbf_host_plan_run_q8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_ulonglong)]),
     "dcbf_host_plan_destroy": (C.c_int, [C.c_void_p]),
@@ -243,6 +245,12 @@ def fused_status() -> None:
     check(st, "dcbf_fused_status")
 
 
+def fused_status_poll() -> None:
+    """Cheap form for work the caller has already synchronised with (no CUDA call unless a kernel raised its flag)."""
+    if _lib is not None and _lib.dcbf_fused_status_poll() != OK:
+        fused_status()
+
+
 def fused_tiling(n_ants, n_beams, flags=0):
     kb, nt, ntc = C.c_int(0), C.c_int(0), C.c_int(0)
     load().dcbf_fused_tiling(n_ants, n_beams, flags, C.byref(kb), C.byref(nt), C.byref(ntc))
@@ -270,16 +278,33 @@ class HostPlan:
                                            n_beams, xeng_id, float(sample_period), flags, chunk_chans, n_slots),
               "dcbf_host_plan_create")
 
-    def run(self, samples, delay_vals, beams) -> None:
-        """numpy arrays (C-contiguous; pinned for overlap) with the reference shapes; blocks until done."""
+    @staticmethod
+    def _check_arrays(triples) -> None:
         import numpy as np
 
-        for arr, shape, dt in ((samples, self.shape_in, np.uint8), (delay_vals, self.shape_dv, np.float32),
-                               (beams, self.shape_out, np.float32)):
+        for arr, shape, dt in triples:
+            if arr is None:
+                continue
             if tuple(arr.shape) != shape or arr.dtype != dt or not arr.flags["C_CONTIGUOUS"]:
                 raise ValueError(f"expected C-contiguous {np.dtype(dt).name} array of shape {shape}, got "
                                  f"{arr.dtype} {arr.shape}")
-        check(load().dcbf_host_plan_run(self._h, samples.ctypes.data, delay_vals.ctypes.data, beams.ctypes.data),
+
+    def set_delay_vals(self, delay_vals) -> None:
+        """Upload the delay model once; ``run(samples, None, beams)`` then moves only the voltages per step."""
+        import numpy as np
+
+        self._check_arrays([(delay_vals, self.shape_dv, np.float32)])
+        check(load().dcbf_host_plan_set_delay_vals(self._h, delay_vals.ctypes.data), "dcbf_host_plan_set_delay_vals")
+
+    def run(self, samples, delay_vals, beams) -> None:
+        """numpy arrays (C-contiguous; pinned for overlap) with the reference shapes; blocks until done.
+        ``delay_vals=None``: the resident delay model of ``set_delay_vals``."""
+        import numpy as np
+
+        self._check_arrays([(samples, self.shape_in, np.uint8), (delay_vals, self.shape_dv, np.float32),
+                            (beams, self.shape_out, np.float32)])
+        check(load().dcbf_host_plan_run(self._h, samples.ctypes.data,
+                                        delay_vals.ctypes.data if delay_vals is not None else None, beams.ctypes.data),
               "dcbf_host_plan_run")
 
     def set_gains(self, gains) -> None:
@@ -295,14 +320,12 @@ class HostPlan:
         """Like ``run`` with int8 requantised beams; returns the number of clipped values."""
         import numpy as np
 
-        for arr, shape, dt in ((samples, self.shape_in, np.uint8), (delay_vals, self.shape_dv, np.float32),
-                               (beams_q8, self.shape_out, np.int8)):
-            if tuple(arr.shape) != shape or arr.dtype != dt or not arr.flags["C_CONTIGUOUS"]:
-                raise ValueError(f"expected C-contiguous {np.dtype(dt).name} array of shape {shape}, got "
-                                 f"{arr.dtype} {arr.shape}")
+        self._check_arrays([(samples, self.shape_in, np.uint8), (delay_vals, self.shape_dv, np.float32),
+                            (beams_q8, self.shape_out, np.int8)])
         sat = C.c_ulonglong(0)
-        check(load().dcbf_host_plan_run_q8(self._h, samples.ctypes.data, delay_vals.ctypes.data, beams_q8.ctypes.data,
-                                           C.byref(sat)), "dcbf_host_plan_run_q8")
+        check(load().dcbf_host_plan_run_q8(self._h, samples.ctypes.data,
+                                           delay_vals.ctypes.data if delay_vals is not None else None,
+                                           beams_q8.ctypes.data, C.byref(sat)), "dcbf_host_plan_run_q8")
         return int(sat.value)
 
     def close(self) -> None:

@@ -192,6 +192,8 @@ int dcbf_fused_status(int* role, int* barrier, int* block) {
     return fused_status(role, barrier, block);
 }
 
+int dcbf_fused_status_poll(void) { return fused_status_poll(); }
+
 void dcbf_debug_set_profile_buffer(unsigned long long* dev_ptr) { fused_set_profile_buffer(dev_ptr); }
 
 void dcbf_fused_tiling(int A, int M, unsigned flags, int* kb_count, int* nt, int* nt_count) {

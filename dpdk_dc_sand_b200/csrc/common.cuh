@@ -53,6 +53,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
                  int M, long long first_chan, double sample_period, const double* batch_dt_s, unsigned flags,
                  cudaStream_t s, const QuantisedOut* q8 = nullptr, const float* beam_weights = nullptr);
 int fused_status(int* role, int* barrier, int* block);
+int fused_status_poll();
 void fused_set_profile_buffer(unsigned long long* dev_ptr);
 void fused_tiling(int A, int M, unsigned flags, int* kb_count, int* nt, int* nt_count);
 

@@ -41,6 +41,7 @@
 #include <cuda.h>
 
 #include <atomic>
+#include <mutex>
 #include <type_traits>
 #include <cuda_fp16.h>
 
@@ -51,17 +52,45 @@ namespace dcbf {
 
 namespace {
 
-// Warp roles.  The SM sub-partition arbiter favours the highest warp id, so ids are handed out in the order
-// of urgency: the MMA issuer and the TMA producer (a few instructions each, everything else waits on them)
-// on top, then the epilogue (drains TMEM into the dominant HBM stream), convert, and the coefficient warps
-// (longest job, but needed a whole channel later) at the bottom.
-constexpr int kCoeffWarp0 = 0, kCoeffWarps = 8;  // warps 0..7
-constexpr int kConvertWarp0 = 8;                 // warps 8..11
-constexpr int kEpilogueWarp0 = 12;               // warps 12..15 (warp % 4 = TMEM lane quarter)
-constexpr int kProducerWarp = 16;
-constexpr int kMmaWarp = 17;     // issues the pol-0 MMAs (and owns the TMEM allocation)
-constexpr int kMmaWarp2 = 18;    // issues the pol-1 MMAs: the issue path, not the tensor pipe, limits narrow tiles
-constexpr int kThreads = 19 * 32;
+// Warp roles, one or more whole warpgroups (4 warps) each so that every role can resize its register allocation
+// with setmaxnreg: the kernel is launched with 72 registers per thread (28 warps), the producer / MMA group and
+// convert drop to what they need, and the epilogue grows from what they released.
+// The SM sub-partition arbiter favours the highest warp id, so ids are handed out in the order of urgency: the MMA
+// issuers and the TMA producer (a few instructions each, everything else waits on them) on top, then the epilogue
+// (drains TMEM into the dominant HBM stream), convert, and the coefficient warps (longest job, but needed a whole
+// unit later) at the bottom.  Sixteen coefficient warps: every one of them is stalled ~85 % of its cycles (loads,
+// dependent FMA chains, shared-memory stores -- ncu), so the role's rate scales with its warp count, and it is the
+// role that bounds short launches (first B tile set) and many antennas x beams.
+#ifndef DCBF_COEFF_WARPS
+#define DCBF_COEFF_WARPS 16
+#endif
+constexpr int kCoeffWarp0 = 0, kCoeffWarps = DCBF_COEFF_WARPS;  // warps 0..15
+constexpr int kConvertWarp0 = kCoeffWarps;                       // warps 16..19
+constexpr int kEpilogueWarp0 = kCoeffWarps + 4;                  // warps 20..23 (warp % 4 = TMEM lane quarter)
+constexpr int kProducerWarp = kCoeffWarps + 8;
+constexpr int kMmaWarp = kCoeffWarps + 9;     // issues the pol-0 MMAs (and owns the TMEM allocation)
+constexpr int kMmaWarp2 = kCoeffWarps + 10;   // issues the pol-1 MMAs: the issue path, not the tensor pipe, limits narrow tiles
+constexpr int kThreads = (kCoeffWarps + 12) * 32;  // the last warp only keeps the last warpgroup whole
+// registers per thread at launch (the __launch_bounds__ cap) and per role after setmaxnreg; the roles' sum must fit the
+// CTA's pool of kThreads * kRegsLaunch
+#if DCBF_COEFF_WARPS == 16
+#define DCBF_REGS_LAUNCH 72
+#define DCBF_REGS_COEFF 72
+#define DCBF_REGS_CONVERT 56
+#define DCBF_REGS_EPILOGUE 104
+#define DCBF_REGS_ISSUE 56
+#else
+#define DCBF_REGS_LAUNCH 96
+#define DCBF_REGS_COEFF 96
+#define DCBF_REGS_CONVERT 72
+#define DCBF_REGS_EPILOGUE 144
+#define DCBF_REGS_ISSUE 72
+#endif
+static_assert(kCoeffWarps % 4 == 0 && kThreads * DCBF_REGS_LAUNCH <= 65536, "launch register file");
+static_assert(kCoeffWarps * DCBF_REGS_COEFF + 4 * (DCBF_REGS_CONVERT + DCBF_REGS_EPILOGUE + DCBF_REGS_ISSUE) <= (kCoeffWarps + 12) * DCBF_REGS_LAUNCH,
+              "register pool of the CTA");
+#define DCBF_STR2(x) #x
+#define DCBF_STR(x) DCBF_STR2(x)
 constexpr int kTileT = 128;    // samples per MMA tile (UMMA M)
 constexpr int kSlabAnts = 16;  // antennas per raw slab / A stage
 constexpr int kKbAnts = 32;    // antennas per B k-block (128-byte swizzle row of fp16)
@@ -89,6 +118,7 @@ enum Role { kRoleProducer = 1, kRoleMma = 2, kRoleEpilogue = 3, kRoleConvert = 4
 
 struct FusedParams {
     const float4* dv;
+    const uint8_t* samples;         // (the kernel reads them through tm_in; only the early L2 prefetch uses the pointer)
     float* out;
     int8_t* out_q8;                 // non-null: requantised int8 beams instead of float32 (dcbf_fused_q8)
     const float* gains;             // [M] per-beam quantisation gain (q8 only)
@@ -116,6 +146,7 @@ struct FusedParams {
     // channels is cut into `split` units along its list of tile_count accumulator tiles (N tile, batch, time tile), so
     // that the last round of the persistent CTAs is a fraction of a channel instead of a whole one
     int n_whole, split, tile_count;
+    int dbg;         // developer experiments: 1 = no delay_vals loads, 2 = no phase / sin-cos arithmetic, 4 = no output stores
     int pdl_wait;    // 1: wait for the preceding kernel of the stream (griddepcontrol.wait) after the prologue
     int raw_extra_off;  // byte offset of the first extra stage inside each 64 KiB B buffer
     uint32_t inv_a;     // floor(2^32 / A) + 1: e / A == umulhi(e, inv_a) for every entry index of an N tile (A >= 2)
@@ -313,8 +344,44 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         }
         fence_proxy_async_smem();
     }
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
+    if (warp == kProducerWarp && lane == 0) prefetch_tensormap(&tm_in);
+    if (warp == kEpilogueWarp0 && lane == 0) prefetch_tensormap(&tm_out);
+    if (warp == kCoeffWarp0 + 1 && prm.pdl_wait && !(prm.dbg & 8)) {
+        // The first unit's inputs -> L2 before anything else asks for memory (and, with programmatic dependent launch,
+        // while the preceding kernel still drains: a prefetch returns no data, and L2 is the coherence point of global
+        // memory, so this is safe ahead of the dependency wait).  The launch is otherwise serial until the first B tile
+        // set is complete, and that set waits for these delay_vals at DRAM latency under the previous launch's write-back.
+        const uint32_t w = blockIdx.x;
+        uint32_t uc;
+        int m0 = 0, b0 = 0, h0, hn = 1;
+        if (kStream) {
+            const uint32_t pc = static_cast<uint32_t>(prm.nt_count * prm.hg_count);
+            uc = w / pc;
+            const int r_ = static_cast<int>(w - uc * pc), it_ = r_ / prm.hg_count;
+            m0 = it_ * (prm.nt >> 1), h0 = 2 * (r_ - it_ * prm.hg_count), hn = min(2, prm.ht_count - h0);
+        } else {
+            int j0 = 0;
+            uc = w;
+            if (w >= static_cast<uint32_t>(prm.n_whole)) {
+                const uint32_t r_ = w - static_cast<uint32_t>(prm.n_whole), c_ = r_ / static_cast<uint32_t>(prm.split);
+                uc = static_cast<uint32_t>(prm.n_whole) + c_;
+                j0 = static_cast<int>(r_ - c_ * static_cast<uint32_t>(prm.split)) * prm.tile_count / prm.split;
+            }
+            const int bh = prm.B * prm.ht_count;
+            m0 = (j0 / bh) * (prm.nt >> 1), b0 = (j0 % bh) / prm.ht_count, h0 = j0 % prm.ht_count;
+        }
+        const size_t dv_bytes = static_cast<size_t>(min(prm.nt >> 1, prm.M - m0)) * prm.A * 16;
+        const char* dv_p = reinterpret_cast<const char*>(prm.dv + (static_cast<size_t>(uc) * prm.M + m0) * prm.A);
+        for (size_t o = static_cast<size_t>(lane) * 8192; o < dv_bytes; o += 32 * 8192)
+            bulk_prefetch_l2(dv_p + o, static_cast<uint32_t>(min(dv_bytes - o, static_cast<size_t>(8192))));
+        const uint32_t row_bytes = static_cast<uint32_t>(min(hn * kTileT, prm.T - h0 * kTileT)) * 4u;
+        for (int a = lane; a < prm.A; a += 32)
+            bulk_prefetch_l2(prm.samples + ((static_cast<size_t>(b0) * prm.A + a) * prm.C + uc) * prm.T * 4 + static_cast<size_t>(h0) * kTileT * 4,
+                             row_bytes);
+    }
     // Programmatic dependent launch, default mode: everything above overlapped the tail of the preceding kernel of
-    // the stream; from here on global memory is touched, so wait until that kernel has completed and flushed.
+    // the stream; from here on global memory is read and written, so wait until that kernel has completed and flushed.
     if (prm.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (kQ8 && warp == 0) {
         // q8: the per-beam gains ride on the coefficients as gain[m] / max|gain| (in [-1, 1], so the fp16 hi+lo split
@@ -325,9 +392,6 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         for (int o = 16; o; o >>= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, o));
         if (lane == 0) ctl->q8_gmax = g;
     }
-    if (warp == kMmaWarp) tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
-    if (warp == kProducerWarp && lane == 0) prefetch_tensormap(&tm_in);
-    if (warp == kEpilogueWarp0 && lane == 0) prefetch_tensormap(&tm_out);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -372,6 +436,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     const unsigned long long role_t0 = prof_lane ? global_ns() : 0ull;
     const unsigned long long role_t0_cta = (kProf && threadIdx.x < 24) ? global_ns() : 0ull;
 
+    if (warp >= kProducerWarp) asm volatile("setmaxnreg.dec.sync.aligned.u32 " DCBF_STR(DCBF_REGS_ISSUE) ";");
     if (warp == kProducerWarp) {
         // =================================== TMA producer ===================================
         uint32_t rs = 0, ph = 0;
@@ -533,6 +598,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         }
     } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + 4) {
         // =================================== epilogue ===================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " DCBF_STR(DCBF_REGS_EPILOGUE) ";");
         const int q = warp & 3;  // TMEM lane quarter this warp may read
         const uint32_t ost = ost_base + static_cast<uint32_t>(q) * (2 * kOutBoxBytes);
         const float q8_gain = kQ8 ? ctl->q8_gmax : 0.f, q8_limit = q8_gain > 0.f ? 127.0f / q8_gain : 0.f;
@@ -581,7 +647,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         ctl->wait_ns[kRoleEpilogue][2] += (tp2 - tp1) | ((global_ns() - tp2) << 32);
                     }
                     if (elect_one()) {
-                        tma_store_3d(&tm_out, sb, n0 + cb, row0, plane);
+                        if (!(prm.dbg & 4)) tma_store_3d(&tm_out, sb, n0 + cb, row0, plane);
                         bulk_commit_group();
                     }
                 }
@@ -853,6 +919,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         }
     } else if (warp >= kConvertWarp0 && warp < kConvertWarp0 + 4) {
         // =================================== convert ===================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " DCBF_STR(DCBF_REGS_CONVERT) ";");
         // thread = one sample row t; per 4-antenna chunk: 4 conflict-free LDS.32, 8 PRMT + 8 HSUB2, 2 STS.128
         // (quarter-warps write 8 distinct 16-byte chunks of the 64B-swizzled rows: conflict-free)
         const int t = threadIdx.x - kConvertWarp0 * 32;
@@ -918,6 +985,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         }
     } else if (warp < kCoeffWarp0 + kCoeffWarps) {
         // =================================== steering coefficients ===================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " DCBF_STR(DCBF_REGS_COEFF) ";");
         // delay_vals[c][m0 .. m0+mt) is one contiguous run of (beam, antenna) entries: the 256 threads walk it
         // with lane <-> consecutive entry, so every warp load is 512 contiguous bytes.  Each entry becomes four
         // 32-bit words (row 2m | row 2m+1) x (fp16 hi | fp16 lo residual); consecutive antennas are consecutive
@@ -926,8 +994,11 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         // evaluated, so HBM latency is covered by arithmetic rather than exposed once per batch.
         // kTv (time-varying steering): one coefficient set per heap, all four delay_vals fields are used.
         using Dv = typename std::conditional<kTv, float4, float2>::type;
-        constexpr int kBatch = kTv ? 4 : 8;
-        constexpr int kIlp = kTv ? 2 : 4;  // entries evaluated together (bounded by the 96-register cap)
+#ifndef DCBF_COEFF_BATCH
+#define DCBF_COEFF_BATCH 4
+#endif
+        constexpr int kBatch = kTv ? 4 : DCBF_COEFF_BATCH;
+        constexpr int kIlp = kTv ? 2 : 4;  // entries evaluated together (bounded by the 72 registers of this role)
         constexpr int kStride = kCoeffWarps * 32;
         const int ctid = threadIdx.x - kCoeffWarp0 * 32;
         const int mt = nt >> 1;  // beams per N tile
@@ -989,9 +1060,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         if constexpr (kStream) {
             // K-streamed B tiles: one step = one 32-antenna k-block of one (channel, N tile, batch) unit, written to
             // ring slot step % 4.  lane <-> antenna of the k-block (a 512-byte run of delay_vals per beam), warp w
-            // takes beams w, w + 8, ...: 8 beams per warp and step.  Coefficients are regenerated per batch in
+            // takes beams w, w + 16, ...: 4 beams per warp and step.  Coefficients are regenerated per batch in
             // this mode (the ring does not keep them).
-            constexpr int kPer = 8;
+            constexpr int kPer = 64 / kCoeffWarps;
             const float ks_inv_gmax = kQ8 && ctl->q8_gmax > 0.f ? 1.0f / ctl->q8_gmax : 0.f;
             const int wl = warp - kCoeffWarp0;
             const int mt = nt >> 1;
@@ -1016,7 +1087,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 for (int u = 0; u < kPer; ++u) {
                     const int m = wl + kCoeffWarps * u;
                     float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (m < n_mte && a < A) t4 = ldg_nc_f4(n_src + static_cast<size_t>(m) * A + a);
+                    if (m < n_mte && a < A && !(prm.dbg & 1)) t4 = ldg_nc_f4(n_src + static_cast<size_t>(m) * A + a);
                     if constexpr (kTv) nxt[u] = t4;
                     else nxt[u] = make_float2(t4.x, t4.z);
                 }
@@ -1068,8 +1139,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         ok = mbar_wait<kProf>(bar(kBopEmpty + slot), ((kstep / kBopSlots) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + slot, ps + 0);
                         if (!ok) break;
                         const int a = kKbAnts * kb + lane;
-                        // beam m = wl + 8 u: row 2 m has the same swizzle phase for every u, so the four words of
-                        // entry u sit at a constant 2048-byte stride from those of entry 0
+                        // beam m = wl + 16 u: row 2 m has the same swizzle phase for every u, so the four words of
+                        // entry u sit at a constant 4096-byte stride from those of entry 0
                         const uint32_t row0 = 2u * static_cast<uint32_t>(wl);
                         const uint32_t d_base = bop_base + slot * kBopSlotBytes + row0 * 128u +
                                                 (((static_cast<uint32_t>(lane) >> 2) ^ (row0 & 7u)) << 4) +
@@ -1080,6 +1151,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                 const int m = wl + kCoeffWarps * u;
                                 if (m < mte) {
                                     float r, small, sn, cs;
+                                    if (prm.dbg & 2) {
+                                        sn = v[u].x, cs = v[u].y;
+                                    } else {
                                     if constexpr (kTv) {
                                         float d_hi, d_lo, ph_hi, ph_lo;
                                         advance_model(v[u].x, v[u].y, dt_hi, dt_lo, &d_hi, &d_lo);
@@ -1089,6 +1163,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                         steer_phase<false>(v[u].x, 0.f, v[u].y, 0.f, s_hi, s_lo, scale, &r, &small);
                                     }
                                     sincospi_reduced(r, small, &sn, &cs);
+                                    }
                                     if (w_tile) {
                                         const float w = __ldg(w_tile + static_cast<size_t>(m) * A + a);
                                         cs *= w;
@@ -1146,7 +1221,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             for (int u = 0; u < kBatch; ++u) {
                 const int e = ne0 + u * kStride;
                 float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (e < n_entries) t4 = ldg_nc_f4(n_src + e);
+                if (e < n_entries && !(prm.dbg & 1)) t4 = ldg_nc_f4(n_src + e);
                 if constexpr (kTv) nxt[u] = t4;
                 else nxt[u] = make_float2(t4.x, t4.z);
             }
@@ -1408,14 +1483,30 @@ static void pick_n_tiling(int A, int M, int parts, int* kb_count, int* nt, int* 
     }
 }
 
+// Status block layout (ints): [0..3] error code / role / barrier / CTA, [4..5] device-visible address of the host
+// flag, [6..7] unused, [kStatusInts ...] the channel-queue counters.
+constexpr int kStatusInts = 8;
+static std::mutex g_init_mu;            // one-time per-device initialisation (status block, kernel attributes)
+static int* g_status_host[64] = {};     // per-device: page-locked, device-mapped flag a failing kernel raises
+
 int get_status_block(int** out) {
     int dev = 0;
     DCBF_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return DCBF_ERR_UNSUPPORTED;
+    std::lock_guard<std::mutex> lock(g_init_mu);
     if (!g_status_dev[dev]) {
         int* p = nullptr;
-        DCBF_CUDA_TRY(cudaMalloc(&p, (4 + 2 * kSchedSlots) * sizeof(int)));
-        DCBF_CUDA_TRY(cudaMemset(p, 0, (4 + 2 * kSchedSlots) * sizeof(int)));
+        int* h = nullptr;
+        int* h_dev = nullptr;
+        DCBF_CUDA_TRY(cudaMalloc(&p, (kStatusInts + 2 * kSchedSlots) * sizeof(int)));
+        DCBF_CUDA_TRY(cudaMemset(p, 0, (kStatusInts + 2 * kSchedSlots) * sizeof(int)));
+        DCBF_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h), 64, cudaHostAllocMapped | cudaHostAllocPortable));
+        h[0] = 0;
+        DCBF_CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h_dev), h, 0));
+        DCBF_CUDA_TRY(cudaMemcpy(p + 4, &h_dev, sizeof(h_dev), cudaMemcpyHostToDevice));
+        // the memset / copy above run on the legacy stream, which non-blocking streams do not wait for
+        DCBF_CUDA_TRY(cudaDeviceSynchronize());
+        g_status_host[dev] = h;
         g_status_dev[dev] = p;
     }
     *out = g_status_dev[dev];
@@ -1440,6 +1531,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
                  cudaStream_t s, const QuantisedOut* q8, const float* beam_weights) {
     FusedParams p{};
     p.dv = reinterpret_cast<const float4*>(delay_vals);
+    p.samples = samples;
     p.out = beams;
     p.weights = beam_weights;
     if (q8) {
@@ -1492,13 +1584,15 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     p.tma_store = !(flags & DCBF_FLAG_DEBUG_DIRECT_EPILOGUE) && (M % (q8 ? 8 : 2) == 0) && (p.nt_count == 1 || p.nt % 32 == 0);
     if (static_cast<long long>(B) * kPols * C > 0x7fffffffLL) return DCBF_ERR_UNSUPPORTED;
     if (int e = get_status_block(&p.status)) return e;
-    static std::atomic<unsigned> ticket{0}, captured_ticket{0};
+    static std::atomic<unsigned> ticket[64], captured_ticket[64];  // per device, like the block the slots live in
+    int slot_dev = 0;
+    DCBF_CUDA_TRY(cudaGetDevice(&slot_dev));
     cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
     DCBF_CUDA_TRY(cudaStreamIsCapturing(s, &capturing));
     const unsigned slot = capturing == cudaStreamCaptureStatusActive
-                              ? kLiveSlots + captured_ticket.fetch_add(1, std::memory_order_relaxed) % kLiveSlots
-                              : ticket.fetch_add(1, std::memory_order_relaxed) % kLiveSlots;
-    p.sched = p.status + 4 + 2 * slot;
+                              ? kLiveSlots + captured_ticket[slot_dev & 63].fetch_add(1, std::memory_order_relaxed) % kLiveSlots
+                              : ticket[slot_dev & 63].fetch_add(1, std::memory_order_relaxed) % kLiveSlots;
+    p.sched = p.status + kStatusInts + 2 * slot;
     p.prof = g_prof_dev;
 
     EncodeTiledFn encode = nullptr;
@@ -1551,10 +1645,13 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     static int n_sms[64] = {};
     int dev = 0;
     DCBF_CUDA_TRY(cudaGetDevice(&dev));
-    if (!n_sms[dev]) {
-        DCBF_CUDA_TRY(cudaDeviceGetAttribute(&n_sms[dev], cudaDevAttrMultiProcessorCount, dev));
-        for (int i = 0; i < kNumKernels; ++i)
-            DCBF_CUDA_TRY(cudaFuncSetAttribute(kKernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    {
+        std::lock_guard<std::mutex> lock(g_init_mu);
+        if (!n_sms[dev]) {
+            for (int i = 0; i < kNumKernels; ++i)
+                DCBF_CUDA_TRY(cudaFuncSetAttribute(kKernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+            DCBF_CUDA_TRY(cudaDeviceGetAttribute(&n_sms[dev], cudaDevAttrMultiProcessorCount, dev));
+        }
     }
     // Whole-tile-set mode: C channels over G persistent CTAs leave a last round of R = C mod G channels in which
     // G - R CTAs idle for a whole channel time (C3 cut over 8 GPUs: 512 channels = 3.46 per CTA, i.e. 4 rounds).  The
@@ -1563,7 +1660,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     p.tile_count = p.nt_count * B * p.ht_count;
     p.n_whole = C;
     p.split = 1;
-    if (!kstream && !(flags & DCBF_FLAG_DEBUG_WHOLE_CHANNELS)) {
+    if (!kstream && !(flags & (DCBF_FLAG_DEBUG_WHOLE_CHANNELS | DCBF_FLAG_STREAMING))) {  // (overlapped launches balance themselves)
         const int rem = C % n_sms[dev];
         const int cut = rem ? std::min(p.tile_count, n_sms[dev] / rem) : 1;
         if (cut > 1) {
@@ -1590,6 +1687,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     // critical path, nothing else changes.  DCBF_FLAG_STREAMING drops the wait (the caller promises independence).
     cfg.numAttrs = (flags & DCBF_FLAG_DEBUG_NO_PDL) ? 0 : 1;
     p.pdl_wait = (flags & DCBF_FLAG_STREAMING) ? 0 : 1;
+    p.dbg = (flags >> 16) & 15;  // developer experiments
     // (int8 output, variant, merged) specialisation; variant: 0 plain, 1 profiling, 2 time-varying steering (the
     // profiler has no time-varying build)
     const int variant = batch_dt_s ? 2 : p.prof ? 1 : 0;
@@ -1599,12 +1697,30 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     return DCBF_OK;
 }
 
+// Non-blocking: has any tcgen05 kernel of this device raised its watchdog since the status was last cleared?  (Reads a
+// page-locked flag the failing kernel writes; meaningful for work the caller has already synchronised with.)
+int fused_status_poll() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return DCBF_OK;
+    const int* h = g_status_host[dev];
+    return h ? *const_cast<const volatile int*>(h) : DCBF_OK;
+}
+
 int fused_status(int* role, int* barrier, int* block) {
     int* blk = nullptr;
     if (int e = get_status_block(&blk)) return e;
+    // every stream of the device, non-blocking ones included (a copy on the legacy stream would not wait for those)
+    DCBF_CUDA_TRY(cudaDeviceSynchronize());
     int h[4] = {};
-    DCBF_CUDA_TRY(cudaMemcpy(h, blk, sizeof(h), cudaMemcpyDeviceToHost));  // synchronises with prior work
-    if (h[0] != 0) DCBF_CUDA_TRY(cudaMemset(blk, 0, (4 + 2 * kSchedSlots) * sizeof(int)));  // also re-arms the counters
+    DCBF_CUDA_TRY(cudaMemcpy(h, blk, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h[0] != 0) {  // clear the status and re-arm the channel counters (an aborted launch leaves them mid-count)
+        DCBF_CUDA_TRY(cudaMemset(blk, 0, 4 * sizeof(int)));
+        DCBF_CUDA_TRY(cudaMemset(blk + kStatusInts, 0, 2 * kSchedSlots * sizeof(int)));
+        DCBF_CUDA_TRY(cudaDeviceSynchronize());
+        int dev = 0;
+        DCBF_CUDA_TRY(cudaGetDevice(&dev));
+        if (g_status_host[dev]) *const_cast<volatile int*>(g_status_host[dev]) = 0;
+    }
     if (role) *role = h[1];
     if (barrier) *barrier = h[2];
     if (block) *block = h[3];

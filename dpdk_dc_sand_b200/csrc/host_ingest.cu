@@ -12,6 +12,7 @@
 // No network code lives here (the reference's DPDK / ibverbs receivers are out of scope): the receive loop calls
 // dcbf_ingest_heap (copy) or dcbf_ingest_heap_ptr (write in place) for every heap it completes.  The chunk returned
 // by dcbf_ingest_pop is exactly the `samples` argument of dcbf_host_plan_run / the source of the H2D copy.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -33,7 +34,10 @@ struct Ingest {
         uint8_t* data = nullptr;
         long long index = -1;          // chunk number = timestamp / (B * step); -1: free
         std::vector<uint8_t> present;  // [B * A]
-        std::vector<uint32_t> received;  // [B * A] payload bytes placed so far by dcbf_ingest_packet
+        // [B * A] byte ranges [begin, end) of each heap placed so far by dcbf_ingest_packet, sorted and disjoint: a
+        // repeated or overlapping packet must not count twice (the heap would be reported complete while another
+        // packet's bytes are still those of the slot's previous chunk)
+        std::vector<std::vector<std::pair<uint32_t, uint32_t>>> received;
         int n_present = 0;
         bool handed_out = false;
     };
@@ -102,7 +106,7 @@ static int slot_for(Ingest* g, long long index) {
             c.n_present = 0;
             c.handed_out = false;
             std::fill(c.present.begin(), c.present.end(), 0);
-            std::fill(c.received.begin(), c.received.end(), 0u);
+            for (auto& r : c.received) r.clear();
             return s;
         }
     }
@@ -173,7 +177,7 @@ int dcbf_ingest_create(dcbf_ingest_t* ingest, int n_chunks, int n_batches, int n
             return DCBF_ERR_UNSUPPORTED;
         }
         c.present.assign(static_cast<size_t>(n_batches) * n_ants, 0);
-        c.received.assign(static_cast<size_t>(n_batches) * n_ants, 0u);
+        c.received.assign(static_cast<size_t>(n_batches) * n_ants, {});
     }
     *ingest = g;
     return DCBF_OK;
@@ -253,6 +257,7 @@ int dcbf_ingest_packet(dcbf_ingest_t ingest, const void* packet, size_t length, 
     if (descriptor) return DCBF_ERR_UNSUPPORTED;  // descriptor heaps carry no data
     if (timestamp >= 0) {  // first packet of a heap (or a sender that repeats the pointers): remember the heap's place
         if (feng_id < 0) feng_id = default_feng_id;
+        if (feng_id < 0 || feng_id >= g->A) return bad();  // 48-bit field: range-check before it is narrowed to int
         if (g->heap_keys.find(static_cast<unsigned long long>(heap_cnt)) == g->heap_keys.end()) {
             g->heap_key_order.push_back(static_cast<unsigned long long>(heap_cnt));
             if (g->heap_key_order.size() > 4096) {
@@ -286,9 +291,30 @@ int dcbf_ingest_packet(dcbf_ingest_t ingest, const void* packet, size_t length, 
         ++g->n_duplicate;
         return DCBF_OK;
     }
+    // merge [heap_offset, heap_offset + payload_len) into the heap's received ranges
+    auto& ranges = c.received[cell];
+    uint32_t lo = static_cast<uint32_t>(heap_offset), hi = lo + static_cast<uint32_t>(payload_len);
+    bool covered = false;
+    std::vector<std::pair<uint32_t, uint32_t>> merged;
+    merged.reserve(ranges.size() + 1);
+    for (const auto& r : ranges) {
+        if (r.first <= lo && hi <= r.second) covered = true;
+        if (r.second < lo || hi < r.first) {
+            merged.push_back(r);  // disjoint and not adjacent
+        } else {
+            lo = std::min(lo, r.first);
+            hi = std::max(hi, r.second);
+        }
+    }
+    if (covered && payload_len > 0) {  // a retransmission of bytes that are already in place
+        ++g->n_duplicate;
+        return DCBF_OK;
+    }
     memcpy(c.data + static_cast<size_t>(cell) * g->heap_bytes + heap_offset, p + header, static_cast<size_t>(payload_len));
-    c.received[cell] += static_cast<uint32_t>(payload_len);
-    if (c.received[cell] >= g->heap_bytes) mark_present(g, slot, cell);
+    merged.emplace_back(lo, hi);
+    std::sort(merged.begin(), merged.end());
+    ranges.swap(merged);
+    if (ranges.size() == 1 && ranges[0].first == 0 && ranges[0].second >= g->heap_bytes) mark_present(g, slot, cell);
     return DCBF_OK;
 }
 

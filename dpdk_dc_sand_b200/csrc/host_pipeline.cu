@@ -24,6 +24,11 @@ struct HostPlan {
         float* beams = nullptr;
     };
     std::vector<Slot> slots;
+    // Resident delay model (dcbf_host_plan_set_delay_vals): the whole [C][M][A][4] table on the device, double-buffered so
+    // that an update lands in the copy the kernels of a run in flight do not read.  Runs that pass delay_vals = NULL use
+    // it: the per-step H2D traffic is then the voltages alone (the delay model changes at control-plane cadence).
+    float* dv_resident[2] = {nullptr, nullptr};
+    int dv_active = -1;
     float* gains = nullptr;                    // device [M], set by dcbf_host_plan_set_gains (q8 runs)
     unsigned long long* saturated = nullptr;   // device counter (q8 runs)
 };
@@ -37,6 +42,8 @@ static int destroy_plan(HostPlan* p) {
         cudaFree(s.beams);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
+    cudaFree(p->dv_resident[0]);
+    cudaFree(p->dv_resident[1]);
     cudaFree(p->gains);
     cudaFree(p->saturated);
     delete p;
@@ -63,6 +70,7 @@ static int run_plan(HostPlan* p, const uint8_t* h_samples, const float* h_dv, vo
     int dev = 0;
     DCBF_CUDA_TRY(cudaGetDevice(&dev));
     if (dev != p->device) return DCBF_ERR_INVALID_ARG;
+    if (!h_dv && p->dv_active < 0) return DCBF_ERR_INVALID_ARG;  // dcbf_host_plan_set_delay_vals first
     if (q8) {
         if (!p->gains) return DCBF_ERR_INVALID_ARG;  // dcbf_host_plan_set_gains first
         if (!p->saturated) DCBF_CUDA_TRY(cudaMalloc(&p->saturated, sizeof(unsigned long long)));
@@ -78,11 +86,15 @@ static int run_plan(HostPlan* p, const uint8_t* h_samples, const float* h_dv, vo
         DCBF_CUDA_TRY(cudaMemcpy2DAsync(s.samples, cc * samp_chan, h_samples + c0 * samp_chan, p->C * samp_chan,
                                         cc * samp_chan, static_cast<size_t>(p->B) * p->A, cudaMemcpyHostToDevice,
                                         s.stream));
-        DCBF_CUDA_TRY(cudaMemcpyAsync(s.delay_vals, h_dv + static_cast<size_t>(c0) * p->M * p->A * 4,
-                                      static_cast<size_t>(cc) * p->M * p->A * 16, cudaMemcpyHostToDevice, s.stream));
+        const float* dv_dev = s.delay_vals;
+        if (h_dv)
+            DCBF_CUDA_TRY(cudaMemcpyAsync(s.delay_vals, h_dv + static_cast<size_t>(c0) * p->M * p->A * 4,
+                                          static_cast<size_t>(cc) * p->M * p->A * 16, cudaMemcpyHostToDevice, s.stream));
+        else
+            dv_dev = p->dv_resident[p->dv_active] + static_cast<size_t>(c0) * p->M * p->A * 4;
         const long long first_chan = static_cast<long long>(p->C) * p->xeng_id + c0;
         const QuantisedOut qo{reinterpret_cast<int8_t*>(s.beams), p->gains, p->saturated};
-        if (int e = launch_fused(s.samples, s.delay_vals, s.beams, p->B, p->A, cc, p->N, p->T, p->M, first_chan,
+        if (int e = launch_fused(s.samples, dv_dev, s.beams, p->B, p->A, cc, p->N, p->T, p->M, first_chan,
                                  p->sample_period, nullptr, p->flags, s.stream, q8 ? &qo : nullptr, nullptr))
             return e;
         DCBF_CUDA_TRY(cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(h_beams) + c0 * beam_chan, p->C * beam_chan, s.beams,
@@ -90,6 +102,7 @@ static int run_plan(HostPlan* p, const uint8_t* h_samples, const float* h_dv, vo
                                         cudaMemcpyDeviceToHost, s.stream));
     }
     for (auto& s : p->slots) DCBF_CUDA_TRY(cudaStreamSynchronize(s.stream));
+    if (fused_status_poll() != DCBF_OK) return fused_status(nullptr, nullptr, nullptr);  // a watchdog fired: the beams are not valid
     if (q8 && h_saturated)
         DCBF_CUDA_TRY(cudaMemcpy(h_saturated, p->saturated, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return DCBF_OK;
@@ -128,8 +141,24 @@ __attribute__((visibility("default"))) int dcbf_host_plan_create(dcbf_host_plan_
 
 __attribute__((visibility("default"))) int dcbf_host_plan_run(dcbf_host_plan_t plan, const uint8_t* samples,
                                                               const float* delay_vals, float* beams) {
-    if (!plan || !samples || !delay_vals || !beams) return DCBF_ERR_INVALID_ARG;
+    if (!plan || !samples || !beams) return DCBF_ERR_INVALID_ARG;  // delay_vals may be NULL: resident delay model
     return run_plan(static_cast<HostPlan*>(plan), samples, delay_vals, beams, false, nullptr);
+}
+
+__attribute__((visibility("default"))) int dcbf_host_plan_set_delay_vals(dcbf_host_plan_t plan, const float* delay_vals) {
+    auto* p = static_cast<HostPlan*>(plan);
+    if (!p || !delay_vals) return DCBF_ERR_INVALID_ARG;
+    int dev = 0;
+    DCBF_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != p->device) return DCBF_ERR_INVALID_ARG;
+    const size_t bytes = static_cast<size_t>(p->C) * p->M * p->A * 16;
+    const int next = p->dv_active == 0 ? 1 : 0;  // never the copy the kernels of the last run read
+    if (!p->dv_resident[next]) DCBF_CUDA_TRY(cudaMalloc(&p->dv_resident[next], bytes));
+    cudaStream_t s = p->slots[0].stream;
+    DCBF_CUDA_TRY(cudaMemcpyAsync(p->dv_resident[next], delay_vals, bytes, cudaMemcpyHostToDevice, s));
+    DCBF_CUDA_TRY(cudaStreamSynchronize(s));
+    p->dv_active = next;
+    return DCBF_OK;
 }
 
 __attribute__((visibility("default"))) int dcbf_host_plan_set_gains(dcbf_host_plan_t plan, const float* beam_gains) {
@@ -143,7 +172,7 @@ __attribute__((visibility("default"))) int dcbf_host_plan_set_gains(dcbf_host_pl
 __attribute__((visibility("default"))) int dcbf_host_plan_run_q8(dcbf_host_plan_t plan, const uint8_t* samples,
                                                                  const float* delay_vals, int8_t* beams_q8,
                                                                  unsigned long long* saturated) {
-    if (!plan || !samples || !delay_vals || !beams_q8) return DCBF_ERR_INVALID_ARG;
+    if (!plan || !samples || !beams_q8) return DCBF_ERR_INVALID_ARG;
     return run_plan(static_cast<HostPlan*>(plan), samples, delay_vals, beams_q8, true, saturated);
 }
 

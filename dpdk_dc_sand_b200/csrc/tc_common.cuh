@@ -15,7 +15,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 int get_encode_fn(EncodeTiledFn* out);  // fused.cu
 // Per-device status block shared by the tcgen05 kernels: [0] = error code, [1] = role, [2] = barrier id, [3] = CTA
-// (read and cleared by dcbf_fused_status); the fused kernel's channel counters follow it.
+// (read and cleared by dcbf_fused_status), [4..5] = device-visible address of a page-locked host flag raised with the
+// error code; the fused kernel's channel counters follow at [8].
 int get_status_block(int** out);        // fused.cu
 
 namespace {
@@ -240,7 +241,7 @@ __device__ __forceinline__ int sched_get(Control* ctl, uint32_t k) {
     return ctl->chan_ring[k & 7];
 }
 
-__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Control* ctl, int* status, int role, int id) {
+__device__ __forceinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Control* ctl, int* status, int role, int id) {
     const unsigned long long t0 = global_ns();
     for (;;) {
         // up to 64 hardware-suspended probes in a 7-instruction loop, then one look at the abort flag / clock
@@ -267,6 +268,10 @@ __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Contr
                 status[1] = role;
                 status[2] = id;
                 status[3] = static_cast<int>(blockIdx.x);
+                // page-locked host flag (address kept in the status block): lets the host notice without a copy
+                volatile int* host_flag = *reinterpret_cast<volatile int* volatile*>(status + 4);
+                if (host_flag) *host_flag = DCBF_ERR_TIMEOUT;
+                __threadfence_system();
             }
             return false;
         }

@@ -31,7 +31,9 @@ class DelayModelUpdater:
         self._pending = None  # (buffer index, weights tensor or None, event)
         self._copy_stream = torch.cuda.Stream(device=self._buffers[0].buffer.device)
         self._staging = [b.empty_like() for b in self._buffers]  # pinned host arrays, one per device buffer
+        self._staging_done = [None, None]  # event after the last DMA out of each staging array
         self._weights = [None, None]
+        self._retired = None  # event on the compute stream after the last launch that may read the inactive buffer
 
     def update(self, delay_vals: np.ndarray, beam_weights: np.ndarray = None) -> None:
         """Start uploading a new model; returns immediately.  The operation keeps using the current one."""
@@ -42,8 +44,16 @@ class DelayModelUpdater:
             raise ValueError(f"delay_vals must have shape {buf.shape}")
         if self._pending is not None:
             self._pending[2].synchronize()  # an earlier, never activated upload into the same buffer
+        if self._staging_done[idx] is not None:
+            self._staging_done[idx].synchronize()  # the previous DMA out of this staging array has finished
         host[...] = delay_vals
         w_dev = None
+        # Kernels queued before the last activate() may still be reading this buffer (it was the active one until then):
+        # the copy waits, on the device, for the point of the compute stream at which it was retired.
+        if self._retired is None:
+            self._retired = torch.cuda.Event()
+            self._retired.record(self.op.command_queue.stream)
+        self._copy_stream.wait_event(self._retired)
         with torch.cuda.stream(self._copy_stream):
             buf.buffer.copy_(torch.from_numpy(np.asarray(host)), non_blocking=True)
             if beam_weights is not None:
@@ -52,6 +62,7 @@ class DelayModelUpdater:
                 self._keep = w_host
             event = torch.cuda.Event()
             event.record(self._copy_stream)
+        self._staging_done[idx] = event
         self._pending = (idx, w_dev, event)
 
     def activate(self) -> bool:
@@ -59,7 +70,11 @@ class DelayModelUpdater:
         if self._pending is None:
             return False
         idx, w_dev, event = self._pending
-        self.op.command_queue.stream.wait_event(event)  # device-side wait: the host does not block
+        stream = self.op.command_queue.stream
+        # every launch queued so far reads the buffer that now becomes the inactive one: remember where they end
+        self._retired = self._torch.cuda.Event()
+        self._retired.record(stream)
+        stream.wait_event(event)  # device-side wait: the host does not block
         self.op.bind(bufin_delay_vals=self._buffers[idx])
         if w_dev is not None:
             self.op.beam_weights = w_dev

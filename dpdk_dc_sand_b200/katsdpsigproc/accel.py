@@ -111,6 +111,10 @@ class CommandQueue(AbstractCommandQueue):
 
     def finish(self) -> None:
         self.stream.synchronize()
+        # an in-kernel watchdog abort leaves partly written beams: surface it where results become visible to the host
+        from .. import _capi
+
+        _capi.fused_status_poll()
 
     def flush(self) -> None:
         pass

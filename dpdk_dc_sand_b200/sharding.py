@@ -110,9 +110,22 @@ def gather_beams(local_beams, shard: ChannelShard, dst: int = 0, group=None):
     if tuple(local_beams.shape)[2] != shard.n_channels_per_stream:
         raise ValueError("local_beams axis 2 must be this rank's n_channels_per_stream")
     local_beams = local_beams.contiguous()
-    # grouped send/recv under the hood (ncclSend/ncclRecv over NVLink/NVSwitch with the nccl backend)
-    parts = [torch.empty_like(local_beams) for _ in range(shard.world)] if dist.get_rank(group) == dst else None
-    dist.gather(local_beams, parts, dst=dst, group=group)
-    if parts is None:
-        return None
-    return torch.cat(parts, dim=2)
+    me = dist.get_rank(group)
+    n_b, n_p, c = local_beams.shape[0], local_beams.shape[1], shard.n_channels_per_stream
+    # One grouped batch of point-to-point transfers (ncclSend / ncclRecv over NVLink / NVSwitch with the nccl backend):
+    # for a fixed (batch, pol) a rank's C channels are one contiguous run of the full-band tensor, so every piece is
+    # received straight into its final place -- no list of parts, no second pass over the gathered bytes on `dst`.
+    if me == dst:
+        full = torch.empty(local_beams.shape[:2] + (shard.n_channels,) + local_beams.shape[3:], dtype=local_beams.dtype,
+                           device=local_beams.device)
+        full[:, :, dst * c:(dst + 1) * c].copy_(local_beams)
+        ops = [dist.P2POp(dist.irecv, full[b, p, r * c:(r + 1) * c], dist.get_global_rank(group, r) if group is not None else r,
+                          group=group)
+               for r in range(shard.world) if r != dst for b in range(n_b) for p in range(n_p)]
+    else:
+        full = None
+        peer = dist.get_global_rank(group, dst) if group is not None else dst
+        ops = [dist.P2POp(dist.isend, local_beams[b, p], peer, group=group) for b in range(n_b) for p in range(n_p)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return full

@@ -108,7 +108,17 @@ int dcbf_beamform(const uint8_t* reordered, const float* coeffs, float* beams, i
 
 /* Stages 1+2+3 in one pass: every voltage byte and every delay value is read from HBM once,
  * neither `reordered` nor `coeffs` is materialised.  tcgen05 (fp16 operands, fp32 accumulate in TMEM).
- * n_chans_total / xeng_id / sample_period as in dcbf_coeffs.  Does not synchronise. */
+ * n_chans_total / xeng_id / sample_period as in dcbf_coeffs.  Does not synchronise.
+ *
+ * Launch ordering: every call is a programmatic dependent launch.  Its prologue (barrier / tensor-memory set-up, L2
+ * prefetch of its first inputs) may overlap the tail of the kernel queued before it on the stream; it then waits for
+ * that kernel to complete and flush before it reads or writes global memory, so the usual stream semantics hold.
+ * DCBF_FLAG_STREAMING removes that wait (see the flag).
+ *
+ * CUDA graphs: launches can be captured and replayed.  A captured launch keeps one of 64 per-device channel-queue
+ * slots for every replay; launches that can run CONCURRENTLY must not share a slot, so: at most 64 captured launches per
+ * device may be in flight at once, and one graph must not be replayed concurrently with itself (replays on one stream,
+ * or serialised by events, are fine).  Live launches draw from a separate pool of 64 slots per device. */
 int dcbf_fused(const uint8_t* samples, const float* delay_vals, float* beams, int n_batches, int n_ants,
                int n_chans, int n_chans_total, int n_samples, int n_beams, int xeng_id, double sample_period,
                unsigned flags, dcbf_stream_t stream);
@@ -155,10 +165,15 @@ int dcbf_coeffs_ex(const float* delay_vals, float* coeffs, int n_batches, int n_
                    int n_chans_total, int n_ants, int n_beams, int xeng_id, double sample_period,
                    const double* batch_dt_s, const float* beam_weights, dcbf_stream_t stream);
 
-/* Blocks until prior work on the current device is done, then returns the status the last dcbf_fused kernels
- * left behind: DCBF_OK, or DCBF_ERR_TIMEOUT if an in-kernel pipeline wait exceeded its 2 s guard (the kernel
- * then exits early instead of hanging; *role / *barrier / *block say who waited on what).  Clears the status. */
+/* Synchronises the whole current device (cudaDeviceSynchronize: every stream, non-blocking ones included), then
+ * returns the status the dcbf_fused / dcbf_beamform kernels left behind: DCBF_OK, or DCBF_ERR_TIMEOUT if an in-kernel
+ * pipeline wait exceeded its 2 s guard (the kernel then exits early instead of hanging, leaving partly written beams;
+ * *role / *barrier / *block say who waited on what).  Clears the status. */
 int dcbf_fused_status(int* role, int* barrier, int* block);
+/* Non-blocking form: DCBF_OK, or the error code a kernel has raised since the status was last cleared (a page-locked
+ * flag the failing kernel writes).  It covers work the caller has already synchronised with (after
+ * cudaStreamSynchronize / an event wait); dcbf_host_plan_run* check it themselves and return the error. */
+int dcbf_fused_status_poll(void);
 
 /* Developer aid: when non-NULL, every dcbf_fused CTA writes 24 uint64 to dev_ptr[blockIdx*24 + role*4 + slot]:
  * nanoseconds each warp role spent blocked per barrier class (slot 0..2) and the role's span (slot 3).
@@ -182,6 +197,10 @@ int dcbf_host_plan_create(dcbf_host_plan_t* plan, int n_batches, int n_ants, int
                           int n_samples, int n_beams, int xeng_id, double sample_period, unsigned flags,
                           int chunk_chans, int n_slots);
 int dcbf_host_plan_run(dcbf_host_plan_t plan, const uint8_t* samples, const float* delay_vals, float* beams);
+/* Resident delay model: upload the whole HOST [C][M][A][4] table once (and again whenever the control plane changes
+ * it: the new table goes into the copy that runs already issued do not read); runs that pass delay_vals = NULL then
+ * use it, so the per-step host-to-device traffic is the voltages alone.  Blocks until the table is on the device. */
+int dcbf_host_plan_set_delay_vals(dcbf_host_plan_t plan, const float* delay_vals);
 /* Requantised-output runs of a plan (dcbf_fused_q8 per chunk): set the per-beam gains (HOST float[n_beams]) once,
  * then run; beams_q8 is a HOST int8 array [B][2][C][T/16][16][2M]; *saturated (may be NULL) gets the clip count. */
 int dcbf_host_plan_set_gains(dcbf_host_plan_t plan, const float* beam_gains);

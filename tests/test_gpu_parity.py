@@ -693,6 +693,32 @@ def test_host_plan_matches_device_path(dropin):
     assert np.all(np.abs(out - orc.beamform_pipeline(x, dv, n, xid, TS)) <= _budget(x))
 
 
+def test_host_plan_resident_delay_model(dropin):
+    """dcbf_host_plan_set_delay_vals: the delay model is uploaded once, runs with delay_vals = NULL use it (per-step
+    H2D = voltages only) and give the bytes of the per-step-upload form; an update lands in the other copy and takes
+    effect from the next run."""
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m, n, xid = 1, 24, 29, 32, 6, 128, 2
+    x = orc.make_samples(b, a, c, t, seed=71)
+    dv1 = orc.make_delay_vals_random(c, m, a, seed=72)
+    dv2 = orc.make_delay_vals_random(c, m, a, seed=73)
+    plan = _capi.HostPlan(b, a, c, n, t, m, xid, TS, chunk_chans=7, n_slots=2)
+    want1, want2, got = (np.zeros((b, 2, c, t // 16, 16, 2 * m), np.float32) for _ in range(3))
+    with pytest.raises(ValueError):
+        plan.run(x, None, got)  # no resident model yet
+    plan.run(x, dv1, want1)
+    plan.run(x, dv2, want2)
+    plan.set_delay_vals(dv1)
+    plan.run(x, None, got)
+    np.testing.assert_array_equal(got, want1)
+    plan.set_delay_vals(dv2)
+    plan.run(x, None, got)
+    np.testing.assert_array_equal(got, want2)
+    assert not np.array_equal(want1, want2)
+    plan.close()
+
+
 def test_c_abi_error_codes(dropin):
     import torch
 
@@ -800,3 +826,87 @@ def test_headline_size_fused_equals_three_kernel_chain_and_is_linear(dropin):
     torch.cuda.synchronize()
     _capi.fused_status()
     assert (16 * o_hi + o_lo - o).abs().max().item() <= 0.05
+
+
+# BASELINE.json configs[2..4] whole on one GPU and as the per-GPU share of 8 (xeng_id > 0): n_ants, n_chans on this GPU,
+# n_samples, n_beams, n_chans of the band, xeng_id
+FULL_SIZE = {
+    "c3": (64, 4096, 256, 64, 4096, 0),
+    "c3_share_of_8": (64, 512, 256, 64, 4096, 5),
+    "c4": (80, 32768, 256, 32, 32768, 0),
+    "c4_share_of_8": (80, 4096, 256, 32, 32768, 7),
+    "c5": (197, 4096, 256, 256, 4096, 0),
+    "c5_share_of_8": (197, 512, 256, 256, 4096, 3),
+}
+
+
+def _full_size_inputs(a, c, t, m, seed):
+    import torch
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.randint(0, 256, (1, a, c, t, 2, 2), dtype=torch.uint8, device=dev, generator=g)
+    dv = torch.zeros((c, m, a, 4), dtype=torch.float32, device=dev)
+    dv[..., 0] = (torch.rand((c, m, a), device=dev, generator=g) * 32 - 16) * TS
+    dv[..., 2] = (torch.rand((c, m, a), device=dev, generator=g) * 2 - 1) * math.pi
+    return x, dv
+
+
+def _sampled_channels(c, seed, count=16):
+    rng = np.random.default_rng(seed)
+    return sorted({0, c - 1, *rng.choice(c, size=count - 2, replace=False).tolist()})
+
+
+@pytest.mark.parametrize("name", list(FULL_SIZE))
+def test_full_size_configs_against_the_oracle(dropin, name):
+    """Every BASELINE configuration at its full size (whole band on one GPU: 64-bit offsets, many-N-tile and K-streamed
+    modes) and as the 8-GPU share with a non-zero xeng_id: 16 channels (first, last, 14 random) of the fused result
+    against the float64 oracle within the 2^-10 * sum|x| budget."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    a, c, t, m, n_total, xid = FULL_SIZE[name]
+    x, dv = _full_size_inputs(a, c, t, m, seed=31)
+    out = torch.empty((1, 2, c, t // 16, 16, 2 * m), dtype=torch.float32, device=x.device)
+    _capi.fused(x, dv, out, 1, a, c, n_total, t, m, xid, TS)
+    torch.cuda.synchronize()
+    _capi.fused_status()
+    worst = 0.0
+    for ch in _sampled_channels(c, seed=32):
+        xs = x[:, :, ch:ch + 1].cpu().numpy()
+        dvs = np.ascontiguousarray(dv[ch:ch + 1].cpu().numpy())
+        ref = orc.beamform_pipeline(xs, dvs, n_total, c * xid + ch, TS)  # a 1-channel engine at the absolute channel
+        got = out[:, :, ch:ch + 1].cpu().numpy()
+        err = np.abs(got.astype(np.float64) - ref)
+        assert np.all(err <= _budget(xs)), (name, ch, float(err.max()))
+        worst = max(worst, float(np.max(err / (_budget(xs) * 2.0 ** 10))))
+    assert worst < 2.0 ** -10
+
+
+def test_full_size_q8_against_the_oracle(dropin):
+    """int8 requantised output at the size the metric is quoted on (C3): sampled channels against the oracle's
+    requantisation of its float64 beams (at most one quantisation step away, practically always equal)."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    a, c, t, m, n_total, xid = FULL_SIZE["c3"]
+    x, dv = _full_size_inputs(a, c, t, m, seed=41)
+    gains = torch.full((m,), 0.02, dtype=torch.float32, device=x.device)  # sum|x| ~ 1e4: a few per cent of the values clip
+    out = torch.empty((1, 2, c, t // 16, 16, 2 * m), dtype=torch.int8, device=x.device)
+    sat = torch.zeros(1, dtype=torch.int64, device=x.device)
+    _capi.fused_q8(x, dv, gains, out, 1, a, c, n_total, t, m, xid, TS, saturated=sat)
+    torch.cuda.synchronize()
+    _capi.fused_status()
+    differing = total = 0
+    for ch in _sampled_channels(c, seed=42):
+        xs = x[:, :, ch:ch + 1].cpu().numpy()
+        dvs = np.ascontiguousarray(dv[ch:ch + 1].cpu().numpy())
+        want, _ = orc.requantise(orc.beamform_pipeline(xs, dvs, n_total, c * xid + ch, TS), gains.cpu().numpy())
+        diff = np.abs(out[:, :, ch:ch + 1].cpu().numpy().astype(np.int32) - want.astype(np.int32))
+        assert diff.max() <= 1, ch
+        differing += int(np.count_nonzero(diff))
+        total += diff.size
+    assert differing <= 1e-3 * total
+    assert 0 < int(sat.item()) < out.numel()

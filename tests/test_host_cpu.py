@@ -293,6 +293,47 @@ def test_ingest_accepts_raw_spead_packets():
     ing.close()
 
 
+def test_ingest_duplicate_and_retransmitted_packets_do_not_complete_a_heap_early():
+    """A repeated packet must not count twice towards its heap: the heap is complete only when every byte range has
+    arrived (a byte count alone would report it present while the missing packet's bytes are still those of the slot's
+    previous chunk, and would then drop the real packet as a duplicate).  A 48-bit feng_id beyond the antenna count is
+    refused instead of being narrowed to a valid one."""
+    from dpdk_dc_sand_b200 import _capi
+
+    B, A, C_, T, step = 1, 2, 4, 16, 4096
+    heap_bytes = C_ * T * 4  # 256: packets of 96, 96, 64 bytes
+    ing = _capi.Ingest(4, B, A, C_, T, step, pinned=False)
+    rng = np.random.default_rng(9)
+    truth = rng.integers(1, 256, (B, A, C_, T, 2, 2), dtype=np.uint8)
+
+    def packets(a, cnt, data):
+        raw = data.tobytes()
+        out = []
+        for off in range(0, heap_bytes, 96):
+            items = [(0x1600, True, 0), (0x4101, True, a), (0x4300, False, 0)] if off == 0 else []
+            out.append(_spead_packet(cnt, heap_bytes, off, raw[off:off + 96], items))
+        return out
+
+    p0, p1 = packets(0, 11, truth[0, 0]), packets(1, 12, truth[0, 1])
+    for pkt in p1:
+        assert ing.packet(pkt)
+    assert ing.packet(p0[0])
+    assert ing.packet(p0[1])
+    assert ing.packet(p0[1])      # duplicate: 96 + 96 + 96 bytes "received", but [192, 256) is still missing
+    assert ing.packet(p0[0])      # retransmission of the first packet
+    assert ing.stats()["duplicate"] == 2
+    assert ing.pop() is None      # not complete yet
+    assert ing.packet(p0[2])      # the real last packet is NOT dropped as a duplicate
+    samples, ts, present = ing.pop()
+    assert present.all()
+    np.testing.assert_array_equal(samples, truth)
+    ing.release(samples)
+    wide = _spead_packet(13, heap_bytes, 0, bytes(96), [(0x1600, True, step), (0x4101, True, 0x100000001), (0x4300, False, 0)])
+    with pytest.raises(ValueError):
+        ing.packet(wide)
+    ing.close()
+
+
 def test_numa_binding_helper_is_optional():
     """sharding.bind_to_device_numa is an optimisation for one-process-per-GPU hosts: without NVML / a GPU it reports
     None and leaves the process alone."""
