@@ -11,9 +11,10 @@
 // the coefficient block [[cos,sin],[-sin,cos]] IS its B operand, both built in shared memory.
 //
 // Per (batch b, pol p, channel c):  D[T x 2M] = X[T x 2A] * W[2A x 2M]   (fp16 operands, fp32 accumulate)
-//   X[t][2a+x]   = f16(sample[b][a][c][t][p][x])          exact: |byte| <= 255
-//   W[2a+x][2m+y] = {{cos, sin}, {-sin, cos}}[x][y] of rot(c, m, a), carried as fp16 hi + fp16 lo
-//                  (two accumulating MMAs; coefficient error ~2^-24) or fp16 hi only (DCBF_FLAG_FP16_COEFF).
+//   X[t][2a+x]   = f16(sample[b][a][c][t][p][x] / 1024)   exact: |byte| <= 255
+//   W[2a+x][2m+y] = 1024 * {{cos, sin}, {-sin, cos}}[x][y] of rot(c, m, a), carried as fp16 hi + fp16 lo
+//                  (two accumulating MMAs; coefficient error ~2^-24) or fp16 hi only (DCBF_FLAG_FP16_COEFF);
+//                  the two powers of two cancel in the product and keep small coefficients out of fp16 subnormals.
 //
 // One persistent CTA per SM takes channels from a dynamic queue.  Warp roles (608 threads):
 //   warps 0-7     coeffs    : delay_vals (coalesced float4, one batch prefetched in registers) -> phase to float64
@@ -155,10 +156,18 @@ struct FusedParams {
     double turns_per_delay;  // -1 / (N * Ts): half-turns of phase per (second of delay x channel offset)
 };
 
-// u8 (or i8) pair -> half2, exact.  `w` holds {p0.re, p0.im, p1.re, p1.im}; sel picks the pol.
+// The two MMA operands carry a power-of-two scale that cancels in the product: the voltages enter as x * 2^-10 (exact
+// in fp16: |x| <= 255), the steering coefficients as c * 2^10, split hi + lo.  A coefficient near zero (cos of a phase
+// next to pi/2, a small beam weight) would otherwise put its hi part, and every lo part below 2^-3, into the fp16
+// subnormal range, where the absolute resolution is stuck at 6e-8 instead of following the value: with the scale the
+// pair resolves 2^-22 relative down to |c| ~ 1e-4 and 6e-11 absolute below that.  The products and the fp32 sums in
+// TMEM are bit-for-bit what they would be without the scale wherever nothing was subnormal.
+constexpr float kCoefScale = 1024.0f;
+
+// u8 (or i8) pair -> half2 of x / 1024, exact.  `w` holds {p0.re, p0.im, p1.re, p1.im}; sel picks the pol.
 __device__ __forceinline__ uint32_t bytes_to_half2(uint32_t w, uint32_t sel, uint32_t bias) {
-    // bytes -> 0x64bb = 1024 + b (fp16), then subtract 1024 (u8) or 1152 (i8 after the ^0x80 re-bias)
-    const uint32_t h = __byte_perm(w, 0x64646464u, sel);
+    // bytes -> 0x3Cbb = 1 + b / 1024 (fp16), then subtract 1 (u8) or 1 + 128 / 1024 (i8 after the ^0x80 re-bias)
+    const uint32_t h = __byte_perm(w, 0x3C3C3C3Cu, sel);
     const __half2 r = __hsub2(*reinterpret_cast<const __half2*>(&h), *reinterpret_cast<const __half2*>(&bias));
     return *reinterpret_cast<const uint32_t*>(&r);
 }
@@ -168,23 +177,25 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// sin(pi (r + small)), cos(pi (r + small)) for |r| < 2^20 half-turns and a tiny correction `small`.  Quadrant
-// split q = rint(2r), t = r - q/2 (exact) + small in [-1/4, 1/4], odd/even Taylor polynomials in t (truncation
-// < 2e-9 and 2e-10), then the quadrant rotation.  Absolute error <= ~1e-7; no special cases (r is finite here).
+// kCoefScale * sin(pi (r + small)), kCoefScale * cos(pi (r + small)) for |r| < 2^20 half-turns and a tiny correction
+// `small`.  Quadrant split q = rint(2r), t = r - q/2 (exact) + small in [-1/4, 1/4], odd/even Taylor polynomials in t
+// (truncation < 2e-9 and 2e-10) whose constants carry the power-of-two scale (same roundings as unscaled), then the
+// quadrant rotation.  Absolute error <= ~1e-7 of the unscaled value; no special cases (r is finite here).
 __device__ __forceinline__ void sincospi_reduced(float r, float small, float* sn, float* cs) {
+    constexpr float K = kCoefScale;
     const float z = fmaf(r, 2.0f, 12582912.0f);  // 1.5 * 2^23: the low mantissa bits now hold rint(2r)
     const int q = __float_as_int(z);
     const float t = fmaf(z - 12582912.0f, -0.5f, r) + small;
     const float s = t * t;
-    float ps = fmaf(s, 0.0821458866f, -0.599264529f);   // pi^9/9!, -pi^7/7!
-    ps = fmaf(ps, s, 2.55016404f);                       // pi^5/5!
-    ps = fmaf(ps, s, -5.16771278f);                      // -pi^3/3!
-    ps = fmaf(ps * s, t, t * 3.14159274f);               // t*pi + t*s*(...)
-    float pc = fmaf(s, -0.0258068914f, 0.235330630f);    // -pi^10/10!, pi^8/8!
-    pc = fmaf(pc, s, -1.33526277f);                      // -pi^6/6!
-    pc = fmaf(pc, s, 4.05871213f);                       // pi^4/4!
-    pc = fmaf(pc, s, -4.93480220f);                      // -pi^2/2!
-    pc = fmaf(pc, s, 1.0f);
+    float ps = fmaf(s, K * 0.0821458866f, K * -0.599264529f);   // pi^9/9!, -pi^7/7!
+    ps = fmaf(ps, s, K * 2.55016404f);                           // pi^5/5!
+    ps = fmaf(ps, s, K * -5.16771278f);                          // -pi^3/3!
+    ps = fmaf(ps * s, t, t * (K * 3.14159274f));                 // t*pi + t*s*(...)
+    float pc = fmaf(s, K * -0.0258068914f, K * 0.235330630f);    // -pi^10/10!, pi^8/8!
+    pc = fmaf(pc, s, K * -1.33526277f);                          // -pi^6/6!
+    pc = fmaf(pc, s, K * 4.05871213f);                           // pi^4/4!
+    pc = fmaf(pc, s, K * -4.93480220f);                          // -pi^2/2!
+    pc = fmaf(pc, s, K);
     const bool swap = q & 1;
     const float a = swap ? pc : ps, b = swap ? ps : pc;
     // q mod 4: 0 -> (s, c); 1 -> (c, -s); 2 -> (-s, -c); 3 -> (-c, s)
@@ -923,7 +934,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         // thread = one sample row t; per 4-antenna chunk: 4 conflict-free LDS.32, 8 PRMT + 8 HSUB2, 2 STS.128
         // (quarter-warps write 8 distinct 16-byte chunks of the 64B-swizzled rows: conflict-free)
         const int t = threadIdx.x - kConvertWarp0 * 32;
-        const uint32_t bias = prm.signed_in ? 0x64806480u : 0x64006400u;  // 1152 | 1024 as fp16 pairs
+        const uint32_t bias = prm.signed_in ? 0x3C803C80u : 0x3C003C00u;  // 1 + 128/1024 | 1 as fp16 pairs
         const uint32_t flip = prm.signed_in ? 0x80808080u : 0u;
         const uint32_t sw = static_cast<uint32_t>((t >> 1) & 3);
         uint32_t slab = 0, rs = 0, rph = 0;

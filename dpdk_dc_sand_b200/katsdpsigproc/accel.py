@@ -300,6 +300,9 @@ class IOSlotBase:
     def __init__(self) -> None:
         self.buffer: Optional[DeviceArray] = None
         self.is_bound = False
+        # optional: called by Operation.buffer() when the slot is asked for while unbound (the fused op-sequence leaves
+        # its intermediates unallocated until somebody wants to look at them)
+        self.on_demand = None
 
     def bind(self, buffer: Optional[DeviceArray]) -> None:
         self.buffer = buffer
@@ -413,6 +416,8 @@ class Operation:
 
     def buffer(self, name: str) -> DeviceArray:
         slot = self.slots.get(name) or self.hidden_slots[name]
+        if slot.buffer is None and slot.on_demand is not None:
+            slot.on_demand()
         if slot.buffer is None:
             raise ValueError(f"slot {name} is not bound")
         return slot.buffer
