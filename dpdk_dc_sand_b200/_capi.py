@@ -71,7 +71,8 @@ class FusedOptions(C.Structure):
     """dcbf_fused_options (include/dcbf.h)."""
 
     _fields_ = [("struct_size", C.c_size_t), ("batch_dt_s", C.POINTER(C.c_double)), ("beam_weights", C.c_void_p),
-                ("beam_gains", C.c_void_p), ("beams_q8", C.c_void_p), ("saturated", C.c_void_p)]
+                ("beam_gains", C.c_void_p), ("beams_q8", C.c_void_p), ("saturated", C.c_void_p),
+                ("sample_dt_s", C.c_double)]
 
 
 SIGNATURES["dcbf_fused_ex"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -189,8 +190,9 @@ def beamform(reordered, coeff, beams, n_batches, n_chans, n_samples, n_ants, n_b
 
 def fused_ex(samples, delay_vals, beams, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id,
              sample_period, flags=0, stream=None, batch_dt=None, weights=None, gains=None, beams_q8=None,
-             saturated=None) -> None:
-    """dcbf_fused_ex: any combination of per-heap times, per-(beam, antenna) weights and int8 output."""
+             saturated=None, sample_dt=0.0) -> None:
+    """dcbf_fused_ex: any combination of per-heap (and, with ``sample_dt``, per-time-tile) times, per-(beam, antenna)
+    weights and int8 output."""
     opts = FusedOptions()
     opts.struct_size = C.sizeof(FusedOptions)
     dt = _dt_array(batch_dt, n_batches) if batch_dt is not None else None  # keep alive until the call returns
@@ -200,16 +202,17 @@ def fused_ex(samples, delay_vals, beams, n_batches, n_ants, n_chans, n_chans_tot
     opts.beam_gains = _ptr(gains) if gains is not None else None
     opts.beams_q8 = _ptr(beams_q8) if beams_q8 is not None else None
     opts.saturated = _ptr(saturated) if saturated is not None else None
+    opts.sample_dt_s = float(sample_dt or 0.0)
     check(load().dcbf_fused_ex(_ptr(samples), _ptr(delay_vals), _ptr(beams) if beams is not None else None, n_batches,
                                n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id, float(sample_period),
                                C.byref(opts), flags, _stream_handle(stream)), "dcbf_fused_ex")
 
 
 def fused(samples, delay_vals, beams, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id,
-          sample_period, flags=0, stream=None, batch_dt=None, weights=None) -> None:
-    if weights is not None:
+          sample_period, flags=0, stream=None, batch_dt=None, weights=None, sample_dt=0.0) -> None:
+    if weights is not None or sample_dt:
         fused_ex(samples, delay_vals, beams, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id,
-                 sample_period, flags, stream, batch_dt=batch_dt, weights=weights)
+                 sample_period, flags, stream, batch_dt=batch_dt, weights=weights, sample_dt=sample_dt)
         return
     if batch_dt is not None:
         check(load().dcbf_fused_tv(_ptr(samples), _ptr(delay_vals), _ptr(beams), n_batches, n_ants, n_chans,

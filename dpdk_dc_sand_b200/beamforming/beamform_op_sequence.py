@@ -81,6 +81,7 @@ class OpSequence(accel.OperationSequence):
         self.fp16_coeff = False
         self.fused = True
         self.batch_times = None
+        self.sample_dt = 0.0
         self.beam_weights = None
         # The fused path never needs the reordered voltages or the coefficients in HBM, so ensure_all_bound() leaves
         # them out; code written against the reference may still ask for them (its own test reads
@@ -128,7 +129,7 @@ class OpSequence(accel.OperationSequence):
             self.buffer("bufin_reorder").buffer, self.buffer("bufin_delay_vals").buffer,
             self.buffer("bufout_mult").buffer, r.n_batches, r.n_ants, r.n_channels_per_stream, c.n_channels,
             r.n_samples_per_channel, c.n_beams, c.xeng_id, c.sample_period, self.flags(), self.command_queue.stream,
-            batch_dt=self.batch_times, weights=weights,
+            batch_dt=self.batch_times, weights=weights, sample_dt=self.sample_dt if self.batch_times is not None else 0.0,
         )
         if self.slots["bufint_data"].is_bound:
             self.prebeamform_reorder()

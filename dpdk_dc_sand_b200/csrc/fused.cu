@@ -139,9 +139,10 @@ struct FusedParams {
     int tma_store;   // 1: epilogue through shared memory + TMA tensor stores; 0: st.global from registers
     int merged;      // hi and lo coefficient rows form ONE N = 2 nt tile per MMA (nt <= 64); the epilogue adds the halves
     int q8_wide;     // q8 only: the N tile is the whole output row (32 / 64 / 128 bytes): one box per 32 rows
-    int hg_count;    // kStream: groups of <= 2 time tiles per (channel, N tile)
-    int sb_count;    // coefficient sets per (channel, N tile): 1, or B with time-varying steering
-    int ub;          // batches sharing one coefficient set: B, or 1 with time-varying steering
+    int hg_count;    // kStream: groups of <= hg_size time tiles per (channel, N tile)
+    int hg_size;     // 2, or 1 when every time tile has its own coefficient set (sub-heap time-varying steering)
+    int sb_count;    // coefficient sets per (channel, N tile): 1; B with per-heap times; B * ht_count with per-tile times
+    int set_tiles;   // accumulator tiles (batch, time tile) sharing one coefficient set: B * ht_count, ht_count or 1
     int raw_stages;  // depth of the raw TMA ring: kRawStages + extra stages placed behind the B tiles
     // whole-tile-set mode: the first n_whole channels are units of their own; each of the remaining C - n_whole
     // channels is cut into `split` units along its list of tile_count accumulator tiles (N tile, batch, time tile), so
@@ -151,7 +152,9 @@ struct FusedParams {
     int pdl_wait;    // 1: wait for the preceding kernel of the stream (griddepcontrol.wait) after the prologue
     int raw_extra_off;  // byte offset of the first extra stage inside each 64 KiB B buffer
     uint32_t inv_a;     // floor(2^32 / A) + 1: e / A == umulhi(e, inv_a) for every entry index of an N tile (A >= 2)
-    float dt_hi[DCBF_MAX_TV_BATCHES], dt_lo[DCBF_MAX_TV_BATCHES];  // per-batch time offset (s) as a float pair
+    double dt_s[DCBF_MAX_TV_BATCHES];  // time-varying steering: time offset (s) of every batch (heap)
+    double sample_dt;                  // ... and seconds per sample inside a heap: != 0 gives every 128-sample time tile its
+                                       // own coefficient set, evaluated at the tile's centre
     double chan_centre;      // absolute index of local channel 0, minus N/2
     double turns_per_delay;  // -1 / (N * Ts): half-turns of phase per (second of delay x channel offset)
 };
@@ -177,81 +180,115 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// kCoefScale * sin(pi (r + small)), kCoefScale * cos(pi (r + small)) for |r| < 2^20 half-turns and a tiny correction
-// `small`.  Quadrant split q = rint(2r), t = r - q/2 (exact) + small in [-1/4, 1/4], odd/even Taylor polynomials in t
-// (truncation < 2e-9 and 2e-10) whose constants carry the power-of-two scale (same roundings as unscaled), then the
-// quadrant rotation.  Absolute error <= ~1e-7 of the unscaled value; no special cases (r is finite here).
-__device__ __forceinline__ void sincospi_reduced(float r, float small, float* sn, float* cs) {
+constexpr double kInvPi = 0.318309886183790671538;
+constexpr float kInvPiHi = static_cast<float>(kInvPi);
+constexpr float kInvPiLo = static_cast<float>(kInvPi - static_cast<double>(kInvPiHi));
+constexpr float kRint = 12582912.0f;  // 1.5 * 2^23: x + kRint - kRint = rint(x), and the low mantissa bits of x + kRint hold it
+
+// Steering phase in half-turns:  x = delay * scale + phase / pi   with   scale = (ch - N/2) * (-1 / (N Ts))
+// (reference: beamformer/unit_test/coeff_generator_cpu.py:143-165), delivered as a quadrant q = rint(2x) (its low two
+// bits are what matter) and the remainder t = x - q/2 in [-1/4, 1/4].  The product delay * scale reaches tens to
+// thousands of half-turns, so it is evaluated as a float pair (scale = s_hi + s_lo, exact FMA residual of the big term,
+// which is reduced mod 2 exactly); no float64 instruction on this path.
+//   static steering (kPair = false): t = (r0 - k/2) + u with r0 = big term mod 2, u = phase/pi + residuals and
+//     k = rint(2 (r0 + u)): two roundings at magnitude <= 1.25 and 0.25 -> angle error <= 2.8e-7 rad for |phase| <= pi
+//     (rms 4e-8; measured against float64 over 4e6 random entries), 6e-7 rad up to |phase| = 4 pi;
+//   per-heap times (kPair = true): delay and phase are float pairs themselves and the sum r0 + phase/pi keeps its
+//     rounding error (two-sum): angle error ~1e-7 rad.
+// Returns false when an operand is outside the range these tricks cover (|delay * scale| >= 2^20 half-turns, i.e.
+// milliseconds of delay, or |phase| >= 4 pi resp. 2^20 pi); the caller then redoes the entry with steer_tq_f64.
+template <bool kPair>
+__device__ __forceinline__ bool steer_tq_fast(float d_hi, float d_lo, float ph_hi, float ph_lo, float s_hi, float s_lo, float* t,
+                                              int* q) {
+    const float p = d_hi * s_hi;
+    float e = fmaf(d_hi, s_hi, -p);  // exact residual of p
+    e = fmaf(d_hi, s_lo, e);
+    if (kPair) e = fmaf(d_lo, s_hi, e);
+    e = fmaf(ph_hi, kInvPiLo, e);
+    if (kPair) e = fmaf(ph_lo, kInvPiHi, e);
+    const float qf = fmaf(p, 0.5f, kRint) - kRint;  // rint(p / 2)
+    const float r0 = fmaf(qf, -2.0f, p);            // p mod 2 in [-1, 1], exact
+    if (!kPair) {
+        const float u = fmaf(ph_hi, kInvPiHi, e);
+        const float z = fmaf(r0 + u, 2.0f, kRint);
+        *q = __float_as_int(z);
+        *t = fmaf(z - kRint, -0.5f, r0) + u;
+        return (fabsf(p) < 1048576.0f) & (fabsf(u) < 4.0f);
+    } else {
+        const float u = ph_hi * kInvPiHi;
+        e += fmaf(ph_hi, kInvPiHi, -u);  // exact residual of u
+        const float s1 = r0 + u;
+        const float bb = s1 - r0;
+        const float err = (r0 - (s1 - bb)) + (u - bb);  // rounding error of s1 (two-sum)
+        const float z = fmaf(s1, 2.0f, kRint);
+        *q = __float_as_int(z);
+        *t = fmaf(z - kRint, -0.5f, s1) + (e + err);
+        return (fabsf(p) < 1048576.0f) & (fabsf(u) < 1048576.0f);
+    }
+}
+// The same in float64, for operands outside the range of steer_tq_fast (nothing physical; any finite input works).
+// (Out of line and by value: a pointer result would force the callers' (t, q) arrays into local memory.)
+struct Tq {
+    float t;
+    int q;
+};
+template <bool kPair>
+__device__ __noinline__ Tq steer_tq_f64(float d_hi, float d_lo, float ph_hi, float ph_lo, double scale) {
+    const double dd = kPair ? static_cast<double>(d_hi) + static_cast<double>(d_lo) : static_cast<double>(d_hi);
+    const double pp = kPair ? static_cast<double>(ph_hi) + static_cast<double>(ph_lo) : static_cast<double>(ph_hi);
+    const double x = fma(dd, scale, pp * kInvPi);
+    const double xr = x - 2.0 * rint(0.5 * x);  // [-1, 1]
+    const double k = rint(2.0 * xr);
+    Tq r;
+    r.t = static_cast<float>(fma(k, -0.5, xr));
+    r.q = static_cast<int>(k);
+    return r;
+}
+
+// kCoefScale * (sin, cos)(pi (t + q/2)) for t in [-1/4, 1/4]: odd / even minimax polynomials in t of degree 7 / 6
+// (fit error 1.8e-9 / 3.2e-8, 9e-8 as evaluated in float32; their constants carry the power-of-two scale, same
+// roundings as unscaled), then the quadrant rotation.  The sign of the sine is returned flipped (`nsn` = -sin): that is
+// the value the B operand holds next to the cosine.
+__device__ __forceinline__ void sincos_quadrant(float t, int q, float* nsn, float* cs) {
     constexpr float K = kCoefScale;
-    const float z = fmaf(r, 2.0f, 12582912.0f);  // 1.5 * 2^23: the low mantissa bits now hold rint(2r)
-    const int q = __float_as_int(z);
-    const float t = fmaf(z - 12582912.0f, -0.5f, r) + small;
     const float s = t * t;
-    float ps = fmaf(s, K * 0.0821458866f, K * -0.599264529f);   // pi^9/9!, -pi^7/7!
-    ps = fmaf(ps, s, K * 2.55016404f);                           // pi^5/5!
-    ps = fmaf(ps, s, K * -5.16771278f);                          // -pi^3/3!
-    ps = fmaf(ps * s, t, t * (K * 3.14159274f));                 // t*pi + t*s*(...)
-    float pc = fmaf(s, K * -0.0258068914f, K * 0.235330630f);    // -pi^10/10!, pi^8/8!
-    pc = fmaf(pc, s, K * -1.33526277f);                          // -pi^6/6!
-    pc = fmaf(pc, s, K * 4.05871213f);                           // pi^4/4!
-    pc = fmaf(pc, s, K * -4.93480220f);                          // -pi^2/2!
+    float ps = fmaf(s, K * -5.8882538010e-01f, K * 2.5497494840e+00f);
+    ps = fmaf(ps, s, K * -5.1677078199e+00f);
+    ps = fmaf(s, ps, K * 3.14159274f);
+    ps *= t;
+    float pc = fmaf(s, K * -1.3072800178e+00f, K * 4.0577017906e+00f);
+    pc = fmaf(pc, s, K * -4.9347918159e+00f);
     pc = fmaf(pc, s, K);
     const bool swap = q & 1;
     const float a = swap ? pc : ps, b = swap ? ps : pc;
     // q mod 4: 0 -> (s, c); 1 -> (c, -s); 2 -> (-s, -c); 3 -> (-c, s)
-    *sn = __int_as_float(__float_as_int(a) ^ ((q << 30) & 0x80000000));
+    *nsn = __int_as_float(__float_as_int(a) ^ (~(q << 30) & 0x80000000));
     *cs = __int_as_float(__float_as_int(b) ^ (((q + 1) << 30) & 0x80000000));
 }
 
-constexpr double kInvPi = 0.318309886183790671538;
-constexpr float kInvPiHi = static_cast<float>(kInvPi);
-constexpr float kInvPiLo = static_cast<float>(kInvPi - static_cast<double>(kInvPiHi));
+// One (beam, antenna) coefficient -> the four 32-bit words of the B operand: rows n = 2m (k = 2a: cos, 2a+1: -sin) and
+// n = 2m+1 (sin, cos), each as fp16 hi and fp16 residual (lo).
+__device__ __forceinline__ void coef_words(float nsn, float cs, uint32_t* hi0, uint32_t* hi1, uint32_t* lo0, uint32_t* lo1) {
+    const uint32_t hi = pack_half2(cs, nsn);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    const float rc = cs - hf.x, rs = nsn - hf.y;
+    *hi0 = hi;
+    *hi1 = pack_half2(-nsn, cs);  // (same roundings as hi: the halves swapped, the sine's sign flipped)
+    *lo0 = pack_half2(rc, rs);
+    *lo1 = pack_half2(-rs, rc);
+}
 
-// Steering phase in half-turns, reduced mod 2:  rot/pi = delay * scale + phase/pi   with
-// scale = (ch - N/2) * (-1/(N Ts))   (reference: beamformer/unit_test/coeff_generator_cpu.py:143-165).
-// Evaluated to float64 accuracy WITHOUT float64 instructions: scale = s_hi + s_lo and 1/pi are split into float
-// pairs, products carry their exact FMA residuals, the big term is reduced mod 2 exactly, and the rounding of
-// the final sum is captured by a two-sum.  Result: r (|r| <= 2) plus a correction `small` for sincospi_reduced.
-// With kPair the delay and the phase are float pairs themselves (time-varying steering).
-// Delays beyond ~1e6 half-turns of phase (milliseconds; nothing physical) take the float64 path.
-template <bool kPair>
-__device__ __forceinline__ void steer_phase_f64(float d_hi, float d_lo, float ph_hi, float ph_lo, double scale, float* r,
-                                                float* small) {
-    const double dd = kPair ? static_cast<double>(d_hi) + static_cast<double>(d_lo) : static_cast<double>(d_hi);
-    const double pp = kPair ? static_cast<double>(ph_hi) + static_cast<double>(ph_lo) : static_cast<double>(ph_hi);
-    const double x = fma(dd, scale, pp * kInvPi);
-    const double xr = x - 2.0 * rint(0.5 * x);
-    *r = static_cast<float>(xr);
-    *small = static_cast<float>(xr - static_cast<double>(*r));
-}
-// The float-pair evaluation alone, branch-free; returns false when the operands are out of its range (the caller then
-// redoes the entry with steer_phase_f64).  Keeping the test out of the arithmetic lets a whole batch of entries be
-// scheduled as one straight-line region (their dependent FMA chains interleave).
-template <bool kPair>
-__device__ __forceinline__ bool steer_phase_fast(float d_hi, float d_lo, float ph_hi, float ph_lo, float s_hi, float s_lo,
-                                                 float* r, float* small) {
-    const float p = d_hi * s_hi;
-    const float u = ph_hi * kInvPiHi;
-    float e = fmaf(d_hi, s_hi, -p);       // exact residual of p
-    e = fmaf(d_hi, s_lo, e);
-    if (kPair) e = fmaf(d_lo, s_hi, e);
-    e += fmaf(ph_hi, kInvPiHi, -u);       // exact residual of u
-    e = fmaf(ph_hi, kInvPiLo, e);
-    if (kPair) e = fmaf(ph_lo, kInvPiHi, e);
-    const float qf = fmaf(p, 0.5f, 12582912.0f) - 12582912.0f;  // rint(p / 2)
-    const float r0 = fmaf(qf, -2.0f, p);                         // p mod 2 in [-1, 1], exact
-    const float s1 = r0 + u;
-    const float bb = s1 - r0;
-    const float err = (r0 - (s1 - bb)) + (u - bb);               // rounding error of s1 (two-sum)
-    *r = s1;
-    *small = e + err;
-    return fabsf(p) < 1048576.0f && fabsf(u) < 1048576.0f;
-}
-template <bool kPair>
-__device__ __forceinline__ void steer_phase(float d_hi, float d_lo, float ph_hi, float ph_lo, float s_hi, float s_lo,
-                                            double scale, float* r, float* small) {
-    if (!steer_phase_fast<kPair>(d_hi, d_lo, ph_hi, ph_lo, s_hi, s_lo, r, small))
-        steer_phase_f64<kPair>(d_hi, d_lo, ph_hi, ph_lo, scale, r, small);
+// Time offset of a coefficient set as a float pair: the heap's, or (sample_dt != 0) that of the centre of time tile h of
+// the heap (the native precursor steps its coefficients per timestamp, dt = t * SAMPLING_PERIOD * FFT_SIZE,
+// beamformer_coefficient_generator/BeamformerKernels.cu:153-156; here per 128-sample MMA tile).
+__device__ __forceinline__ void set_time(const FusedParams& prm, int b, int h, float* dt_hi, float* dt_lo) {
+    double dt = prm.dt_s[b];
+    if (prm.sample_dt != 0.0) {
+        const int n = min(kTileT, prm.T - h * kTileT);
+        dt += (static_cast<double>(h * kTileT) + 0.5 * static_cast<double>(n - 1)) * prm.sample_dt;
+    }
+    *dt_hi = static_cast<float>(dt);
+    *dt_lo = static_cast<float>(dt - static_cast<double>(*dt_hi));
 }
 
 // base + rate * dt as a float pair (dt = dt_hi + dt_lo): the model value at a heap's timestamp
@@ -370,7 +407,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             const uint32_t pc = static_cast<uint32_t>(prm.nt_count * prm.hg_count);
             uc = w / pc;
             const int r_ = static_cast<int>(w - uc * pc), it_ = r_ / prm.hg_count;
-            m0 = it_ * (prm.nt >> 1), h0 = 2 * (r_ - it_ * prm.hg_count), hn = min(2, prm.ht_count - h0);
+            m0 = it_ * (prm.nt >> 1), h0 = prm.hg_size * (r_ - it_ * prm.hg_count), hn = min(prm.hg_size, prm.ht_count - h0);
         } else {
             int j0 = 0;
             uc = w;
@@ -429,12 +466,12 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             *j0 = s_ * prm.tile_count / prm.split, *j1 = (s_ + 1) * prm.tile_count / prm.split;
         }
     };
-    const int bh_count = prm.ub * prm.ht_count;  // accumulator tiles per coefficient set
+    const int bh_count = prm.set_tiles;  // accumulator tiles per coefficient set
     // kStream: unit -> channel, N tile, first time tile and number of time tiles of the group
     auto unit_decode = [&](uint32_t w, uint32_t* uc, int* uit, int* uh0, int* uhn) {
         const uint32_t c_ = w / per_chan, r_ = w - c_ * per_chan;
         const int it_ = static_cast<int>(r_) / prm.hg_count, hg_ = static_cast<int>(r_) - it_ * prm.hg_count;
-        *uc = c_, *uit = it_, *uh0 = 2 * hg_, *uhn = min(2, prm.ht_count - 2 * hg_);
+        *uc = c_, *uit = it_, *uh0 = prm.hg_size * hg_, *uhn = min(prm.hg_size, prm.ht_count - prm.hg_size * hg_);
     };
     const uint32_t part_bytes = static_cast<uint32_t>(nt * 128);            // one part of a k-block: [nt rows][128 B]
     const uint32_t bop_kb_bytes = static_cast<uint32_t>(parts) * part_bytes;  // one k-block: [part][nt rows][128 B]
@@ -1074,6 +1111,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             // takes beams w, w + 16, ...: 4 beams per warp and step.  Coefficients are regenerated per batch in
             // this mode (the ring does not keep them).
             constexpr int kPer = 64 / kCoeffWarps;
+            static_assert(kPer == 4, "the K-streamed coefficient step is written for four entries per thread");
             const float ks_inv_gmax = kQ8 && ctl->q8_gmax > 0.f ? 1.0f / ctl->q8_gmax : 0.f;
             const int wl = warp - kCoeffWarp0;
             const int mt = nt >> 1;
@@ -1131,70 +1169,112 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 unit_decode(w, &c, &it, &uh0, &uhn);
                 const double scale = (static_cast<double>(c) + prm.chan_centre) * prm.turns_per_delay;
                 const float s_hi = static_cast<float>(scale), s_lo = static_cast<float>(scale - static_cast<double>(s_hi));
-                {
-                    const int m0 = it * mt, mte = min(mt, M - m0);
-                    const float* w_tile = prm.weights ? prm.weights + static_cast<size_t>(m0) * A : nullptr;
-                    for (int bkb = 0; bkb < B * prm.kb_count && ok; ++bkb, ++kstep) {
-                        const int kb = bkb % prm.kb_count;
+                const int m0 = it * mt, mte = min(mt, M - m0);
+                const float* w_tile = prm.weights ? prm.weights + static_cast<size_t>(m0) * A : nullptr;
+                const bool scaled = kQ8 || w_tile != nullptr;
+                for (int b = 0; b < B && ok; ++b) {
+                    float dt_hi = 0.f, dt_lo = 0.f;
+                    if constexpr (kTv) set_time(prm, b, uh0, &dt_hi, &dt_lo);  // this batch's (and time tile's) coefficients
+                    for (int kb = 0; kb < prm.kb_count && ok; ++kb, ++kstep) {
                         const uint32_t slot = kstep % kBopSlots;
-                        float dt_hi = 0.f, dt_lo = 0.f;
-                        if constexpr (kTv) {  // per-heap time: this step's coefficients belong to batch bkb / kb_count
-                            dt_hi = prm.dt_hi[bkb / prm.kb_count];
-                            dt_lo = prm.dt_lo[bkb / prm.kb_count];
-                        }
                         Dv v[kPer];
 #pragma unroll
                         for (int u = 0; u < kPer; ++u) v[u] = nxt[u];
                         advance_cursor();
                         issue_loads();
-                        ok = mbar_wait<kProf>(bar(kBopEmpty + slot), ((kstep / kBopSlots) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + slot, ps + 0);
-                        if (!ok) break;
                         const int a = kKbAnts * kb + lane;
-                        // beam m = wl + 16 u: row 2 m has the same swizzle phase for every u, so the four words of
-                        // entry u sit at a constant 4096-byte stride from those of entry 0
-                        const uint32_t row0 = 2u * static_cast<uint32_t>(wl);
-                        const uint32_t d_base = bop_base + slot * kBopSlotBytes + row0 * 128u +
-                                                (((static_cast<uint32_t>(lane) >> 2) ^ (row0 & 7u)) << 4) +
-                                                ((static_cast<uint32_t>(lane) & 3u) << 2);
-                        if (a < A) {
+                        // optional real factor per entry: ?beam-weights and / or the requantisation gain of the beam
+                        // relative to the largest one (tiny tables that stay in L1 / L2)
+                        float f[kPer];
+                        if (scaled) {
 #pragma unroll
                             for (int u = 0; u < kPer; ++u) {
                                 const int m = wl + kCoeffWarps * u;
-                                if (m < mte) {
-                                    float r, small, sn, cs;
-                                    if (prm.dbg & 2) {
-                                        sn = v[u].x, cs = v[u].y;
+                                f[u] = 1.0f;
+                                if (m < mte && a < A) {
+                                    if (w_tile) f[u] = __ldg(w_tile + static_cast<size_t>(m) * A + a);
+                                    if constexpr (kQ8) f[u] *= __ldg(prm.gains + m0 + m) * ks_inv_gmax;
+                                }
+                            }
+                        }
+                        ok = mbar_wait<kProf>(bar(kBopEmpty + slot), ((kstep / kBopSlots) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + slot, ps + 0);
+                        if (!ok) break;
+                        // beam m = wl + 16 u: row 2 m has the same swizzle phase for every u, so the four words of
+                        // entry u sit at a constant 4096-byte stride from those of entry 0 (immediate offsets)
+                        const uint32_t row0 = 2u * static_cast<uint32_t>(wl);
+                        const uint32_t d0 = bop_base + slot * kBopSlotBytes + row0 * 128u +
+                                            (((static_cast<uint32_t>(lane) >> 2) ^ (row0 & 7u)) << 4) +
+                                            ((static_cast<uint32_t>(lane) & 3u) << 2);
+                        const uint32_t d1 = (d0 + 128u) ^ 16u;  // row + 1: swizzle phase (row & 7) | 1
+                        const uint32_t d0l = d0 + part_bytes, d1l = d1 + part_bytes;
+                        // kGroup entries at a time as one straight-line region, so that their dependent chains interleave:
+                        // reduced phases (float pairs; a rare out-of-range group is redone in float64), sin / cos, fp16 split
+                        constexpr int kGroup = kTv ? 2 : 4;
+                        if (!(prm.dbg & 2)) {
+#pragma unroll
+                            for (int g = 0; g < kPer; g += kGroup) {
+                                float t[kGroup];
+                                int q[kGroup];
+                                bool in_range = true;
+                                if constexpr (kTv) {
+                                    float d_hi[kGroup], d_lo[kGroup], ph_hi[kGroup], ph_lo[kGroup];
+#pragma unroll
+                                    for (int u = 0; u < kGroup; ++u) {
+                                        advance_model(v[g + u].x, v[g + u].y, dt_hi, dt_lo, &d_hi[u], &d_lo[u]);
+                                        advance_model(v[g + u].z, v[g + u].w, dt_hi, dt_lo, &ph_hi[u], &ph_lo[u]);
+                                        in_range &= steer_tq_fast<true>(d_hi[u], d_lo[u], ph_hi[u], ph_lo[u], s_hi, s_lo, &t[u], &q[u]);
+                                    }
+                                    if (!in_range) {
+#pragma unroll
+                                        for (int u = 0; u < kGroup; ++u) {
+                                            const Tq r = steer_tq_f64<true>(d_hi[u], d_lo[u], ph_hi[u], ph_lo[u], scale);
+                                            t[u] = r.t, q[u] = r.q;
+                                        }
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int u = 0; u < kGroup; ++u)
+                                        in_range &= steer_tq_fast<false>(v[g + u].x, 0.f, v[g + u].y, 0.f, s_hi, s_lo, &t[u], &q[u]);
+                                    if (!in_range) {
+#pragma unroll
+                                        for (int u = 0; u < kGroup; ++u) {
+                                            const Tq r = steer_tq_f64<false>(v[g + u].x, 0.f, v[g + u].y, 0.f, scale);
+                                            t[u] = r.t, q[u] = r.q;
+                                        }
+                                    }
+                                }
+                                auto emit = [&](auto gu_c, int u) {
+                                    constexpr int gu = decltype(gu_c)::value;
+                                    float nsn, cs;
+                                    sincos_quadrant(t[u], q[u], &nsn, &cs);
+                                    if (scaled) {
+                                        nsn *= f[gu];
+                                        cs *= f[gu];
+                                    }
+                                    uint32_t hi0, hi1, lo0, lo1;
+                                    coef_words(nsn, cs, &hi0, &hi1, &lo0, &lo1);
+                                    if (a < A && wl + kCoeffWarps * gu < mte) {
+                                        constexpr int kOff = gu * (2 * kCoeffWarps * 128);
+                                        st_shared_u32_off<kOff>(d0, hi0);
+                                        st_shared_u32_off<kOff>(d1, hi1);
+                                        if (parts > 1) {
+                                            st_shared_u32_off<kOff>(d0l, lo0);
+                                            st_shared_u32_off<kOff>(d1l, lo1);
+                                        }
+                                    }
+                                };
+                                if constexpr (kGroup == 4) {
+                                    emit(std::integral_constant<int, 0>{}, 0);
+                                    emit(std::integral_constant<int, 1>{}, 1);
+                                    emit(std::integral_constant<int, 2>{}, 2);
+                                    emit(std::integral_constant<int, 3>{}, 3);
+                                } else {
+                                    if (g == 0) {
+                                        emit(std::integral_constant<int, 0>{}, 0);
+                                        emit(std::integral_constant<int, 1>{}, 1);
                                     } else {
-                                    if constexpr (kTv) {
-                                        float d_hi, d_lo, ph_hi, ph_lo;
-                                        advance_model(v[u].x, v[u].y, dt_hi, dt_lo, &d_hi, &d_lo);
-                                        advance_model(v[u].z, v[u].w, dt_hi, dt_lo, &ph_hi, &ph_lo);
-                                        steer_phase<true>(d_hi, d_lo, ph_hi, ph_lo, s_hi, s_lo, scale, &r, &small);
-                                    } else {
-                                        steer_phase<false>(v[u].x, 0.f, v[u].y, 0.f, s_hi, s_lo, scale, &r, &small);
-                                    }
-                                    sincospi_reduced(r, small, &sn, &cs);
-                                    }
-                                    if (w_tile) {
-                                        const float w = __ldg(w_tile + static_cast<size_t>(m) * A + a);
-                                        cs *= w;
-                                        sn *= w;
-                                    }
-                                    if constexpr (kQ8) {  // requantisation gain of this beam, relative to the largest one
-                                        const float g = __ldg(prm.gains + m0 + m) * ks_inv_gmax;
-                                        cs *= g;
-                                        sn *= g;
-                                    }
-                                    const uint32_t hi = pack_half2(cs, sn);
-                                    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-                                    const uint32_t lo = pack_half2(cs - hf.x, sn - hf.y);
-                                    const uint32_t d0 = d_base + static_cast<uint32_t>(u) * (2u * kCoeffWarps * 128u);
-                                    const uint32_t d1 = (d0 + 128u) ^ 16u;
-                                    st_shared_u32(d0, hi ^ 0x80000000u);
-                                    st_shared_u32(d1, __byte_perm(hi, 0u, 0x1032u));
-                                    if (parts > 1) {
-                                        st_shared_u32(d0 + part_bytes, lo ^ 0x80000000u);
-                                        st_shared_u32(d1 + part_bytes, __byte_perm(lo, 0u, 0x1032u));
+                                        emit(std::integral_constant<int, 2>{}, 0);
+                                        emit(std::integral_constant<int, 3>{}, 1);
                                     }
                                 }
                             }
@@ -1283,52 +1363,54 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             const float* g_tile = nullptr;
             const float q8_inv_gmax = kQ8 && ctl->q8_gmax > 0.f ? 1.0f / ctl->q8_gmax : 0.f;
             const bool two_parts = parts > 1;
-            // reduced phase (r, small) of one entry, float pairs only; false: out of range, redo in float64
-            auto phase_fast = [&](const Dv& dv, float* r, float* small) {
+            // quadrant + remainder of one entry's steering phase, float pairs only; false: out of range, redo in float64
+            auto phase_fast = [&](const Dv& dv, float* t, int* q) {
                 if constexpr (kTv) {
                     float d_hi, d_lo, ph_hi, ph_lo;
                     advance_model(dv.x, dv.y, dt_hi, dt_lo, &d_hi, &d_lo);
                     advance_model(dv.z, dv.w, dt_hi, dt_lo, &ph_hi, &ph_lo);
-                    return steer_phase_fast<true>(d_hi, d_lo, ph_hi, ph_lo, s_hi, s_lo, r, small);
+                    return steer_tq_fast<true>(d_hi, d_lo, ph_hi, ph_lo, s_hi, s_lo, t, q);
                 } else {
-                    return steer_phase_fast<false>(dv.x, 0.f, dv.y, 0.f, s_hi, s_lo, r, small);
+                    return steer_tq_fast<false>(dv.x, 0.f, dv.y, 0.f, s_hi, s_lo, t, q);
                 }
             };
-            auto phase_f64 = [&](const Dv& dv, float* r, float* small) {
+            auto phase_f64 = [&](const Dv& dv) {
                 if constexpr (kTv) {
                     float d_hi, d_lo, ph_hi, ph_lo;
                     advance_model(dv.x, dv.y, dt_hi, dt_lo, &d_hi, &d_lo);
                     advance_model(dv.z, dv.w, dt_hi, dt_lo, &ph_hi, &ph_lo);
-                    steer_phase_f64<true>(d_hi, d_lo, ph_hi, ph_lo, scale, r, small);
+                    return steer_tq_f64<true>(d_hi, d_lo, ph_hi, ph_lo, scale);
                 } else {
-                    steer_phase_f64<false>(dv.x, 0.f, dv.y, 0.f, scale, r, small);
+                    return steer_tq_f64<false>(dv.x, 0.f, dv.y, 0.f, scale);
                 }
             };
-            // reduced phase of one (beam, antenna) entry -> four 32-bit words of the B tile at d0 (row 2m) and d1 (row 2m+1)
-            auto finish = [&](float r, float small, uint32_t d0, int e) {
-                float sn, cs;
-                sincospi_reduced(r, small, &sn, &cs);
-                if (w_tile) {  // ?beam-weights: real weight of this (beam, antenna); the table is tiny and stays in L1/L2
+            // (quadrant, remainder) of one (beam, antenna) entry -> four 32-bit words of the B tile at d0 (row 2m) and d1
+            // (row 2m+1); `valid` only guards the stores and the optional table reads (the arithmetic is branch-free)
+            auto finish = [&](float t, int q, uint32_t d0, int e, bool valid) {
+                float nsn, cs;
+                sincos_quadrant(t, q, &nsn, &cs);
+                if (w_tile && valid) {  // ?beam-weights: real weight of this (beam, antenna); the table is tiny and stays in L1/L2
                     const float w = __ldg(w_tile + e);
                     cs *= w;
-                    sn *= w;
+                    nsn *= w;
                 }
                 if constexpr (kQ8) {  // requantisation gain of this entry's beam, relative to the largest one
-                    const float g = __ldg(g_tile + (A == 1 ? static_cast<uint32_t>(e) : __umulhi(static_cast<uint32_t>(e), prm.inv_a))) * q8_inv_gmax;
-                    cs *= g;
-                    sn *= g;
+                    if (valid) {
+                        const float g = __ldg(g_tile + (A == 1 ? static_cast<uint32_t>(e) : __umulhi(static_cast<uint32_t>(e), prm.inv_a))) * q8_inv_gmax;
+                        cs *= g;
+                        nsn *= g;
+                    }
                 }
-                // fp16 hi + fp16 residual of (cos, sin)
-                const uint32_t hi = pack_half2(cs, sn);
-                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-                const uint32_t lo = pack_half2(cs - hf.x, sn - hf.y);
-                // B^T rows: n = 2m -> (k=2a: cos, k=2a+1: -sin);  n = 2m+1 -> (sin, cos)
+                uint32_t hi0, hi1, lo0, lo1;
+                coef_words(nsn, cs, &hi0, &hi1, &lo0, &lo1);
                 const uint32_t d1 = (d0 + 128u) ^ 16u;  // row + 1: swizzle phase (row & 7) | 1
-                st_shared_u32(d0, hi ^ 0x80000000u);
-                st_shared_u32(d1, __byte_perm(hi, 0u, 0x1032u));
-                if (two_parts) {
-                    st_shared_u32(d0 + part_bytes, lo ^ 0x80000000u);
-                    st_shared_u32(d1 + part_bytes, __byte_perm(lo, 0u, 0x1032u));
+                if (valid) {
+                    st_shared_u32(d0, hi0);
+                    st_shared_u32(d1, hi1);
+                    if (two_parts) {
+                        st_shared_u32(d0 + part_bytes, lo0);
+                        st_shared_u32(d1 + part_bytes, lo1);
+                    }
                 }
             };
             auto b_addr = [&](uint32_t buf, int ml, int a) {
@@ -1338,9 +1420,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             };
             for (int isb = j0 / bh_count, isb_last = (j1 - 1) / bh_count; isb <= isb_last && ok; ++isb, ++step) {
                 const int it = isb / sb_count, sb = isb - it * sb_count;
-                if constexpr (kTv) {
-                    dt_hi = prm.dt_hi[sb];
-                    dt_lo = prm.dt_lo[sb];
+                if constexpr (kTv) {  // set sb of the N tile: batch sb, or (per-tile times) batch sb / ht_count, time tile sb % ht_count
+                    const int sets_per_batch = sb_count / B;
+                    set_time(prm, sb / sets_per_batch, sb % sets_per_batch, &dt_hi, &dt_lo);
                 }
                 const uint32_t bb = step % kBopBufs;
                 const int m0 = it * mt;
@@ -1393,22 +1475,21 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     const bool whole = (e0 - ctid) + kStride * kBatch <= entries;  // batch inside the tile (uniform over the role)
 #pragma unroll
                     for (int g = 0; g < kBatch; g += kIlp) {
-                        float ph_r[kIlp], ph_s[kIlp];
+                        float ph_t[kIlp];
+                        int ph_q[kIlp];
                         bool in_range = true;
 #pragma unroll
-                        for (int u = 0; u < kIlp; ++u) in_range &= phase_fast(v[g + u], &ph_r[u], &ph_s[u]);
+                        for (int u = 0; u < kIlp; ++u) in_range &= phase_fast(v[g + u], &ph_t[u], &ph_q[u]);
                         if (!in_range) {
 #pragma unroll
-                            for (int u = 0; u < kIlp; ++u) phase_f64(v[g + u], &ph_r[u], &ph_s[u]);
+                            for (int u = 0; u < kIlp; ++u) {
+                                const Tq r = phase_f64(v[g + u]);
+                                ph_t[u] = r.t, ph_q[u] = r.q;
+                            }
                         }
-                        if (whole) {
 #pragma unroll
-                            for (int u = 0; u < kIlp; ++u) finish(ph_r[u], ph_s[u], d0[g + u], e0 + (g + u) * kStride);
-                        } else {
-#pragma unroll
-                            for (int u = 0; u < kIlp; ++u)
-                                if (e0 + (g + u) * kStride < entries) finish(ph_r[u], ph_s[u], d0[g + u], e0 + (g + u) * kStride);
-                        }
+                        for (int u = 0; u < kIlp; ++u)
+                            finish(ph_t[u], ph_q[u], d0[g + u], e0 + (g + u) * kStride, whole || e0 + (g + u) * kStride < entries);
                     }
                 }
                 if (!ok) break;
@@ -1539,7 +1620,7 @@ int get_encode_fn(EncodeTiledFn* out) {
 
 int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T,
                  int M, long long first_chan, double sample_period, const double* batch_dt_s, unsigned flags,
-                 cudaStream_t s, const QuantisedOut* q8, const float* beam_weights) {
+                 cudaStream_t s, const QuantisedOut* q8, const float* beam_weights, double sample_dt_s) {
     FusedParams p{};
     p.dv = reinterpret_cast<const float4*>(delay_vals);
     p.samples = samples;
@@ -1562,20 +1643,21 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     p.turns_per_delay = -1.0 / (static_cast<double>(N) * sample_period);
     // TMA stores need a 16-byte row pitch (even beam count) and 32-column boxes that stay inside their N tile
     p.sb_count = 1;
-    p.ub = B;
+    p.set_tiles = B * p.ht_count;
+    p.hg_size = 2;
     if (batch_dt_s) {  // time-varying steering: one coefficient set per heap
         if (B > DCBF_MAX_TV_BATCHES) return DCBF_ERR_UNSUPPORTED;
-        p.sb_count = B;
-        p.ub = 1;
-        for (int b = 0; b < B; ++b) {
-            p.dt_hi[b] = static_cast<float>(batch_dt_s[b]);
-            p.dt_lo[b] = static_cast<float>(batch_dt_s[b] - static_cast<double>(p.dt_hi[b]));
-        }
+        const bool per_tile = sample_dt_s != 0.0 && p.ht_count > 1;
+        p.sb_count = per_tile ? B * p.ht_count : B;
+        p.set_tiles = per_tile ? 1 : p.ht_count;
+        p.hg_size = per_tile ? 1 : 2;
+        p.sample_dt = sample_dt_s;
+        for (int b = 0; b < B; ++b) p.dt_s[b] = batch_dt_s[b];
     }
     // Many antennas x beams: a whole B tile set no longer fits 64 KiB with a useful width (the voltages would be
     // re-converted for every narrow N tile).  Stream B by 32-antenna k-blocks instead: N tiles of up to 128 columns.
     const bool kstream = (p.nt_count > 1 || no_whole_tiles) && !(flags & DCBF_FLAG_DEBUG_NO_KSTREAM);
-    p.hg_count = (p.ht_count + 1) / 2;
+    p.hg_count = (p.ht_count + p.hg_size - 1) / p.hg_size;
     if (no_whole_tiles && !kstream) return DCBF_ERR_UNSUPPORTED;  // (the k-block ring itself has no antenna limit)
     if (kstream) {
         const int n_pad = ((2 * M + 15) / 16) * 16;

@@ -175,6 +175,11 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+// (the offset becomes the instruction's immediate)
+template <int kOff>
+__device__ __forceinline__ void st_shared_u32_off(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(kOff) : "memory");
+}
 __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }

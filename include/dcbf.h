@@ -144,6 +144,12 @@ unsigned long long dcbf_fused_q8_bytes(int n_batches, int n_ants, int n_chans, i
 /* General form of the fused call: every optional feature through one options block (zero-initialise, set
  * struct_size = sizeof(dcbf_fused_options), fill what is needed; NULL opts == dcbf_fused).
  *   batch_dt_s    HOST double[n_batches]  per-heap time offsets, as dcbf_fused_tv
+ *   sample_dt_s   seconds between consecutive samples of a heap (the precursor's SAMPLING_PERIOD * FFT_SIZE,
+ *                 beamformer_coefficient_generator/BeamformerKernels.cu:153-156, which re-evaluates its coefficients per
+ *                 timestamp).  Non-zero (needs batch_dt_s = the time of each heap's FIRST sample): every 128-sample
+ *                 time tile of a heap is steered with its own coefficient set, evaluated at the tile's centre
+ *                 batch_dt_s[b] + (t0 + (n - 1) / 2) * sample_dt_s, instead of one set per heap -- the residual phase
+ *                 drift inside a tile is rate * 64 * sample_dt_s.  0 = one set per heap at batch_dt_s[b].
  *   beam_weights  DEVICE float[n_beams][n_ants]  real weight of every input on every beam, multiplied into the
  *                 steering coefficient -- what the control plane's `?beam-weights <stream> w_0 .. w_{A-1}` request carries
  *                 (reference: ngkcs/ngkcs/corr3_servlet.py:140-153, which only forwards it); update it between calls
@@ -156,6 +162,7 @@ typedef struct dcbf_fused_options {
     const float* beam_gains;
     int8_t* beams_q8;
     unsigned long long* saturated;
+    double sample_dt_s;
 } dcbf_fused_options;
 int dcbf_fused_ex(const uint8_t* samples, const float* delay_vals, float* beams, int n_batches, int n_ants,
                   int n_chans, int n_chans_total, int n_samples, int n_beams, int xeng_id, double sample_period,

@@ -242,12 +242,32 @@ def beamform_pipeline(
     acc_dtype=np.float64,
     batch_dt=None,
     weights=None,
+    sample_dt=None,
+    tile=None,
 ) -> np.ndarray:
-    """(B,A,C,T,P,2) u8 + (C,M,A,4) f32 -> (B,P,C,T//16,16,2M) in ``acc_dtype``."""
+    """(B,A,C,T,P,2) u8 + (C,M,A,4) f32 -> (B,P,C,T//16,16,2M) in ``acc_dtype``.
+
+    ``sample_dt`` (with ``batch_dt`` = time of each heap's first sample): the steering follows the delay model INSIDE
+    the heap, sample t of heap b being steered at ``batch_dt[b] + t * sample_dt`` -- what the native precursor's
+    per-timestamp coefficients do (beamformer_coefficient_generator/BeamformerKernels.cu:153-167, dt = t *
+    SAMPLING_PERIOD * FFT_SIZE).  ``tile`` = n restates dcbf_fused_ex's approximation of it instead: one coefficient
+    set per n consecutive samples, evaluated at their centre ``batch_dt[b] + (t0 + (n_t - 1) / 2) * sample_dt``."""
     b, a, c, t, p, x = samples.shape
     m = delay_vals.shape[1]
     re = reorder(samples)
     d = _as_real(re, signed_input, acc_dtype)
+    if batch_dt is not None and sample_dt:
+        dt_flat = d.reshape(b, p, c, t, 2 * a)
+        out = np.empty((b, p, c, t, 2 * m), acc_dtype)
+        step = int(tile) if tile else 1
+        for ib in range(b):
+            for t0 in range(0, t, step):
+                n_t = min(step, t - t0)
+                when = float(batch_dt[ib]) + (t0 + 0.5 * (n_t - 1)) * float(sample_dt)
+                co = steering_coeffs(delay_vals, 1, 1, c, n_channels, a, m, xeng_id, sample_period,
+                                     out_dtype=np.float64, _dt=when, weights=weights)[0, 0].astype(acc_dtype)
+                out[ib, :, :, t0:t0 + n_t] = np.einsum("pctj,cjn->pctn", dt_flat[ib, :, :, t0:t0 + n_t], co)
+        return out.reshape(b, p, c, t // SAMPLES_PER_BLOCK, SAMPLES_PER_BLOCK, 2 * m)
     if batch_dt is not None:
         co = steering_coeffs(delay_vals, b, 1, c, n_channels, a, m, xeng_id, sample_period, out_dtype=np.float64,
                              batch_dt=batch_dt, weights=weights)
