@@ -97,7 +97,8 @@ constexpr int kSlabAnts = 16;  // antennas per raw slab / A stage
 constexpr int kKbAnts = 32;    // antennas per B k-block (128-byte swizzle row of fp16)
 constexpr int kRawStages = 4;      // raw stages with their own shared memory ...
 constexpr int kMaxRawStages = 8;   // ... plus up to 4 more in the unused tail of the two B buffers (narrow N tiles)
-constexpr int kAopStages = 2;
+constexpr int kAopStages = 2;      // A stages with their own shared memory ...
+constexpr int kMaxAopStages = 4;   // ... plus, with K-streamed B, two more behind a B ring of three (not four) slots
 constexpr int kBopBufs = 2;
 constexpr int kBopSlots = 4;    // kStream: B k-block ring (4 x 32 KiB) instead of 2 whole tile sets
 constexpr int kBopSlotBytes = kBopBufs * 64 * 1024 / kBopSlots;
@@ -322,7 +323,7 @@ __device__ __forceinline__ uint32_t quantise4(const uint32_t (&r)[32], int j, fl
 // ------------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------------
-template <bool kProf, bool kTv, bool kQ8, bool kMerged, bool kStream>
+template <bool kProf, bool kTv, bool kQ8, bool kMerged, bool kStream, bool kPair = false>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_constant__ CUtensorMap tm_in,
                       const __grid_constant__ CUtensorMap tm_out) {
@@ -344,9 +345,17 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
 
     // barrier ids (also reported by the watchdog)
     const int kRawFull = 0, kRawEmpty = kRawFull + kMaxRawStages, kAopFull = kRawEmpty + kMaxRawStages,
-              kAopEmpty = kAopFull + kAopStages, kBopFull = kAopEmpty + kAopStages, kBopEmpty = kBopFull + kBopSlots,
+              kAopEmpty = kAopFull + kMaxAopStages, kBopFull = kAopEmpty + kMaxAopStages, kBopEmpty = kBopFull + kBopSlots,
               kAccFull = kBopEmpty + kBopSlots, kAccEmpty = kAccFull + kAccBufs, kNumBars = kAccEmpty + kAccBufs;
-    static_assert(2 * (kMaxRawStages + kAopStages + kBopSlots + kAccBufs) * 8 <= 320, "barrier area");
+    static_assert(2 * (kMaxRawStages + kMaxAopStages + kBopSlots + kAccBufs) * 8 <= 320, "barrier area");
+    // K-streamed B: every slab is a convert -> MMA -> convert round trip (fence, arrive, wake-up, commit), so the depth of
+    // the A ring bounds the slab rate more than the look-ahead of the B ring does (ncu: every role of a two-stage
+    // pipeline sat in its barrier waits).  Four A stages, the two extra ones in the fourth slot of the B ring.
+    constexpr uint32_t kAStages = kStream ? kMaxAopStages : kAopStages;
+    constexpr uint32_t kBSlots = kStream ? 3 : kBopSlots;
+    auto aop_addr = [&](uint32_t as) {
+        return as < kAopStages ? aop_base + as * kAopStageBytes : bop_base + 3u * kBopSlotBytes + (as - kAopStages) * kAopStageBytes;
+    };
     static_assert(320 + sizeof(Control) <= kCtlBytes, "control area");
     // raw stage s: its own 8 KiB for s < kRawStages, else alternately behind the tiles of B buffer 0 / 1
     const uint32_t raw_stages = static_cast<uint32_t>(prm.raw_stages);
@@ -364,17 +373,17 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             mbar_init(bar(kRawFull + s), 1);
             mbar_init(bar(kRawEmpty + s), 4);
         }
-        for (int s = 0; s < kAopStages; ++s) {
-            mbar_init(bar(kAopFull + s), 4);
+        for (int s = 0; s < kMaxAopStages; ++s) {
+            mbar_init(bar(kAopFull + s), kPair ? 8 : 4);  // (a pair's barriers of this kind live in CTA 0 and count both CTAs)
             mbar_init(bar(kAopEmpty + s), 2);  // one tcgen05.commit per MMA warp
         }
         for (int s = 0; s < kBopSlots; ++s) {
-            mbar_init(bar(kBopFull + s), kCoeffWarps);
+            mbar_init(bar(kBopFull + s), kPair ? 2 * kCoeffWarps : kCoeffWarps);
             mbar_init(bar(kBopEmpty + s), 2);
         }
         for (int s = 0; s < kAccBufs; ++s) {
             mbar_init(bar(kAccFull + s), 2);
-            mbar_init(bar(kAccEmpty + s), 4);
+            mbar_init(bar(kAccEmpty + s), kPair ? 8 : 4);
         }
         ctl->abort = 0;
         ctl->chan_pub = 0;
@@ -392,10 +401,13 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         }
         fence_proxy_async_smem();
     }
-    if (warp == kMmaWarp) tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
+    if (warp == kMmaWarp) {
+        if (kPair) tmem_alloc_pair(smem_u32(&ctl->tmem_base), kTmemCols);
+        else tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
+    }
     if (warp == kProducerWarp && lane == 0) prefetch_tensormap(&tm_in);
     if (warp == kEpilogueWarp0 && lane == 0) prefetch_tensormap(&tm_out);
-    if (warp == kCoeffWarp0 + 1 && prm.pdl_wait && !(prm.dbg & 8)) {
+    if (!kPair && warp == kCoeffWarp0 + 1 && prm.pdl_wait && !(prm.dbg & 8)) {
         // The first unit's inputs -> L2 before anything else asks for memory (and, with programmatic dependent launch,
         // while the preceding kernel still drains: a prefetch returns no data, and L2 is the coherence point of global
         // memory, so this is safe ahead of the dependency wait).  The launch is otherwise serial until the first B tile
@@ -441,9 +453,15 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         if (lane == 0) ctl->q8_gmax = g;
     }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync();  // the peer's barriers are initialised before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
+    // CTA pair (kPair): the two CTAs of a cluster share every unit -- CTA r converts time tile uh0 + r and generates the
+    // coefficients of beams [64 r, 64 r + 64) of the N tile; CTA 0 issues the cta_group::2 MMAs (M = 256: 128 rows in each
+    // CTA's tensor memory, each CTA supplying its own A rows and its half of the B rows) and owns the barriers that
+    // collect both CTAs' arrivals; its commits are multicast to both CTAs.
+    const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
 
     const int A = prm.A, C = prm.C, T = prm.T, M = prm.M, B = prm.B;
     const int N2 = 2 * M;
@@ -473,7 +491,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         const int it_ = static_cast<int>(r_) / prm.hg_count, hg_ = static_cast<int>(r_) - it_ * prm.hg_count;
         *uc = c_, *uit = it_, *uh0 = prm.hg_size * hg_, *uhn = min(prm.hg_size, prm.ht_count - prm.hg_size * hg_);
     };
-    const uint32_t part_bytes = static_cast<uint32_t>(nt * 128);            // one part of a k-block: [nt rows][128 B]
+    const int nt_cta = kPair ? nt >> 1 : nt;  // B rows (output columns) this CTA's shared memory holds: a pair splits the N tile
+    const uint32_t part_bytes = static_cast<uint32_t>(nt_cta * 128);        // one part of a k-block: [nt_cta rows][128 B]
     const uint32_t bop_kb_bytes = static_cast<uint32_t>(parts) * part_bytes;  // one k-block: [part][nt rows][128 B]
     // profiling: lane 0 of each role's first warp accounts blocked time per barrier class (slot) and role span
     const bool prof_lane = kProf && lane == 0 && (warp == kProducerWarp || warp == kMmaWarp || warp == kEpilogueWarp0 ||
@@ -484,7 +503,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     const unsigned long long role_t0 = prof_lane ? global_ns() : 0ull;
     const unsigned long long role_t0_cta = (kProf && threadIdx.x < 24) ? global_ns() : 0ull;
 
-    if (warp >= kProducerWarp) asm volatile("setmaxnreg.dec.sync.aligned.u32 " DCBF_STR(DCBF_REGS_ISSUE) ";");
+    if (warp >= kProducerWarp) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " DCBF_STR(DCBF_REGS_ISSUE) ";");
+    }
     if (warp == kProducerWarp) {
         // =================================== TMA producer ===================================
         uint32_t rs = 0, ph = 0;
@@ -507,8 +528,13 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 int uit, uh0, uhn;
                 unit_decode(w, &uc, &uit, &uh0, &uhn);
                 for (int b = 0; b < B && ok; ++b)
-                    for (int s = 0; s < prm.slab_count && ok; ++s)
-                        for (int i = 0; i < uhn && ok; ++i) ok = load_slab(uh0 + i, static_cast<int>(uc), s, b);
+                    for (int s = 0; s < prm.slab_count && ok; ++s) {
+                        if (kPair) {  // this CTA's time tile (past the end of the heap: an all-zero box, nothing is stored)
+                            ok = load_slab(uh0 + static_cast<int>(cta_rank), static_cast<int>(uc), s, b);
+                        } else {
+                            for (int i = 0; i < uhn && ok; ++i) ok = load_slab(uh0 + i, static_cast<int>(uc), s, b);
+                        }
+                    }
             }
         } else {
             // per accumulator tile (N tile, batch, time tile): its antenna slabs
@@ -533,11 +559,61 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         const int mma_parts = kMerged ? 1 : parts;
         const uint32_t acc_cols = static_cast<uint32_t>(kMerged ? 2 * nt : nt);  // TMEM columns per (buffer, pol)
         const uint32_t idesc = make_idesc_f16(static_cast<int>(acc_cols));
-        const uint32_t a_lo0 = desc_lo(aop_base), b_lo0 = desc_lo(bop_base);
+        const uint32_t b_lo0 = desc_lo(bop_base);
         const uint32_t part_lo = part_bytes >> 4, kb_lo = bop_kb_bytes >> 4;
         uint32_t slab = 0, unit = 0, step = 0;
         bool ok = true;
-        if constexpr (kStream) {
+        if constexpr (kPair) {
+            // CTA pair: CTA 0 issues for both.  One cta_group::2 MMA covers both time tiles of the unit (M = 256: rows
+            // 0..127 = this CTA's tile, 128..255 = the peer's) and the whole N tile (each CTA holds half of its B rows);
+            // accumulators: pol p at TMEM columns [p nt, (p + 1) nt) of both CTAs.  Commits go to both CTAs' barriers.
+            if (cta_rank == 0) {
+                const uint32_t pol = warp == kMmaWarp ? 0u : 1u;
+                const uint32_t idesc2 = make_idesc_f16(nt, false, false, 256);
+                const uint32_t d_tmem = tmem_base + pol * static_cast<uint32_t>(nt);
+                uint32_t kstep = 0;
+                for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
+                    for (int b = 0; b < B && ok; ++b, ++unit) {
+                        ok = mbar_wait<kProf>(bar(kAccEmpty), (unit & 1u) ^ 1u, ctl, prm.status, kRoleMma, kAccEmpty, ps + 1);
+                        if (!ok) break;
+                        tc_fence_after();
+                        for (int s = 0; s < prm.slab_count && ok; ++s, ++slab) {
+                            const uint32_t slot = kstep % kBSlots;
+                            if ((s & 1) == 0)
+                                ok = mbar_wait<kProf>(bar(kBopFull + slot), (kstep / kBSlots) & 1u, ctl, prm.status, kRoleMma, kBopFull + slot, ps + 0);
+                            const uint32_t as = slab % kAStages;
+                            if (ok) ok = mbar_wait<kProf>(bar(kAopFull + as), (slab / kAStages) & 1u, ctl, prm.status, kRoleMma, kAopFull + as, ps + 2);
+                            if (!ok) break;
+                            tc_fence_after();
+                            const int n_ants = min(kSlabAnts, A - s * kSlabAnts);
+                            const int k_steps = (n_ants + 7) >> 3;
+                            const uint32_t b_lo = b_lo0 + slot * (kBopSlotBytes >> 4) + static_cast<uint32_t>(s & 1) * 4u;
+                            const uint32_t a_lo = desc_lo(aop_addr(as)) + pol * (kAopTileBytes >> 4);
+                            if (elect_one()) {
+#pragma unroll
+                                for (int part = 0; part < 2; ++part) {
+                                    if (part < parts) {
+#pragma unroll
+                                        for (int kk = 0; kk < 2; ++kk) {
+                                            if (kk < k_steps)
+                                                umma_f16_pair(d_tmem, make_desc(a_lo + 2u * kk, kDescHiSw64),
+                                                              make_desc(b_lo + part * part_lo + 2u * kk, kDescHiSw128), idesc2,
+                                                              (s | part | kk) != 0);
+                                        }
+                                    }
+                                }
+                                umma_commit_pair(bar(kAopEmpty + as));
+                                if ((s & 1) == 1 || s == prm.slab_count - 1) umma_commit_pair(bar(kBopEmpty + slot));  // last use of this k-block
+                            }
+                            __syncwarp();
+                            if ((s & 1) == 1 || s == prm.slab_count - 1) ++kstep;
+                        }
+                        if (ok && elect_one()) umma_commit_pair(bar(kAccFull));
+                        __syncwarp();
+                    }
+                }
+            }
+        } else if constexpr (kStream) {
             // K-streamed B: one ring slot per 32-antenna k-block; all (time tile, pol) accumulators of a
             // (channel, N tile, batch) unit are open at once (ht x 2 x nt TMEM columns), slabs outer, time tiles inner
             const uint32_t pol = warp == kMmaWarp ? 0u : 1u;
@@ -551,18 +627,18 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     if (!ok) break;
                     tc_fence_after();
                     for (int s = 0; s < prm.slab_count && ok; ++s) {
-                        const uint32_t slot = kstep % kBopSlots;
+                        const uint32_t slot = kstep % kBSlots;
                         if ((s & 1) == 0)
-                            ok = mbar_wait<kProf>(bar(kBopFull + slot), (kstep / kBopSlots) & 1u, ctl, prm.status, kRoleMma, kBopFull + slot, ps + 0);
+                            ok = mbar_wait<kProf>(bar(kBopFull + slot), (kstep / kBSlots) & 1u, ctl, prm.status, kRoleMma, kBopFull + slot, ps + 0);
                         const int n_ants = min(kSlabAnts, A - s * kSlabAnts);
                         const int k_steps = (n_ants + 7) >> 3;
                         const uint32_t b_lo = b_lo0 + slot * (kBopSlotBytes >> 4) + static_cast<uint32_t>(s & 1) * 4u;
                         for (int h = 0; h < uhn && ok; ++h, ++slab) {
-                            const uint32_t as = slab % kAopStages;
-                            ok = mbar_wait<kProf>(bar(kAopFull + as), (slab / kAopStages) & 1u, ctl, prm.status, kRoleMma, kAopFull + as, ps + 2);
+                            const uint32_t as = slab % kAStages;
+                            ok = mbar_wait<kProf>(bar(kAopFull + as), (slab / kAStages) & 1u, ctl, prm.status, kRoleMma, kAopFull + as, ps + 2);
                             if (!ok) break;
                             tc_fence_after();
-                            const uint32_t a_lo = a_lo0 + as * (kAopStageBytes >> 4) + pol * (kAopTileBytes >> 4);
+                            const uint32_t a_lo = desc_lo(aop_addr(as)) + pol * (kAopTileBytes >> 4);
                             const uint32_t d_tmem = tmem_base + (static_cast<uint32_t>(h) * kPols + pol) * static_cast<uint32_t>(nt);
                             if (elect_one()) {
 #pragma unroll
@@ -607,13 +683,13 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     tc_fence_after();
                     const uint32_t d_tmem0 = tmem_base + ab * kPols * acc_cols;
                     for (int s = 0; s < prm.slab_count; ++s, ++slab) {
-                        const uint32_t as = slab % kAopStages;
-                        ok = mbar_wait<kProf>(bar(kAopFull + as), (slab / kAopStages) & 1u, ctl, prm.status, kRoleMma, kAopFull + as, ps + 2);
+                        const uint32_t as = slab % kAStages;
+                        ok = mbar_wait<kProf>(bar(kAopFull + as), (slab / kAStages) & 1u, ctl, prm.status, kRoleMma, kAopFull + as, ps + 2);
                         if (!ok) break;
                         tc_fence_after();
                         const int n_ants = min(kSlabAnts, A - s * kSlabAnts);
                         const int k_steps = (n_ants + 7) >> 3;  // 8 antennas = 16 k per MMA
-                        const uint32_t a_lo = a_lo0 + as * (kAopStageBytes >> 4);
+                        const uint32_t a_lo = desc_lo(aop_addr(as));
                         // B: k-block s/2, 64-byte half s%2 of its 128-byte rows
                         const uint32_t b_lo = b_lo0 + bb * (kBopBufBytes >> 4) + static_cast<uint32_t>(s >> 1) * kb_lo + static_cast<uint32_t>(s & 1) * 4u;
                         if (elect_one()) {
@@ -752,7 +828,25 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 }
             }
         };
-        if constexpr (kStream) {
+        if constexpr (kPair) {
+            // this CTA's 128 rows (time tile uh0 + rank) of both pols; the accumulators go back to CTA 0's issuer
+            for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
+                uint32_t c;
+                int it, uh0, uhn;
+                unit_decode(w, &c, &it, &uh0, &uhn);
+                for (int b = 0; b < B && ok; ++b, ++unit) {
+                    ok = mbar_wait<kProf>(bar(kAccFull), unit & 1u, ctl, prm.status, kRoleEpilogue, kAccFull, ps + 0);
+                    if (!ok) break;
+                    tc_fence_after();
+                    for (int p = 0; p < kPols; ++p)
+                        store_tile_f32(static_cast<uint32_t>(p) * static_cast<uint32_t>(nt), b, p, c,
+                                       (uh0 + static_cast<int>(cta_rank)) * kTileT, it * nt);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(bar(kAccEmpty), 0);
+                }
+            }
+        } else if constexpr (kStream) {
             // all (time tile, pol) accumulators of a (channel, N tile, batch) unit complete together
             for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
                 uint32_t c;
@@ -982,7 +1076,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 uint32_t uc;
                 int uit, uh0;
                 unit_decode(w, &uc, &uit, &uh0, &tiles);
-                tiles *= B;
+                tiles = kPair ? B : tiles * B;  // (a pair: one time tile per CTA)
             } else {
                 uint32_t uc;
                 int j0, j1;
@@ -992,16 +1086,16 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             {
                 for (int bh = 0; bh < tiles && ok; ++bh)
                     for (int s = 0; s < prm.slab_count; ++s, ++slab) {
-                        const uint32_t as = slab % kAopStages;
+                        const uint32_t as = slab % kAStages;
                         ok = mbar_wait2<kProf>(bar(kRawFull + rs), rph, kRawFull + rs, bar(kAopEmpty + as),
-                                               ((slab / kAopStages) & 1u) ^ 1u, kAopEmpty + as, ctl, prm.status, kRoleConvert, ps + 0);
+                                               ((slab / kAStages) & 1u) ^ 1u, kAopEmpty + as, ctl, prm.status, kRoleConvert, ps + 0);
                         if (!ok) break;
                         // antennas beyond A were zero-filled by the TMA box: byte 0 -> value 0 (u8), and
                         // 0 ^ 0x80 - 128 -> 0 (i8), so the K padding of the operand needs no special case
                         unsigned long long tc0 = 0, tc1 = 0;
                         if (kProf && prof_lane) tc0 = global_ns();
                         const uint32_t src = raw_addr(rs) + t * 4;
-                        const uint32_t dst0 = aop_base + as * kAopStageBytes + t * 64;
+                        const uint32_t dst0 = aop_addr(as) + t * 64;
                         // all 16 loads first (the volatile shared-memory accesses keep their program order, so
                         // interleaving them with the stores would expose the load latency once per chunk)
                         uint32_t w[kSlabAnts];
@@ -1022,7 +1116,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            mbar_arrive(bar(kAopFull + as));
+                            if (kPair) mbar_arrive_cluster(bar(kAopFull + as), 0);  // the issuer (CTA 0) waits for both CTAs' tiles
+                            else mbar_arrive(bar(kAopFull + as));
                             mbar_arrive(bar(kRawEmpty + rs));
                         }
                         if (++rs == raw_stages) rs = 0, rph ^= 1u;
@@ -1050,6 +1145,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         constexpr int kStride = kCoeffWarps * 32;
         const int ctid = threadIdx.x - kCoeffWarp0 * 32;
         const int mt = nt >> 1;  // beams per N tile
+        // CTA pair: this CTA generates (and warms) the coefficients of its half of the N tile's beams
+        const int mt_cta = kPair ? mt >> 1 : mt, m_cta0 = kPair ? static_cast<int>(cta_rank) * mt_cta : 0;
         const int dm = kStride / A, da = kStride - dm * A;  // (beam, antenna) advance per kStride entries
         const int ml_first = ctid / A, a_first = ctid - ml_first * A;
         // common shape (A = 64, 32, ...): a thread keeps its antenna and moves 4k beams per step, so its B
@@ -1064,7 +1161,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         int sch_n = 0, sch_raw = 0;  // sch_raw: counter value still in flight (not touched until it is published)
         bool sch_end = false, sch_pending = false;
         auto warm_l2 = [&](int ch, int m0) {  // delay_vals of one (channel, N tile) step -> L2
-            const size_t bytes = static_cast<size_t>(min(mt, M - m0)) * A * 16;
+            m0 += m_cta0;
+            if (m0 >= M) return;
+            const size_t bytes = static_cast<size_t>(min(mt_cta, M - m0)) * A * 16;
             const char* p = reinterpret_cast<const char*>(prm.dv + (static_cast<size_t>(ch) * M + m0) * A);
             for (size_t o = 0; o < bytes; o += 65536)
                 bulk_prefetch_l2(p + o, static_cast<uint32_t>(min(bytes - o, static_cast<size_t>(65536))));
@@ -1087,9 +1186,11 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             __threadfence_block();
             ctl->chan_pub = ++sch_n;
         };
+        // (CTA pairs: both CTAs must walk the same sequence, so it is the static one: pair p takes units p, p + pairs, ...)
         auto sch_request = [&]() {
             if (!sch_end && !sch_pending) {
-                sch_raw = atomicAdd(prm.sched, 1);
+                sch_raw = kPair ? sch_n * static_cast<int>(gridDim.x >> 1) + static_cast<int>(blockIdx.x >> 1) - static_cast<int>(gridDim.x)
+                                : atomicAdd(prm.sched, 1);
                 sch_pending = true;
             }
         };
@@ -1100,7 +1201,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             }
         };
         if (is_sched) {
-            sch_publish(static_cast<int>(blockIdx.x));
+            sch_publish(static_cast<int>(kPair ? blockIdx.x >> 1 : blockIdx.x));
             sch_request();
         }
         __syncwarp();
@@ -1114,31 +1215,39 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             static_assert(kPer == 4, "the K-streamed coefficient step is written for four entries per thread");
             const float ks_inv_gmax = kQ8 && ctl->q8_gmax > 0.f ? 1.0f / ctl->q8_gmax : 0.f;
             const int wl = warp - kCoeffWarp0;
-            const int mt = nt >> 1;
             uint32_t nk = 0;
             int nw = sched_get(ctl, 0), nb = 0, nkb = 0;  // load cursor: unit, batch, k-block
-            Dv nxt[kPer];  // static: (delay_s, phase_rad); kTv: all four fields
-            // the cursor's unit, decoded once per unit (the divisions would otherwise sit in every k-block step)
-            const float4* n_src = prm.dv;  // delay_vals of (channel, first beam of the N tile)
-            int n_mte = 0;                 // beams in the N tile; 0 past the last unit
+            // delay_vals in flight: the loads of a step are issued kDepth steps ahead, into one of kDepth register sets
+            // picked by the step's parity (one copy of the step body per set, so that the set is a compile-time choice).
+            constexpr int kDepth = 1;  // (2 was tried: 301 -> 320 us at the C5 share even with 80 registers for this role)
+            Dv nxt[kDepth][kPer];  // static: (delay_s, phase_rad); kTv: all four fields
+            // the cursor's unit, decoded once per unit (the divisions would otherwise sit in every k-block step): this
+            // thread's entry (beam wl, antenna lane) of the unit's first k-block, and which of its four beams exist
+            const float4* n_ptr = prm.dv;
+            uint32_t n_mask = 0;  // bit u: beam wl + 16 u is inside the N tile; 0 past the last unit
+            const size_t u_stride = static_cast<size_t>(kCoeffWarps) * A;  // entries between this thread's beams
             auto cursor_decode = [&]() {
-                n_mte = 0;
+                n_mask = 0;
                 if (static_cast<uint32_t>(nw) < n_units) {
                     const int nc = nw / static_cast<int>(per_chan), nit = (nw - nc * static_cast<int>(per_chan)) / prm.hg_count;
-                    n_mte = min(mt, M - nit * mt);
-                    n_src = prm.dv + (static_cast<size_t>(nc) * M + nit * mt) * A;
+                    const int n_mte = max(0, min(mt_cta, M - (nit * mt + m_cta0)));
+#pragma unroll
+                    for (int u = 0; u < kPer; ++u) n_mask |= (wl + kCoeffWarps * u < n_mte ? 1u : 0u) << u;
+                    n_ptr = prm.dv + (static_cast<size_t>(nc) * M + nit * mt + m_cta0 + wl) * A + lane;
                 }
+                if (prm.dbg & 1) n_mask = 0;
             };
             cursor_decode();
-            auto issue_loads = [&]() {
-                const int a = kKbAnts * nkb + lane;
+            auto issue_loads = [&](auto set_c) {
+                constexpr int set = decltype(set_c)::value;
+                const float4* p = n_ptr + kKbAnts * nkb;
+                const uint32_t mask = kKbAnts * nkb + lane < A ? n_mask : 0u;
 #pragma unroll
                 for (int u = 0; u < kPer; ++u) {
-                    const int m = wl + kCoeffWarps * u;
                     float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (m < n_mte && a < A && !(prm.dbg & 1)) t4 = ldg_nc_f4(n_src + static_cast<size_t>(m) * A + a);
-                    if constexpr (kTv) nxt[u] = t4;
-                    else nxt[u] = make_float2(t4.x, t4.z);
+                    if (mask & (1u << u)) t4 = ldg_nc_f4(p + u * u_stride);
+                    if constexpr (kTv) nxt[set][u] = t4;
+                    else nxt[set][u] = make_float2(t4.x, t4.z);
                 }
             };
             auto advance_cursor = [&]() {
@@ -1160,45 +1269,48 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 nw = sched_get(ctl, nk);
                 cursor_decode();
             };
-            issue_loads();
+            issue_loads(std::integral_constant<int, 0>{});
+            if constexpr (kDepth > 1) {
+                advance_cursor();
+                issue_loads(std::integral_constant<int, kDepth - 1>{});
+            }
             uint32_t kstep = 0;
             bool ok = true;
             for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
                 uint32_t c;
                 int it, uh0, uhn;
                 unit_decode(w, &c, &it, &uh0, &uhn);
-                const double scale = (static_cast<double>(c) + prm.chan_centre) * prm.turns_per_delay;
-                const float s_hi = static_cast<float>(scale), s_lo = static_cast<float>(scale - static_cast<double>(s_hi));
-                const int m0 = it * mt, mte = min(mt, M - m0);
+                // half-turns of phase per second of delay at this channel, as a float pair.  Pinned in registers: left
+                // to itself the compiler re-derives the pair from the channel index in every k-block step, and the
+                // float64 pipe those five instructions run on is narrow (ncu: 27 % of this role's stall samples).
+                float s_hi, s_lo;
+                {
+                    const double scale = (static_cast<double>(c) + prm.chan_centre) * prm.turns_per_delay;
+                    s_hi = static_cast<float>(scale), s_lo = static_cast<float>(scale - static_cast<double>(s_hi));
+                    asm volatile("" : "+f"(s_hi), "+f"(s_lo));
+                }
+                const int m0 = it * mt + m_cta0, mte = max(0, min(mt_cta, M - m0));
                 const float* w_tile = prm.weights ? prm.weights + static_cast<size_t>(m0) * A : nullptr;
                 const bool scaled = kQ8 || w_tile != nullptr;
+                uint32_t u_mask = 0;  // bit u: beam wl + 16 u exists
+#pragma unroll
+                for (int u = 0; u < kPer; ++u) u_mask |= (wl + kCoeffWarps * u < mte ? 1u : 0u) << u;
                 for (int b = 0; b < B && ok; ++b) {
                     float dt_hi = 0.f, dt_lo = 0.f;
                     if constexpr (kTv) set_time(prm, b, uh0, &dt_hi, &dt_lo);  // this batch's (and time tile's) coefficients
                     for (int kb = 0; kb < prm.kb_count && ok; ++kb, ++kstep) {
-                        const uint32_t slot = kstep % kBopSlots;
+                      auto do_step = [&](auto set_c) {
+                        constexpr int set = decltype(set_c)::value;
+                        const uint32_t slot = kstep % kBSlots;
                         Dv v[kPer];
 #pragma unroll
-                        for (int u = 0; u < kPer; ++u) v[u] = nxt[u];
+                        for (int u = 0; u < kPer; ++u) v[u] = nxt[set][u];
                         advance_cursor();
-                        issue_loads();
+                        issue_loads(set_c);
                         const int a = kKbAnts * kb + lane;
-                        // optional real factor per entry: ?beam-weights and / or the requantisation gain of the beam
-                        // relative to the largest one (tiny tables that stay in L1 / L2)
-                        float f[kPer];
-                        if (scaled) {
-#pragma unroll
-                            for (int u = 0; u < kPer; ++u) {
-                                const int m = wl + kCoeffWarps * u;
-                                f[u] = 1.0f;
-                                if (m < mte && a < A) {
-                                    if (w_tile) f[u] = __ldg(w_tile + static_cast<size_t>(m) * A + a);
-                                    if constexpr (kQ8) f[u] *= __ldg(prm.gains + m0 + m) * ks_inv_gmax;
-                                }
-                            }
-                        }
-                        ok = mbar_wait<kProf>(bar(kBopEmpty + slot), ((kstep / kBopSlots) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + slot, ps + 0);
-                        if (!ok) break;
+                        const uint32_t st_mask = a < A ? u_mask : 0u;  // entries of this thread that are stored
+                        ok = mbar_wait<kProf>(bar(kBopEmpty + slot), ((kstep / kBSlots) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + slot, ps + 0);
+                        if (!ok) return;
                         // beam m = wl + 16 u: row 2 m has the same swizzle phase for every u, so the four words of
                         // entry u sit at a constant 4096-byte stride from those of entry 0 (immediate offsets)
                         const uint32_t row0 = 2u * static_cast<uint32_t>(wl);
@@ -1208,9 +1320,26 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         const uint32_t d1 = (d0 + 128u) ^ 16u;  // row + 1: swizzle phase (row & 7) | 1
                         const uint32_t d0l = d0 + part_bytes, d1l = d1 + part_bytes;
                         // kGroup entries at a time as one straight-line region, so that their dependent chains interleave:
-                        // reduced phases (float pairs; a rare out-of-range group is redone in float64), sin / cos, fp16 split
+                        // reduced phases (float pairs; a rare out-of-range group is redone in float64), sin / cos, fp16
+                        // split.  Two copies of the region: with and without the optional real factor per entry (?beam-weights
+                        // and / or the requantisation gain of the beam relative to the largest one; tiny tables that stay in
+                        // L1 / L2) -- as one region the plain path's arithmetic would share a scoreboard with those loads and
+                        // through it wait for the delay_vals just requested for the NEXT step (ncu: 10 % of this role's samples)
                         constexpr int kGroup = kTv ? 2 : 4;
-                        if (!(prm.dbg & 2)) {
+                        auto generate = [&](auto scaled_c) {
+                            constexpr bool kScaled = decltype(scaled_c)::value;
+                            float f[kPer];
+                            if constexpr (kScaled) {
+#pragma unroll
+                                for (int u = 0; u < kPer; ++u) {
+                                    const int m = wl + kCoeffWarps * u;
+                                    f[u] = 1.0f;
+                                    if (st_mask & (1u << u)) {
+                                        if (w_tile) f[u] = __ldg(w_tile + static_cast<size_t>(m) * A + a);
+                                        if constexpr (kQ8) f[u] *= __ldg(prm.gains + m0 + m) * ks_inv_gmax;
+                                    }
+                                }
+                            }
 #pragma unroll
                             for (int g = 0; g < kPer; g += kGroup) {
                                 float t[kGroup];
@@ -1225,6 +1354,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                         in_range &= steer_tq_fast<true>(d_hi[u], d_lo[u], ph_hi[u], ph_lo[u], s_hi, s_lo, &t[u], &q[u]);
                                     }
                                     if (!in_range) {
+                                        const double scale = (static_cast<double>(c) + prm.chan_centre) * prm.turns_per_delay;
 #pragma unroll
                                         for (int u = 0; u < kGroup; ++u) {
                                             const Tq r = steer_tq_f64<true>(d_hi[u], d_lo[u], ph_hi[u], ph_lo[u], scale);
@@ -1236,6 +1366,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                     for (int u = 0; u < kGroup; ++u)
                                         in_range &= steer_tq_fast<false>(v[g + u].x, 0.f, v[g + u].y, 0.f, s_hi, s_lo, &t[u], &q[u]);
                                     if (!in_range) {
+                                        const double scale = (static_cast<double>(c) + prm.chan_centre) * prm.turns_per_delay;
 #pragma unroll
                                         for (int u = 0; u < kGroup; ++u) {
                                             const Tq r = steer_tq_f64<false>(v[g + u].x, 0.f, v[g + u].y, 0.f, scale);
@@ -1247,13 +1378,13 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                     constexpr int gu = decltype(gu_c)::value;
                                     float nsn, cs;
                                     sincos_quadrant(t[u], q[u], &nsn, &cs);
-                                    if (scaled) {
+                                    if constexpr (kScaled) {
                                         nsn *= f[gu];
                                         cs *= f[gu];
                                     }
                                     uint32_t hi0, hi1, lo0, lo1;
                                     coef_words(nsn, cs, &hi0, &hi1, &lo0, &lo1);
-                                    if (a < A && wl + kCoeffWarps * gu < mte) {
+                                    if (st_mask & (1u << gu)) {
                                         constexpr int kOff = gu * (2 * kCoeffWarps * 128);
                                         st_shared_u32_off<kOff>(d0, hi0);
                                         st_shared_u32_off<kOff>(d1, hi1);
@@ -1278,10 +1409,20 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                     }
                                 }
                             }
+                        };
+                        if (!(prm.dbg & 2)) {
+                            if (scaled) generate(std::true_type{});
+                            else generate(std::false_type{});
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(bar(kBopFull + slot));
+                        if (lane == 0) {
+                            if (kPair) mbar_arrive_cluster(bar(kBopFull + slot), 0);  // the issuer (CTA 0) waits for both halves
+                            else mbar_arrive(bar(kBopFull + slot));
+                        }
+                      };
+                      if (kDepth > 1 && (kstep & 1u)) do_step(std::integral_constant<int, kDepth - 1>{});
+                      else do_step(std::integral_constant<int, 0>{});
                     }
                 }
             }
@@ -1505,7 +1646,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     // ---- teardown ----
     if (prof_lane) ctl->wait_ns[my_role][3] = global_ns() - role_t0;
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync();  // nothing of the peer (arrivals, multicast commits, MMA reads of this CTA's tiles) is still under way
+    else __syncthreads();
     if (threadIdx.x == 0) {  // last CTA out re-arms the channel counter for the next launch that uses this slot
         __threadfence();
         if (atomicAdd(prm.sched + 1, 1) == static_cast<int>(gridDim.x) - 1) {
@@ -1523,7 +1665,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     }
     if (warp == kMmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -1533,7 +1676,7 @@ constexpr int kSchedSlots = 2 * kLiveSlots;  // the second half belongs to launc
 using KernelFn = void (*)(const FusedParams, const CUtensorMap, const CUtensorMap);
 // index = 6 * q8 + 2 * variant (0 plain, 1 profiling, 2 time-varying) + merged; [12] .. [16] = K-streamed B (plain,
 // profiling, time-varying, int8 output, int8 output + time-varying)
-constexpr int kNumKernels = 17;
+constexpr int kNumKernels = 19;  // [17], [18] = K-streamed B on CTA pairs (cta_group::2): plain, profiling
 KernelFn const kKernels[kNumKernels] = {
     fused_beamform_kernel<false, false, false, false, false>, fused_beamform_kernel<false, false, false, true, false>,
     fused_beamform_kernel<true, false, false, false, false>,  fused_beamform_kernel<true, false, false, true, false>,
@@ -1544,6 +1687,8 @@ KernelFn const kKernels[kNumKernels] = {
     fused_beamform_kernel<false, false, false, false, true>,  fused_beamform_kernel<true, false, false, false, true>,
     fused_beamform_kernel<false, true, false, false, true>,
     fused_beamform_kernel<false, false, true, false, true>,   fused_beamform_kernel<false, true, true, false, true>,
+    fused_beamform_kernel<false, false, false, false, true, true>,
+    fused_beamform_kernel<true, false, false, false, true, true>,
 };
 
 int* g_status_dev[64] = {};  // per-device: 4-int status block + kSchedSlots x {next, done} channel counters
@@ -1659,9 +1804,15 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     const bool kstream = (p.nt_count > 1 || no_whole_tiles) && !(flags & DCBF_FLAG_DEBUG_NO_KSTREAM);
     p.hg_count = (p.ht_count + p.hg_size - 1) / p.hg_size;
     if (no_whole_tiles && !kstream) return DCBF_ERR_UNSUPPORTED;  // (the k-block ring itself has no antenna limit)
+    // CTA pairs for the plain K-streamed case with at least two time tiles and more than 128 output columns: the two CTAs
+    // of a cluster take one time tile each and half of the coefficients each, N tiles of up to 256 columns (one
+    // cta_group::2 MMA of M = 256): per output byte half the coefficient and conversion work and ~40 % less shared-memory
+    // traffic (every B row is read by the tensor cores once for 256 output rows instead of once for 128).
+    const int n_pad = ((2 * M + 15) / 16) * 16;
+    const bool pair = kstream && !batch_dt_s && !q8 && T > kTileT && n_pad > 128 && !(flags & DCBF_FLAG_DEBUG_NO_PAIR);
     if (kstream) {
-        const int n_pad = ((2 * M + 15) / 16) * 16;
-        p.nt_count = (n_pad + 127) / 128;
+        const int cap = pair ? 256 : 128;
+        p.nt_count = (n_pad + cap - 1) / cap;
         p.nt = ((((n_pad + p.nt_count - 1) / p.nt_count) + 31) / 32) * 32;
     }
     p.merged = !kstream && p.parts == 2 && p.nt <= 64;
@@ -1764,27 +1915,51 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     const long long units = kstream ? static_cast<long long>(C) * p.nt_count * p.hg_count
                                     : static_cast<long long>(p.n_whole) + static_cast<long long>(C - p.n_whole) * p.split;
     if (units > 0x7ffffff0LL) return DCBF_ERR_UNSUPPORTED;  // what the CTAs draw from the queue
-    const int grid = units < n_sms[dev] ? static_cast<int>(units) : n_sms[dev];
+    int grid = units < n_sms[dev] ? static_cast<int>(units) : n_sms[dev];
+    if (pair) {  // one cluster of two CTAs per TPC the driver will co-schedule
+        static int n_pairs[64] = {};
+        if (!n_pairs[dev]) {
+            cudaLaunchConfig_t occ{};
+            occ.gridDim = dim3(2 * n_sms[dev]);
+            occ.blockDim = dim3(kThreads);
+            occ.dynamicSmemBytes = kSmemBytes;
+            cudaLaunchAttribute ca[1];
+            ca[0].id = cudaLaunchAttributeClusterDimension;
+            ca[0].val.clusterDim.x = 2, ca[0].val.clusterDim.y = 1, ca[0].val.clusterDim.z = 1;
+            occ.attrs = ca;
+            occ.numAttrs = 1;
+            int n = 0;
+            DCBF_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kKernels[17], &occ));
+            n_pairs[dev] = n > 0 ? n : n_sms[dev] / 2;
+        }
+        grid = 2 * static_cast<int>(units < n_pairs[dev] ? units : n_pairs[dev]);
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2, attr[1].val.clusterDim.y = 1, attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     // Every launch may start while the preceding kernel of the stream drains (programmatic dependent launch).  By
     // default the kernel then waits for that kernel's completion (griddepcontrol.wait) right after its prologue, before
     // it touches global memory: launch latency, barrier / TMEM set-up and the zeroing of the B tiles are off the
     // critical path, nothing else changes.  DCBF_FLAG_STREAMING drops the wait (the caller promises independence).
     cfg.numAttrs = (flags & DCBF_FLAG_DEBUG_NO_PDL) ? 0 : 1;
+    if (pair) {
+        if (!cfg.numAttrs) attr[0] = attr[1];
+        ++cfg.numAttrs;
+    }
     p.pdl_wait = (flags & DCBF_FLAG_STREAMING) ? 0 : 1;
     p.dbg = (flags >> 16) & 15;  // developer experiments
     // (int8 output, variant, merged) specialisation; variant: 0 plain, 1 profiling, 2 time-varying steering (the
     // profiler has no time-varying build)
     const int variant = batch_dt_s ? 2 : p.prof ? 1 : 0;
-    auto kernel = kstream ? kKernels[q8 ? (batch_dt_s ? 16 : 15) : batch_dt_s ? 14 : 12 + (p.prof ? 1 : 0)] : kKernels[(q8 ? 6 : 0) + 2 * variant + (p.merged ? 1 : 0)];
+    auto kernel = pair ? kKernels[17 + (p.prof ? 1 : 0)] : kstream ? kKernels[q8 ? (batch_dt_s ? 16 : 15) : batch_dt_s ? 14 : 12 + (p.prof ? 1 : 0)] : kKernels[(q8 ? 6 : 0) + 2 * variant + (p.merged ? 1 : 0)];
     DCBF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, p, tm_in, tm_out));
     DCBF_CHECK_LAUNCH("fused_beamform_kernel");
     return DCBF_OK;

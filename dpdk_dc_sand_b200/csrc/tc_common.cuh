@@ -37,15 +37,26 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// kCluster: acquire at cluster scope (the barrier also collects arrivals from the other CTA of a pair).
+template <bool kCluster = false>
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
+    if (kCluster)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
     return ok;
 }
 // True on exactly one lane of a converged warp.  ptxas knows the guarded region is single-threaded, so
@@ -122,6 +133,49 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 // mbarrier arrive once every tcgen05.mma issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of a TPC share one MMA; CTA rank 0 issues ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster.  Default semantics (release at
+// CTA scope), as in every 2-SM pipeline of CUTLASS: what the arrival publishes are this CTA's own shared-memory writes,
+// already made visible to the async proxy by fence.proxy.async, which the pair's tensor cores read in place.  (The
+// .release.cluster form costs a GPU-scope MEMBAR + ERRBAR per arrival: 10 % of all stall samples in the first build.)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 rem;\n\t"
+        "mapa.shared::cluster.u32 rem, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [rem];\n\t}" ::"r"(bar), "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {  // same warp id in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem, 128 rows in each CTA] (+)= A[smem, each CTA its 128 rows] * B[smem, each CTA half of the N rows]
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// Arrive on the mbarrier at this offset in BOTH CTAs of the pair once every MMA issued so far has completed.
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -215,9 +269,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
 }
 // Instruction descriptor for kind::f16: fp32 accumulate, both operands K-major, M = 128, N = n.
 // a_bf16 / b_bf16 select bfloat16 instead of fp16 for that operand (the two formats are independent fields).
-__device__ __forceinline__ uint32_t make_idesc_f16(int n, bool a_bf16 = false, bool b_bf16 = false) {
+// m = 128, or 256 for a cta_group::2 instruction (128 rows in each CTA of the pair).
+__device__ __forceinline__ uint32_t make_idesc_f16(int n, bool a_bf16 = false, bool b_bf16 = false, int m = 128) {
     return (1u << 4) | (a_bf16 ? 1u << 7 : 0u) | (b_bf16 ? 1u << 10 : 0u) | (static_cast<uint32_t>(n >> 3) << 17) |
-           (static_cast<uint32_t>(128 >> 4) << 24);
+           (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -285,13 +340,16 @@ __device__ __forceinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Co
 // Warp-collective: every lane waits; the result is made warp-uniform.
 // kProf builds only: `slot` >= 0 on exactly one lane of a role makes that lane account its blocked time (the
 // first try_wait may itself suspend the thread, so the whole call is timed).
-template <bool kProf>
+template <bool kProf, bool kCluster = false>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, Control* ctl, int* status, int role, int id,
                                           int slot = -1) {
     unsigned long long t0 = 0;
     if (kProf && slot >= 0) t0 = global_ns();
-    bool ok = mbar_try_wait(bar, parity) != 0;
-    if (!ok) ok = mbar_wait_slow(bar, parity, ctl, status, role, id);
+    bool ok = mbar_try_wait<kCluster>(bar, parity) != 0;
+    if (!ok) {
+        ok = mbar_wait_slow(bar, parity, ctl, status, role, id);
+        if (kCluster && ok) mbar_try_wait<true>(bar, parity);  // (completed: this probe only adds the cluster-scope acquire)
+    }
     if (kProf && slot >= 0) ctl->wait_ns[role][slot] += global_ns() - t0;
     return __all_sync(0xffffffffu, ok);
 }

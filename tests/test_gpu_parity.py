@@ -398,6 +398,35 @@ def test_time_varying_steering_with_many_antennas_and_beams(dropin):
     np.testing.assert_allclose(outs[0], outs[1], rtol=0, atol=float(_budget(x).max()) * 2.0 ** -6)
 
 
+@pytest.mark.parametrize("case", [(1, 197, 4, 256, 256), (1, 100, 5, 384, 100), (2, 197, 3, 256, 130), (1, 520, 3, 160, 70),
+                                  (1, 64, 9, 256, 200), (3, 33, 4, 640, 97)],
+                         ids=["c5_like", "three_time_tiles", "two_heaps_ragged_n", "520_antennas_ragged_t", "64_antennas",
+                              "odd_beams_five_tiles"])
+def test_cta_pair_mode(dropin, case):
+    """Many antennas x beams run on CTA pairs (cta_group::2 MMAs of M = 256, two time tiles and half of the coefficients
+    per CTA): inside the budget against the float64 oracle, and bit-identical to the single-CTA K-streamed kernel
+    (same products, same accumulation order), including heaps whose last pair has one tile, ragged last tiles and N tiles."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m = case
+    n, xid = 1024, 2
+    x = orc.make_samples(b, a, c, t, seed=71)
+    dv = orc.make_delay_vals_random(c, m, a, seed=72)
+    ref = orc.beamform_pipeline(x, dv, n, xid, TS)
+    dx, ddv = torch.from_numpy(x).cuda(), torch.from_numpy(dv).cuda()
+    outs = []
+    for flags in (0, _capi.FLAG_DEBUG_NO_PAIR):
+        out = torch.full(ref.shape, float("nan"), dtype=torch.float32, device="cuda")
+        _capi.fused(dx, ddv, out, b, a, c, n, t, m, xid, TS, flags)
+        torch.cuda.synchronize()
+        _capi.fused_status()
+        outs.append(out.cpu().numpy())
+    assert np.all(np.abs(outs[0].astype(np.float64) - ref) <= _budget(x))
+    np.testing.assert_array_equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("case", [(2, 64, 3, 512, 6, 4096, 6), (1, 100, 2, 384, 100, 512, 1), (2, 16, 5, 208, 4, 256, 0)],
                          ids=["whole_tile_sets", "k_streamed", "ragged_last_tile"])
 def test_sub_heap_time_varying_steering(dropin, case):
