@@ -78,6 +78,8 @@ class FusedOptions(C.Structure):
 
 SIGNATURES["dcbf_fused_ex"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_double, C.POINTER(FusedOptions), C.c_uint, C.c_void_p])
+SIGNATURES["dcbf_coeffs_f16"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_double, C.POINTER(C.c_double), C.c_void_p, C.c_void_p])
 SIGNATURES["dcbf_coeffs_ex"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_double, C.POINTER(C.c_double), C.c_void_p, C.c_void_p])
 
@@ -169,6 +171,14 @@ def _dt_array(batch_dt, n_batches):
 
 def coeffs(delay_vals, out, n_batches, n_pols, n_chans, n_chans_total, n_ants, n_beams, xeng_id, sample_period,
            stream=None, batch_dt=None, weights=None) -> None:
+    """Stand-alone steering coefficients; a float16 ``out`` tensor selects dcbf_coeffs_f16 (same layout, fp16)."""
+    if getattr(out, "dtype", None) is not None and str(out.dtype).endswith("float16"):
+        dt = _dt_array(batch_dt, n_batches) if batch_dt is not None else None
+        check(load().dcbf_coeffs_f16(_ptr(delay_vals), _ptr(out), n_batches, n_pols, n_chans, n_chans_total, n_ants,
+                                     n_beams, xeng_id, float(sample_period), dt,
+                                     _ptr(weights) if weights is not None else None, _stream_handle(stream)),
+              "dcbf_coeffs_f16")
+        return
     if weights is not None:
         dt = _dt_array(batch_dt, n_batches) if batch_dt is not None else None
         check(load().dcbf_coeffs_ex(_ptr(delay_vals), _ptr(out), n_batches, n_pols, n_chans, n_chans_total, n_ants,

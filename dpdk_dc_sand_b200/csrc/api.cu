@@ -110,6 +110,18 @@ int dcbf_coeffs_ex(const float* delay_vals, float* coeffs, int B, int P, int C, 
                          static_cast<cudaStream_t>(stream));
 }
 
+int dcbf_coeffs_f16(const float* delay_vals, void* coeffs_f16, int B, int P, int C, int N, int A, int M, int xeng_id,
+                    double sample_period, const double* batch_dt_s, const float* beam_weights, dcbf_stream_t stream) {
+    if (!delay_vals || !coeffs_f16 || B <= 0 || P <= 0 || C <= 0 || N <= 0 || A <= 0 || M <= 0 || xeng_id < 0 ||
+        !(sample_period > 0.0))
+        return DCBF_ERR_INVALID_ARG;
+    if (!aligned16(delay_vals) || (reinterpret_cast<uintptr_t>(coeffs_f16) & 3u)) return DCBF_ERR_INVALID_ARG;
+    if (batch_dt_s && B > DCBF_MAX_TV_BATCHES) return DCBF_ERR_UNSUPPORTED;
+    if (int e = check_device()) return e;
+    return launch_coeffs_f16(delay_vals, coeffs_f16, B, P, C, N, A, M, xeng_id, sample_period, batch_dt_s, beam_weights,
+                             static_cast<cudaStream_t>(stream));
+}
+
 int dcbf_beamform(const uint8_t* reordered, const float* coeffs, float* beams, int B, int C, int T, int A, int M,
                   unsigned flags, dcbf_stream_t stream) {
     if (!reordered || !coeffs || !beams || B <= 0 || C <= 0 || A <= 0 || M <= 0 || bad_t(T))

@@ -36,6 +36,9 @@ int launch_reorder(const uint8_t* samples, uint8_t* reordered, int B, int A, int
 // batch_dt_s: NULL (static steering) or B host doubles (seconds since the delay model's reference time)
 int launch_coeffs(const float* delay_vals, float* coeffs, int B, int P, int C, int N, int A, int M, int xeng_id,
                   double sample_period, const double* batch_dt_s, const float* beam_weights, cudaStream_t s);
+// fp16 output in the same layout (the precursor's 16-bit coefficient option)
+int launch_coeffs_f16(const float* delay_vals, void* coeffs, int B, int P, int C, int N, int A, int M, int xeng_id,
+                      double sample_period, const double* batch_dt_s, const float* beam_weights, cudaStream_t s);
 int launch_beamform(const uint8_t* reordered, const float* coeffs, float* beams, int B, int C, int T, int A, int M,
                     unsigned flags, cudaStream_t s);
 // tcgen05 version (beamform_tc.cu) for shapes its TMA descriptors can express: even beam count

@@ -173,6 +173,14 @@ int dcbf_coeffs_ex(const float* delay_vals, float* coeffs, int n_batches, int n_
                    int n_chans_total, int n_ants, int n_beams, int xeng_id, double sample_period,
                    const double* batch_dt_s, const float* beam_weights, dcbf_stream_t stream);
 
+/* dcbf_coeffs_ex with half-precision output: coeffs_f16 [B][P][C][2A][2M] fp16 (IEEE binary16), every value the
+ * round-to-nearest fp16 of the float32 coefficient -- the 16-bit output option of the native precursor
+ * (beamformer_coefficient_generator/BeamformerKernels.cu:113-115, 172-185: __floats2half2_rn of (real, imag)), in this
+ * library's real-expanded layout.  Halves the coefficient traffic of a consumer that does not need 24 bits. */
+int dcbf_coeffs_f16(const float* delay_vals, void* coeffs_f16, int n_batches, int n_pols, int n_chans,
+                    int n_chans_total, int n_ants, int n_beams, int xeng_id, double sample_period,
+                    const double* batch_dt_s, const float* beam_weights, dcbf_stream_t stream);
+
 /* Synchronises the whole current device (cudaDeviceSynchronize: every stream, non-blocking ones included), then
  * returns the status the dcbf_fused / dcbf_beamform kernels left behind: DCBF_OK, or DCBF_ERR_TIMEOUT if an in-kernel
  * pipeline wait exceeded its 2 s guard (the kernel then exits early instead of hanging, leaving partly written beams;

@@ -398,6 +398,32 @@ def test_time_varying_steering_with_many_antennas_and_beams(dropin):
     np.testing.assert_allclose(outs[0], outs[1], rtol=0, atol=float(_budget(x).max()) * 2.0 ** -6)
 
 
+@pytest.mark.parametrize("case", [(1, 2, 5, 64, 64, 4096, 3), (2, 1, 3, 33, 20, 256, 0), (1, 2, 2, 80, 100, 1024, 1),
+                                  (3, 2, 4, 7, 6, 64, 0), (1, 1, 2, 16, 3, 64, 0)],
+                         ids=["M64_whole_rows", "M20", "M100_two_beam_tiles", "M6_plain_stores_for_f16", "M3_plain_stores"])
+def test_coeff_generator_bulk_tiles_and_half_output(dropin, case):
+    """The stand-alone coefficient kernel stages every tile in the output layout and writes the (batch, pol) replicas
+    with bulk copies; odd row pitches take plain stores.  float32: equal to the float64 oracle to 1e-6 in every
+    replica.  float16 (the precursor's 16-bit output, BeamformerKernels.cu:172-185): exactly the round-to-nearest fp16
+    of the float32 output."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, p, c, a, m, n, xid = case
+    dv = orc.make_delay_vals_random(c, m, a, seed=81)
+    ref = orc.steering_coeffs(dv, b, p, c, n, a, m, xid, TS, out_dtype=np.float64)
+    ddv = torch.from_numpy(dv).cuda()
+    out32 = torch.full(ref.shape, float("nan"), dtype=torch.float32, device="cuda")
+    out16 = torch.full(ref.shape, float("nan"), dtype=torch.float16, device="cuda")
+    _capi.coeffs(ddv, out32, b, p, c, n, a, m, xid, TS)
+    _capi.coeffs(ddv, out16, b, p, c, n, a, m, xid, TS)
+    torch.cuda.synchronize()
+    got32, got16 = out32.cpu().numpy(), out16.cpu().numpy()
+    assert np.abs(got32.astype(np.float64) - ref).max() <= 1e-6
+    np.testing.assert_array_equal(got16, got32.astype(np.float16))
+
+
 @pytest.mark.parametrize("case", [(1, 197, 4, 256, 256), (1, 100, 5, 384, 100), (2, 197, 3, 256, 130), (1, 520, 3, 160, 70),
                                   (1, 64, 9, 256, 200), (3, 33, 4, 640, 97)],
                          ids=["c5_like", "three_time_tiles", "two_heaps_ragged_n", "520_antennas_ragged_t", "64_antennas",
