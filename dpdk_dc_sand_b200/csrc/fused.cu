@@ -189,43 +189,35 @@ constexpr float kRint = 12582912.0f;  // 1.5 * 2^23: x + kRint - kRint = rint(x)
 // Steering phase in half-turns:  x = delay * scale + phase / pi   with   scale = (ch - N/2) * (-1 / (N Ts))
 // (reference: beamformer/unit_test/coeff_generator_cpu.py:143-165), delivered as a quadrant q = rint(2x) (its low two
 // bits are what matter) and the remainder t = x - q/2 in [-1/4, 1/4].  The product delay * scale reaches tens to
-// thousands of half-turns, so it is evaluated as a float pair (scale = s_hi + s_lo, exact FMA residual of the big term,
-// which is reduced mod 2 exactly); no float64 instruction on this path.
-//   static steering (kPair = false): t = (r0 - k/2) + u with r0 = big term mod 2, u = phase/pi + residuals and
-//     k = rint(2 (r0 + u)): two roundings at magnitude <= 1.25 and 0.25 -> angle error <= 2.8e-7 rad for |phase| <= pi
-//     (rms 4e-8; measured against float64 over 4e6 random entries), 6e-7 rad up to |phase| = 4 pi;
-//   per-heap times (kPair = true): delay and phase are float pairs themselves and the sum r0 + phase/pi keeps its
-//     rounding error (two-sum): angle error ~1e-7 rad.
-// Returns false when an operand is outside the range these tricks cover (|delay * scale| >= 2^20 half-turns, i.e.
-// milliseconds of delay, or |phase| >= 4 pi resp. 2^20 pi); the caller then redoes the entry with steer_tq_f64.
+// thousands of half-turns, so it is evaluated to float64 accuracy WITHOUT float64 instructions: scale = s_hi + s_lo
+// and 1/pi are split into float pairs, products carry their exact FMA residuals, the big term is reduced mod 2
+// exactly, and the rounding of the sum r0 + phase/pi is captured by a two-sum.  Angle error ~1e-7 rad.  (A leaner
+// variant without the two-sum and the residual of phase/pi -- 6 instructions fewer, 2.8e-7 rad -- was measured: no
+// faster at any configuration, the arithmetic of this role is off the critical path, and it cost four more cases of the
+// reference's own op-sequence test, whose atol = 1e-4 sits ~1e-7 sum|x| above zero where the antennas cancel.)
+// With kPair the delay and the phase are float pairs themselves (time-varying steering).
+// Returns false when an operand is outside the range these tricks cover (|delay * scale| or |phase / pi| >= 2^20
+// half-turns, i.e. milliseconds of delay); the caller then redoes the entry with steer_tq_f64.
 template <bool kPair>
 __device__ __forceinline__ bool steer_tq_fast(float d_hi, float d_lo, float ph_hi, float ph_lo, float s_hi, float s_lo, float* t,
                                               int* q) {
     const float p = d_hi * s_hi;
+    const float u = ph_hi * kInvPiHi;
     float e = fmaf(d_hi, s_hi, -p);  // exact residual of p
     e = fmaf(d_hi, s_lo, e);
     if (kPair) e = fmaf(d_lo, s_hi, e);
+    e += fmaf(ph_hi, kInvPiHi, -u);  // exact residual of u
     e = fmaf(ph_hi, kInvPiLo, e);
     if (kPair) e = fmaf(ph_lo, kInvPiHi, e);
     const float qf = fmaf(p, 0.5f, kRint) - kRint;  // rint(p / 2)
     const float r0 = fmaf(qf, -2.0f, p);            // p mod 2 in [-1, 1], exact
-    if (!kPair) {
-        const float u = fmaf(ph_hi, kInvPiHi, e);
-        const float z = fmaf(r0 + u, 2.0f, kRint);
-        *q = __float_as_int(z);
-        *t = fmaf(z - kRint, -0.5f, r0) + u;
-        return (fabsf(p) < 1048576.0f) & (fabsf(u) < 4.0f);
-    } else {
-        const float u = ph_hi * kInvPiHi;
-        e += fmaf(ph_hi, kInvPiHi, -u);  // exact residual of u
-        const float s1 = r0 + u;
-        const float bb = s1 - r0;
-        const float err = (r0 - (s1 - bb)) + (u - bb);  // rounding error of s1 (two-sum)
-        const float z = fmaf(s1, 2.0f, kRint);
-        *q = __float_as_int(z);
-        *t = fmaf(z - kRint, -0.5f, s1) + (e + err);
-        return (fabsf(p) < 1048576.0f) & (fabsf(u) < 1048576.0f);
-    }
+    const float s1 = r0 + u;
+    const float bb = s1 - r0;
+    const float err = (r0 - (s1 - bb)) + (u - bb);  // rounding error of s1 (two-sum)
+    const float z = fmaf(s1, 2.0f, kRint);
+    *q = __float_as_int(z);
+    *t = fmaf(z - kRint, -0.5f, s1) + (e + err);
+    return (fabsf(p) < 1048576.0f) & (fabsf(u) < 1048576.0f);
 }
 // The same in float64, for operands outside the range of steer_tq_fast (nothing physical; any finite input works).
 // (Out of line and by value: a pointer result would force the callers' (t, q) arrays into local memory.)
@@ -246,19 +238,23 @@ __device__ __noinline__ Tq steer_tq_f64(float d_hi, float d_lo, float ph_hi, flo
     return r;
 }
 
-// kCoefScale * (sin, cos)(pi (t + q/2)) for t in [-1/4, 1/4]: odd / even minimax polynomials in t of degree 7 / 6
-// (fit error 1.8e-9 / 3.2e-8, 9e-8 as evaluated in float32; their constants carry the power-of-two scale, same
-// roundings as unscaled), then the quadrant rotation.  The sign of the sine is returned flipped (`nsn` = -sin): that is
+// kCoefScale * (sin, cos)(pi (t + q/2)) for t in [-1/4, 1/4]: odd / even Taylor polynomials in t of degree 9 / 10
+// (truncation < 2e-9 and 2e-10; their constants carry the power-of-two scale, same roundings as unscaled), then the
+// quadrant rotation.  Absolute error <= ~6e-8 of the unscaled value as evaluated in float32.  (Degree-7 / degree-6
+// minimax fits -- three FFMA fewer, 9e-8 -- were measured: no faster, and two more cases of the reference's own
+// op-sequence test fell out of its atol = 1e-4.)  The sign of the sine is returned flipped (`nsn` = -sin): that is
 // the value the B operand holds next to the cosine.
 __device__ __forceinline__ void sincos_quadrant(float t, int q, float* nsn, float* cs) {
     constexpr float K = kCoefScale;
     const float s = t * t;
-    float ps = fmaf(s, K * -5.8882538010e-01f, K * 2.5497494840e+00f);
-    ps = fmaf(ps, s, K * -5.1677078199e+00f);
-    ps = fmaf(s, ps, K * 3.14159274f);
-    ps *= t;
-    float pc = fmaf(s, K * -1.3072800178e+00f, K * 4.0577017906e+00f);
-    pc = fmaf(pc, s, K * -4.9347918159e+00f);
+    float ps = fmaf(s, K * 0.0821458866f, K * -0.599264529f);   // pi^9/9!, -pi^7/7!
+    ps = fmaf(ps, s, K * 2.55016404f);                           // pi^5/5!
+    ps = fmaf(ps, s, K * -5.16771278f);                          // -pi^3/3!
+    ps = fmaf(ps * s, t, t * (K * 3.14159274f));                 // t*pi + t*s*(...)
+    float pc = fmaf(s, K * -0.0258068914f, K * 0.235330630f);    // -pi^10/10!, pi^8/8!
+    pc = fmaf(pc, s, K * -1.33526277f);                          // -pi^6/6!
+    pc = fmaf(pc, s, K * 4.05871213f);                           // pi^4/4!
+    pc = fmaf(pc, s, K * -4.93480220f);                          // -pi^2/2!
     pc = fmaf(pc, s, K);
     const bool swap = q & 1;
     const float a = swap ? pc : ps, b = swap ? ps : pc;
