@@ -72,6 +72,13 @@ constexpr int kProducerWarp = kCoeffWarps + 8;
 constexpr int kMmaWarp = kCoeffWarps + 9;     // issues the pol-0 MMAs (and owns the TMEM allocation)
 constexpr int kMmaWarp2 = kCoeffWarps + 10;   // issues the pol-1 MMAs: the issue path, not the tensor pipe, limits narrow tiles
 constexpr int kThreads = (kCoeffWarps + 12) * 32;  // the last warp only keeps the last warpgroup whole
+// int8 output: a second epilogue warpgroup, warps 28..31, one group per pol.  Quantising costs ~3 ALU instructions per
+// value on top of the float32 epilogue, and the four epilogue warps share their schedulers with the coefficient role:
+// they were busy 275 of 290 us at C3 while every other role waited for them.  The kernel then starts from 64 registers
+// per thread (32 warps) and splits 72 (coefficients) / 72 (epilogue) / 40 / 40.
+constexpr int kEpilogue2Warp0 = kCoeffWarps + 12;
+constexpr int kThreadsQ8 = kThreads + 128;
+static_assert(kThreadsQ8 * 64 <= 65536 && kCoeffWarps * 72 + 8 * 72 + 4 * 40 + 4 * 40 <= (kCoeffWarps + 16) * 64, "register pool, int8 output");
 // registers per thread at launch (the __launch_bounds__ cap) and per role after setmaxnreg; the roles' sum must fit the
 // CTA's pool of kThreads * kRegsLaunch
 #if DCBF_COEFF_WARPS == 16
@@ -316,11 +323,25 @@ __device__ __forceinline__ uint32_t quantise4(const uint32_t (&r)[32], int j, fl
     return __byte_perm(__byte_perm(m[0], m[1], 0x0040u), __byte_perm(m[2], m[3], 0x0040u), 0x5410u);
 }
 
+// The same for values that are known to stay below 2^15 quantisation steps (the caller checks 510 * A * max|gain| -- the
+// largest |beam * gain| 8-bit voltages can produce -- against it): scale, round and bias by 128 in one FFMA (an even
+// bias keeps round-half-even), then clamp PAIRS of 16-bit results with one add-min-relu each, pack, and undo the bias on
+// the packed word: 11 instructions per four values instead of 15.
+__device__ __forceinline__ uint32_t quantise4_fast(const uint32_t (&r)[32], int j, float gain) {
+    uint32_t m[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = __float_as_uint(fmaf(__uint_as_float(r[4 * j + i]), gain, 12582912.0f + 128.0f));
+    // low halves = k + 128;  relu(min(k + 127, 254)) = clip(k, -127, 127) + 127
+    const uint32_t c01 = __viaddmin_s16x2_relu(__byte_perm(m[0], m[1], 0x5410u), 0xffffffffu, 0x00fe00feu);
+    const uint32_t c23 = __viaddmin_s16x2_relu(__byte_perm(m[2], m[3], 0x5410u), 0xffffffffu, 0x00fe00feu);
+    return (__byte_perm(c01, c23, 0x6420u) + 0x01010101u) ^ 0x80808080u;  // bytes t in [0, 254] -> t - 127 (two's complement)
+}
+
 // ------------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------------
 template <bool kProf, bool kTv, bool kQ8, bool kMerged, bool kStream, bool kPair = false>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kQ8 ? kThreadsQ8 : kThreads, 1)
 fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_constant__ CUtensorMap tm_in,
                       const __grid_constant__ CUtensorMap tm_out) {
     extern __shared__ uint8_t smem_raw[];
@@ -379,7 +400,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         }
         for (int s = 0; s < kAccBufs; ++s) {
             mbar_init(bar(kAccFull + s), 2);
-            mbar_init(bar(kAccEmpty + s), kPair ? 8 : 4);
+            mbar_init(bar(kAccEmpty + s), (kPair ? 8 : 4) * (kQ8 ? 2 : 1));  // one arrival per epilogue warp (and CTA)
         }
         ctl->abort = 0;
         ctl->chan_pub = 0;
@@ -393,7 +414,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         const int used16 = kStream ? kBopBufBytes / 16 : prm.raw_extra_off / 16;  // 16-byte units per buffer
         for (int buf = 0; buf < kBopBufs; ++buf) {
             uint4* z = reinterpret_cast<uint4*>(smem_gen + buf * kBopBufBytes);
-            for (int i = threadIdx.x; i < used16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+            for (int i = threadIdx.x; i < used16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
         }
         fence_proxy_async_smem();
     }
@@ -499,8 +520,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     const unsigned long long role_t0 = prof_lane ? global_ns() : 0ull;
     const unsigned long long role_t0_cta = (kProf && threadIdx.x < 24) ? global_ns() : 0ull;
 
-    if (warp >= kProducerWarp) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 " DCBF_STR(DCBF_REGS_ISSUE) ";");
+    if (warp >= kProducerWarp && warp < kProducerWarp + 4) {
+        if constexpr (kQ8) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 " DCBF_STR(DCBF_REGS_ISSUE) ";");
     }
     if (warp == kProducerWarp) {
         // =================================== TMA producer ===================================
@@ -716,12 +738,21 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 __syncwarp();
             }
         }
-    } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + 4) {
+    } else if ((warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + 4) || (kQ8 && warp >= kEpilogue2Warp0)) {
         // =================================== epilogue ===================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 " DCBF_STR(DCBF_REGS_EPILOGUE) ";");
+        if constexpr (kQ8) asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 " DCBF_STR(DCBF_REGS_EPILOGUE) ";");
         const int q = warp & 3;  // TMEM lane quarter this warp may read
-        const uint32_t ost = ost_base + static_cast<uint32_t>(q) * (2 * kOutBoxBytes);
+        // int8 output: two warpgroups, group g quantises pol g; every warp then has 4 KiB of staging (one wide box or
+        // four 1 KiB blocks) instead of 8
+        const int egroup = kQ8 && warp >= kEpilogue2Warp0 ? 1 : 0;
+        const uint32_t ost = ost_base + (kQ8 ? static_cast<uint32_t>(egroup * 4 + q) * kOutBoxBytes
+                                             : static_cast<uint32_t>(q) * (2 * kOutBoxBytes));
         const float q8_gain = kQ8 ? ctl->q8_gmax : 0.f, q8_limit = q8_gain > 0.f ? 127.0f / q8_gain : 0.f;
+        // 8-bit voltages bound every beam by 510 A (|re| + |im| <= 510 per antenna, unit coefficients, gains <= max|gain|):
+        // when that is below 2^15 quantisation steps the packed 16-bit clamp is exact (no counter, no weights: both need
+        // the float comparison)
+        const bool q8_fast = kQ8 && !prm.saturated && !prm.weights && 510.0f * static_cast<float>(A) * q8_gain < 32000.0f;
         constexpr bool merged = kMerged;  // a specialisation: the extra 32 registers must not weigh on the wide-tile build
         const uint32_t acc_cols = static_cast<uint32_t>(merged ? 2 * nt : nt);  // TMEM columns per (buffer, pol)
         // 32 accumulator columns of this thread's row; merged tiles keep the hi and lo coefficient parts in two
@@ -853,7 +884,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         if (!ok) break;
                         tc_fence_after();
                         for (int h = 0; h < uhn; ++h)
-                            for (int p = 0; p < kPols; ++p) {
+                            for (int p = kQ8 ? egroup : 0; p < (kQ8 ? egroup + 1 : kPols); ++p) {  // (int8 output: this warpgroup's pol)
                                 const uint32_t col0 = (static_cast<uint32_t>(h) * kPols + p) * static_cast<uint32_t>(nt);
                                 if constexpr (kQ8) {
                                     // requantised output, 32-column blocks through four rotating 1 KiB boxes (as below)
@@ -874,8 +905,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                         }
 #pragma unroll
                                         for (int j = 0; j < 8; ++j)
-                                            w[j] = prm.saturated ? quantise4<true>(r, j, q8_gain, q8_limit, &clipped)
-                                                                 : quantise4<false>(r, j, q8_gain, q8_limit, &clipped);
+                                            w[j] = q8_fast ? quantise4_fast(r, j, q8_gain)
+                                                   : prm.saturated ? quantise4<true>(r, j, q8_gain, q8_limit, &clipped)
+                                                                   : quantise4<false>(r, j, q8_gain, q8_limit, &clipped);
                                         if (prm.tma_store) {
                                             const uint32_t sb = ost + (box & 3u) * 1024u;
                                             const uint32_t dst = sb + lane * 32;  // [32 rows][32 B], 32B swizzle
@@ -934,12 +966,12 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                 // whole output rows (nt = 2M bytes: 32, 64 or 128) -> one box of 32 rows per pol:
                                 // 4x fewer, 4x longer rows for the TMA store engine than 32-byte pieces
                                 const uint32_t cmask = static_cast<uint32_t>(nt >> 4) - 1u;  // swizzle span = row length
-                                for (int p = 0; p < kPols && row0 < T; ++p, ++box) {
+                                for (int p = egroup; p <= egroup && row0 < T; ++p, ++box) {  // this warpgroup's pol
                                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kPols + p) * acc_cols;
-                                    const uint32_t sb = ost + (box & 1u) * kOutBoxBytes;
+                                    const uint32_t sb = ost;
                                     unsigned long long tp0 = 0, tp1 = 0, tp2 = 0;
                                     if (kProf && prof_lane) tp0 = global_ns();
-                                    bulk_wait_group_read<1>();  // (issuing lane) the store that last read this box is done
+                                    bulk_wait_group_read<0>();  // (issuing lane) the store that last read this box is done
                                     __syncwarp();
                                     if (kProf && prof_lane) tp1 = global_ns();
                                     // 32 columns of row `lane` -> 16-byte chunks c0/16 and c0/16 + 1, XOR-swizzled by the
@@ -948,8 +980,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                         uint32_t w[8];
 #pragma unroll
                                         for (int j = 0; j < 8; ++j)
-                                            w[j] = prm.saturated ? quantise4<true>(r, j, q8_gain, q8_limit, &clipped)
-                                                                 : quantise4<false>(r, j, q8_gain, q8_limit, &clipped);
+                                            w[j] = q8_fast ? quantise4_fast(r, j, q8_gain)
+                                                   : prm.saturated ? quantise4<true>(r, j, q8_gain, q8_limit, &clipped)
+                                                                   : quantise4<false>(r, j, q8_gain, q8_limit, &clipped);
                                         const uint32_t a0 = static_cast<uint32_t>(lane * nt + c0);
                                         const uint32_t a1 = a0 + 16u;
                                         st_shared_v4(sb + (a0 ^ (((a0 >> 7) & cmask) << 4)), w[0], w[1], w[2], w[3]);
@@ -962,18 +995,12 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                             tmem_wait_ld();
                                             put32(r, cb);
                                         }
-                                    } else {  // the next 32 columns are on their way from TMEM while these are quantised
-                                        uint32_t r0[32], r1[32];
-                                        tmem_ld_32x32b_x32(taddr, r0);
-                                        for (int cb = 0; cb < nt; cb += 64) {
+                                    } else {
+                                        for (int cb = 0; cb < nt; cb += 32) {
+                                            uint32_t r[32];
+                                            tmem_ld_32x32b_x32(taddr + cb, r);
                                             tmem_wait_ld();
-                                            if (cb + 32 < nt) tmem_ld_32x32b_x32(taddr + cb + 32, r1);
-                                            put32(r0, cb);
-                                            if (cb + 32 < nt) {
-                                                tmem_wait_ld();
-                                                if (cb + 64 < nt) tmem_ld_32x32b_x32(taddr + cb + 64, r0);
-                                                put32(r1, cb + 32);
-                                            }
+                                            put32(r, cb);
                                         }
                                     }
                                     if (kProf && prof_lane) tp2 = global_ns();
@@ -1005,8 +1032,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                 }
 #pragma unroll
                                 for (int j = 0; j < 8; ++j)
-                                    w[j] = prm.saturated ? quantise4<true>(r, j, q8_gain, q8_limit, &clipped)
-                                                         : quantise4<false>(r, j, q8_gain, q8_limit, &clipped);
+                                    w[j] = q8_fast ? quantise4_fast(r, j, q8_gain)
+                                           : prm.saturated ? quantise4<true>(r, j, q8_gain, q8_limit, &clipped)
+                                                           : quantise4<false>(r, j, q8_gain, q8_limit, &clipped);
                                 if (prm.tma_store) {
                                     const uint32_t dst = sb + lane * 32;  // [32 rows][32 B], 32B swizzle
                                     const uint32_t x = static_cast<uint32_t>((lane >> 2) & 1) << 4;
@@ -1028,7 +1056,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                                 static_cast<uint16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffffu);
                                 }
                             };
-                            for (int p = 0; p < kPols; ++p) {
+                            for (int p = egroup; p <= egroup; ++p) {  // this warpgroup's pol
                                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kPols + p) * acc_cols;
                                 const int plane = (b * kPols + p) * C + c;
                                 for (int cb = 0; cb < nt && row0 < T && n0 + cb < N2; cb += 32, ++box) {
@@ -1057,7 +1085,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         }
     } else if (warp >= kConvertWarp0 && warp < kConvertWarp0 + 4) {
         // =================================== convert ===================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 " DCBF_STR(DCBF_REGS_CONVERT) ";");
+        if constexpr (kQ8) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 " DCBF_STR(DCBF_REGS_CONVERT) ";");
         // thread = one sample row t; per 4-antenna chunk: 4 conflict-free LDS.32, 8 PRMT + 8 HSUB2, 2 STS.128
         // (quarter-warps write 8 distinct 16-byte chunks of the 64B-swizzled rows: conflict-free)
         const int t = threadIdx.x - kConvertWarp0 * 32;
@@ -1124,7 +1153,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         }
     } else if (warp < kCoeffWarp0 + kCoeffWarps) {
         // =================================== steering coefficients ===================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 " DCBF_STR(DCBF_REGS_COEFF) ";");
+        if constexpr (kQ8) asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");  // (from 64 at launch)
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 " DCBF_STR(DCBF_REGS_COEFF) ";");
         // delay_vals[c][m0 .. m0+mt) is one contiguous run of (beam, antenna) entries: the 256 threads walk it
         // with lane <-> consecutive entry, so every warp load is 512 contiguous bytes.  Each entry becomes four
         // 32-bit words (row 2m | row 2m+1) x (fp16 hi | fp16 lo residual); consecutive antennas are consecutive
@@ -1932,7 +1962,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(q8 ? kThreadsQ8 : kThreads);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[2];

@@ -519,6 +519,14 @@ def test_fused_q8_requantised_output(dropin, case):
     assert np.count_nonzero(diff) <= 1e-3 * diff.size
     assert want_clipped > 0 and abs(int(sat.item()) - want_clipped) <= 2 + 1e-3 * want_clipped
     assert _capi.fused_q8_bytes(b, a, c, t, m) == x.size + dv.size * 4 + got.size + 4 * m
+    # without the saturation counter the epilogue clamps pairs of 16-bit results (packed add-min-relu) whenever
+    # 510 * A * max|gain| < 2^15 steps, which these gains satisfy: the bytes must not change
+    assert 510.0 * a * float(gains.max()) < 32000.0
+    out2 = torch.full(ref.shape, 77, dtype=torch.int8, device="cuda")
+    _capi.fused_q8(torch.from_numpy(x).cuda(), torch.from_numpy(dv).cuda(), torch.from_numpy(gains).cuda(), out2,
+                   b, a, c, n, t, m, xid, TS, flags=flags)
+    _capi.fused_status()
+    np.testing.assert_array_equal(out2.cpu().numpy(), got)
 
 
 def test_q8_operator_and_host_plan(dropin):
