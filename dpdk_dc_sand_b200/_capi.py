@@ -73,7 +73,7 @@ class FusedOptions(C.Structure):
 
     _fields_ = [("struct_size", C.c_size_t), ("batch_dt_s", C.POINTER(C.c_double)), ("beam_weights", C.c_void_p),
                 ("beam_gains", C.c_void_p), ("beams_q8", C.c_void_p), ("saturated", C.c_void_p),
-                ("sample_dt_s", C.c_double)]
+                ("sample_dt_s", C.c_double), ("beam_weights_log2", C.c_int)]
 
 
 SIGNATURES["dcbf_fused_ex"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -201,7 +201,7 @@ def beamform(reordered, coeff, beams, n_batches, n_chans, n_samples, n_ants, n_b
 
 def fused_ex(samples, delay_vals, beams, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id,
              sample_period, flags=0, stream=None, batch_dt=None, weights=None, gains=None, beams_q8=None,
-             saturated=None, sample_dt=0.0) -> None:
+             saturated=None, sample_dt=0.0, weights_log2=0) -> None:
     """dcbf_fused_ex: any combination of per-heap (and, with ``sample_dt``, per-time-tile) times, per-(beam, antenna)
     weights and int8 output."""
     opts = FusedOptions()
@@ -214,16 +214,18 @@ def fused_ex(samples, delay_vals, beams, n_batches, n_ants, n_chans, n_chans_tot
     opts.beams_q8 = _ptr(beams_q8) if beams_q8 is not None else None
     opts.saturated = _ptr(saturated) if saturated is not None else None
     opts.sample_dt_s = float(sample_dt or 0.0)
+    opts.beam_weights_log2 = int(weights_log2) if weights is not None else 0
     check(load().dcbf_fused_ex(_ptr(samples), _ptr(delay_vals), _ptr(beams) if beams is not None else None, n_batches,
                                n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id, float(sample_period),
                                C.byref(opts), flags, _stream_handle(stream)), "dcbf_fused_ex")
 
 
 def fused(samples, delay_vals, beams, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id,
-          sample_period, flags=0, stream=None, batch_dt=None, weights=None, sample_dt=0.0) -> None:
+          sample_period, flags=0, stream=None, batch_dt=None, weights=None, sample_dt=0.0, weights_log2=0) -> None:
     if weights is not None or sample_dt:
         fused_ex(samples, delay_vals, beams, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id,
-                 sample_period, flags, stream, batch_dt=batch_dt, weights=weights, sample_dt=sample_dt)
+                 sample_period, flags, stream, batch_dt=batch_dt, weights=weights, sample_dt=sample_dt,
+                 weights_log2=weights_log2)
         return
     if batch_dt is not None:
         check(load().dcbf_fused_tv(_ptr(samples), _ptr(delay_vals), _ptr(beams), n_batches, n_ants, n_chans,

@@ -14,7 +14,7 @@ that code inspecting ``bufint_*`` after a call still finds the reference's conte
 """
 from .. import _capi
 from ..katsdpsigproc import accel
-from .coeff_generator import CoeffGeneratorTemplate, _device_weights
+from .coeff_generator import CoeffGeneratorTemplate, _device_weights, weights_log2
 from .matrix_multiply import MatrixMultiplyTemplate
 from .prebeamform_reorder import PreBeamformReorderTemplate
 
@@ -130,6 +130,7 @@ class OpSequence(accel.OperationSequence):
             self.buffer("bufout_mult").buffer, r.n_batches, r.n_ants, r.n_channels_per_stream, c.n_channels,
             r.n_samples_per_channel, c.n_beams, c.xeng_id, c.sample_period, self.flags(), self.command_queue.stream,
             batch_dt=self.batch_times, weights=weights, sample_dt=self.sample_dt if self.batch_times is not None else 0.0,
+            weights_log2=weights_log2(self),
         )
         if self.slots["bufint_data"].is_bound:
             self.prebeamform_reorder()

@@ -7,6 +7,8 @@ reference's operation order, float64 sincos, float32 store; ``delay_vals[c][beam
 reference GPU kernel's read index transposes ant/beam, which only uniform delays hide).  The launch does not
 host-synchronise (the reference calls ``cuda.synchronize()``, :250).
 """
+import math
+
 import numpy as np
 
 from .. import _capi
@@ -58,7 +60,25 @@ def _device_weights(op):
         op.beam_weights = w  # uploaded once; assign a new array to change the weights
     if tuple(w.shape) != (n_beams, n_ants) or w.dtype != torch.float32:
         raise ValueError("beam_weights must be float32 of shape (n_beams, n_ants)")
-    return w.contiguous()
+    w = w.contiguous()
+    # power-of-two bound of the weights for the fused kernel (dcbf_fused_options.beam_weights_log2), found once per
+    # tensor: max|w| <= 2^e keeps the fp16 coefficient pair at full precision for weights from 6e-5 to 3e4
+    if getattr(op, "_beam_weights_log2_of", None) is not w:
+        wmax = float(w.abs().max().item()) if w.numel() else 0.0
+        if not math.isfinite(wmax):
+            raise ValueError("beam_weights must be finite")
+        e = 0 if wmax == 0.0 else int(math.ceil(math.log2(wmax)))
+        if e > 15:
+            raise ValueError(f"beam_weights up to {wmax:g}: the fused path takes |w| <= 32768")
+        op._beam_weights_log2 = max(e, -14)
+        op._beam_weights_log2_of = w
+        op.beam_weights = w
+    return w
+
+
+def weights_log2(op) -> int:
+    """The power-of-two bound `_device_weights` found for ``op.beam_weights`` (0 without weights)."""
+    return int(getattr(op, "_beam_weights_log2", 0)) if op.beam_weights is not None else 0
 
 
 class CoeffGenerator(Operation):

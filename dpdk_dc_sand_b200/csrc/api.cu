@@ -194,11 +194,12 @@ int dcbf_fused_ex(const uint8_t* samples, const float* delay_vals, float* beams,
         return DCBF_ERR_INVALID_ARG;
     if (o.batch_dt_s && B > DCBF_MAX_TV_BATCHES) return DCBF_ERR_UNSUPPORTED;
     if (!(o.sample_dt_s == o.sample_dt_s) || (o.sample_dt_s != 0.0 && !o.batch_dt_s)) return DCBF_ERR_INVALID_ARG;
+    if (o.beam_weights_log2 < -14 || o.beam_weights_log2 > 15) return DCBF_ERR_INVALID_ARG;
     if (int e = check_device()) return e;
     const QuantisedOut qo{o.beams_q8, o.beam_gains, o.saturated};
     return launch_fused(samples, delay_vals, beams, B, A, C, N, T, M, static_cast<long long>(C) * xeng_id, sample_period,
                         o.batch_dt_s, flags, static_cast<cudaStream_t>(stream), q8 ? &qo : nullptr, o.beam_weights,
-                        o.batch_dt_s ? o.sample_dt_s : 0.0);
+                        o.batch_dt_s ? o.sample_dt_s : 0.0, o.beam_weights ? o.beam_weights_log2 : 0);
 }
 
 int dcbf_fused_status(int* role, int* barrier, int* block) {

@@ -42,6 +42,7 @@
 #include <cuda.h>
 
 #include <atomic>
+#include <cmath>
 #include <mutex>
 #include <type_traits>
 #include <cuda_fp16.h>
@@ -144,6 +145,11 @@ struct FusedParams {
     int ht_count;    // ceil(T / 128)
     int parts;       // 2 = fp16 hi+lo coefficients, 1 = fp16 hi only
     int signed_in;
+    // byte -> fp16 conversion of the voltages: byte b under the exponent byte `a_magic` is 2^(E-15) (1 + b / 1024), minus
+    // `a_bias` = 2^(E-15) (times 1 + 128/1024 for int8 input after the ^0x80 re-bias) leaves b * 2^(E-25); E = 15 + the
+    // caller's beam_weights_log2 (0: the plain 2^-10).  w_scale = 2^-beam_weights_log2 goes onto the weights.
+    uint32_t a_magic, a_bias;
+    float w_scale;
     int tma_store;   // 1: epilogue through shared memory + TMA tensor stores; 0: st.global from registers
     int merged;      // hi and lo coefficient rows form ONE N = 2 nt tile per MMA (nt <= 64); the epilogue adds the halves
     int q8_wide;     // q8 only: the N tile is the whole output row (32 / 64 / 128 bytes): one box per 32 rows
@@ -176,9 +182,9 @@ struct FusedParams {
 constexpr float kCoefScale = 1024.0f;
 
 // u8 (or i8) pair -> half2 of x / 1024, exact.  `w` holds {p0.re, p0.im, p1.re, p1.im}; sel picks the pol.
-__device__ __forceinline__ uint32_t bytes_to_half2(uint32_t w, uint32_t sel, uint32_t bias) {
+__device__ __forceinline__ uint32_t bytes_to_half2(uint32_t w, uint32_t sel, uint32_t bias, uint32_t magic) {
     // bytes -> 0x3Cbb = 1 + b / 1024 (fp16), then subtract 1 (u8) or 1 + 128 / 1024 (i8 after the ^0x80 re-bias)
-    const uint32_t h = __byte_perm(w, 0x3C3C3C3Cu, sel);
+    const uint32_t h = __byte_perm(w, magic, sel);
     const __half2 r = __hsub2(*reinterpret_cast<const __half2*>(&h), *reinterpret_cast<const __half2*>(&bias));
     return *reinterpret_cast<const uint32_t*>(&r);
 }
@@ -1090,7 +1096,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         // thread = one sample row t; per 4-antenna chunk: 4 conflict-free LDS.32, 8 PRMT + 8 HSUB2, 2 STS.128
         // (quarter-warps write 8 distinct 16-byte chunks of the 64B-swizzled rows: conflict-free)
         const int t = threadIdx.x - kConvertWarp0 * 32;
-        const uint32_t bias = prm.signed_in ? 0x3C803C80u : 0x3C003C00u;  // 1 + 128/1024 | 1 as fp16 pairs
+        const uint32_t bias = prm.a_bias, magic = prm.a_magic;  // (plain scale: 0x3C003C00 | 0x3C803C80 and 0x3C3C3C3C)
         const uint32_t flip = prm.signed_in ? 0x80808080u : 0u;
         const uint32_t sw = static_cast<uint32_t>((t >> 1) & 3);
         uint32_t slab = 0, rs = 0, rph = 0;
@@ -1131,11 +1137,11 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
 #pragma unroll
                             for (int i = 0; i < 4; ++i) w[4 * j + i] ^= flip;
                             const uint32_t off = (static_cast<uint32_t>(j) ^ sw) << 4;
-                            st_shared_v4(dst0 + off, bytes_to_half2(w[4 * j], 0x4140u, bias), bytes_to_half2(w[4 * j + 1], 0x4140u, bias),
-                                         bytes_to_half2(w[4 * j + 2], 0x4140u, bias), bytes_to_half2(w[4 * j + 3], 0x4140u, bias));
-                            st_shared_v4(dst0 + kAopTileBytes + off, bytes_to_half2(w[4 * j], 0x4342u, bias),
-                                         bytes_to_half2(w[4 * j + 1], 0x4342u, bias), bytes_to_half2(w[4 * j + 2], 0x4342u, bias),
-                                         bytes_to_half2(w[4 * j + 3], 0x4342u, bias));
+                            st_shared_v4(dst0 + off, bytes_to_half2(w[4 * j], 0x4140u, bias, magic), bytes_to_half2(w[4 * j + 1], 0x4140u, bias, magic),
+                                         bytes_to_half2(w[4 * j + 2], 0x4140u, bias, magic), bytes_to_half2(w[4 * j + 3], 0x4140u, bias, magic));
+                            st_shared_v4(dst0 + kAopTileBytes + off, bytes_to_half2(w[4 * j], 0x4342u, bias, magic),
+                                         bytes_to_half2(w[4 * j + 1], 0x4342u, bias, magic), bytes_to_half2(w[4 * j + 2], 0x4342u, bias, magic),
+                                         bytes_to_half2(w[4 * j + 3], 0x4342u, bias, magic));
                         }
                         if (kProf && prof_lane) tc1 = global_ns();
                         fence_proxy_async_smem();
@@ -1361,7 +1367,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                     const int m = wl + kCoeffWarps * u;
                                     f[u] = 1.0f;
                                     if (st_mask & (1u << u)) {
-                                        if (w_tile) f[u] = __ldg(w_tile + static_cast<size_t>(m) * A + a);
+                                        if (w_tile) f[u] = __ldg(w_tile + static_cast<size_t>(m) * A + a) * prm.w_scale;
                                         if constexpr (kQ8) f[u] *= __ldg(prm.gains + m0 + m) * ks_inv_gmax;
                                     }
                                 }
@@ -1557,7 +1563,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 float nsn, cs;
                 sincos_quadrant(t, q, &nsn, &cs);
                 if (w_tile && valid) {  // ?beam-weights: real weight of this (beam, antenna); the table is tiny and stays in L1/L2
-                    const float w = __ldg(w_tile + e);
+                    const float w = __ldg(w_tile + e) * prm.w_scale;
                     cs *= w;
                     nsn *= w;
                 }
@@ -1791,7 +1797,7 @@ int get_encode_fn(EncodeTiledFn* out) {
 
 int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T,
                  int M, long long first_chan, double sample_period, const double* batch_dt_s, unsigned flags,
-                 cudaStream_t s, const QuantisedOut* q8, const float* beam_weights, double sample_dt_s) {
+                 cudaStream_t s, const QuantisedOut* q8, const float* beam_weights, double sample_dt_s, int weights_log2) {
     FusedParams p{};
     p.dv = reinterpret_cast<const float4*>(delay_vals);
     p.samples = samples;
@@ -1805,6 +1811,13 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     p.B = B, p.A = A, p.C = C, p.T = T, p.M = M;
     p.parts = (flags & DCBF_FLAG_FP16_COEFF) ? 1 : 2;
     p.signed_in = (flags & DCBF_FLAG_SIGNED_INPUT) ? 1 : 0;
+    {
+        const uint32_t e_field = static_cast<uint32_t>(15 + (beam_weights ? weights_log2 : 0));  // fp16 exponent field, 1 .. 30
+        const uint32_t half_bias = (e_field << 10) | (p.signed_in ? 0x80u : 0u);
+        p.a_magic = (e_field << 2) * 0x01010101u;
+        p.a_bias = half_bias * 0x00010001u;
+        p.w_scale = std::ldexp(1.0f, -(beam_weights ? weights_log2 : 0));
+    }
     pick_n_tiling(A, M, p.parts, &p.kb_count, &p.nt, &p.nt_count);
     const bool no_whole_tiles = p.nt < 16;  // > 512 antennas (hi+lo): not even a 16-column tile set fits a 64 KiB buffer
     p.slab_count = (A + kSlabAnts - 1) / kSlabAnts;

@@ -155,6 +155,12 @@ unsigned long long dcbf_fused_q8_bytes(int n_batches, int n_ants, int n_chans, i
  *                 steering coefficient -- what the control plane's `?beam-weights <stream> w_0 .. w_{A-1}` request carries
  *                 (reference: ngkcs/ngkcs/corr3_servlet.py:140-153, which only forwards it); update it between calls
  *                 like delay_vals, nothing is cached
+ *                 Range: the weights enter the tensor cores as fp16 pairs scaled by 2^10 / 2^beam_weights_log2, so
+ *                 max|w| <= 2^beam_weights_log2 must hold (default 0: |w| <= 1; up to 60 is still safe).
+ *   beam_weights_log2   e in [-14, 15]: the caller's bound max|w| <= 2^e.  The kernel multiplies the weights by 2^-e and
+ *                 the voltages by 2^e (both exact: the voltages' scale is the exponent of the byte -> fp16 conversion),
+ *                 so weights from 6e-5 to 3e4 keep the full precision of the coefficient pair.  The Python operators set
+ *                 it from the weights themselves.
  *   beams_q8 / beam_gains / saturated   int8 output as dcbf_fused_q8 (then `beams` may be NULL) */
 typedef struct dcbf_fused_options {
     size_t struct_size;
@@ -164,6 +170,7 @@ typedef struct dcbf_fused_options {
     int8_t* beams_q8;
     unsigned long long* saturated;
     double sample_dt_s;
+    int beam_weights_log2;
 } dcbf_fused_options;
 int dcbf_fused_ex(const uint8_t* samples, const float* delay_vals, float* beams, int n_batches, int n_ants,
                   int n_chans, int n_chans_total, int n_samples, int n_beams, int xeng_id, double sample_period,

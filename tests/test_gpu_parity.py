@@ -590,6 +590,36 @@ def test_beam_weights(dropin):
         np.testing.assert_allclose(outs[True], outs[False], rtol=0, atol=float(_budget(x).max()) * 2.0 ** -5)
 
 
+@pytest.mark.parametrize("scale", [1e-4, 1.0, 37.0, 1e4], ids=["w_1e-4", "w_1", "w_37", "w_1e4"])
+def test_beam_weights_of_any_magnitude(dropin, scale):
+    """Weights far from 1 (|w| > 64 used to overflow the fp16 coefficient pair, |w| < 1e-3 lost its
+    residual to fp16 subnormals): the operator passes a power-of-two bound of the weights (beam_weights_log2), the
+    kernel moves it from the coefficients onto the voltages' conversion exponent, and the result keeps the same
+    RELATIVE accuracy at every magnitude -- inside the budget scaled by max|w|, and equal to the float64-weighted
+    three-kernel chain."""
+    from beamforming.beamform_op_sequence import OpSequenceTemplate
+
+    ctx, queue = dropin
+    b, a, c, t, m, n, xid = 1, 40, 5, 128, 6, 1024, 1
+    x = orc.make_samples(b, a, c, t, seed=75)
+    dv = orc.make_delay_vals_random(c, m, a, seed=76)
+    w = (np.random.default_rng(77).uniform(0.1, 1.0, (m, a)) * scale).astype(np.float32)
+    ref = orc.beamform_pipeline(x, dv, n, xid, TS, weights=w)
+    outs = {}
+    for fused in (True, False):
+        op = OpSequenceTemplate(ctx, b, 2, c, n, t // 16, 16, a, m, xid, TS, t).instantiate(queue)
+        op.fused, op.beam_weights = fused, w
+        op.ensure_all_bound()
+        op.buffer("bufin_reorder").set(queue, x)
+        op.buffer("bufin_delay_vals").set(queue, dv)
+        op()
+        outs[fused] = op.buffer("bufout_mult").get(queue).astype(np.float64)
+        assert np.all(np.isfinite(outs[fused]))
+    wmax = float(np.abs(w).max())
+    assert np.all(np.abs(outs[True] - ref) <= 2.0 ** -10 * wmax * _budget(x))  # 2^-20 * max|w| * sum|x|
+    np.testing.assert_allclose(outs[True], outs[False], rtol=0, atol=float(_budget(x).max()) * wmax * 2.0 ** -8)
+
+
 def test_delay_model_updater_switches_at_a_heap_boundary(dropin):
     """Double-buffered delay_vals / weights update: heaps launched before activate() use the old
     model, heaps launched after it use the new one, and the upload runs on a side stream."""
