@@ -21,7 +21,8 @@ void count_launch(unsigned n = 1);
         if (_e != cudaSuccess) return ::dcbf::record_cuda_error(_e, #expr); \
     } while (0)
 
-// Peek (not clear) launch errors right after a kernel launch.
+// Launch errors right after a kernel launch (cudaGetLastError returns AND clears the error; it is recorded for
+// dcbf_last_cuda_error and the call fails).
 #define DCBF_CHECK_LAUNCH(name)                                         \
     do {                                                                \
         cudaError_t _e = cudaGetLastError();                            \
