@@ -162,7 +162,8 @@ struct FusedParams {
     // channels is cut into `split` units along its list of tile_count accumulator tiles (N tile, batch, time tile), so
     // that the last round of the persistent CTAs is a fraction of a channel instead of a whole one
     int n_whole, split, tile_count;
-    int dbg;         // developer experiments: 1 = no delay_vals loads, 2 = no phase / sin-cos arithmetic, 4 = no output stores
+    int dbg;         // developer experiments: 1 = no delay_vals loads, 2 = no phase / sin-cos arithmetic, 4 = no output stores,
+                     // 8 = no L2 prefetches of delay_vals (C3: 268 -> 290 us without them; C5 share: no difference)
     int pdl_wait;    // 1: wait for the preceding kernel of the stream (griddepcontrol.wait) after the prologue
     int raw_extra_off;  // byte offset of the first extra stage inside each 64 KiB B buffer
     uint32_t inv_a;     // floor(2^32 / A) + 1: e / A == umulhi(e, inv_a) for every entry index of an N tile (A >= 2)
@@ -1197,6 +1198,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             if (m0 >= M) return;
             const size_t bytes = static_cast<size_t>(min(mt_cta, M - m0)) * A * 16;
             const char* p = reinterpret_cast<const char*>(prm.dv + (static_cast<size_t>(ch) * M + m0) * A);
+            if (prm.dbg & 8) return;
             for (size_t o = 0; o < bytes; o += 65536)
                 bulk_prefetch_l2(p + o, static_cast<uint32_t>(min(bytes - o, static_cast<size_t>(65536))));
         };
