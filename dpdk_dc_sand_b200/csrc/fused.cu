@@ -277,6 +277,16 @@ __device__ __forceinline__ void sincos_quadrant(float t, int q, float* nsn, floa
     *cs = __int_as_float(__float_as_int(b) ^ (((q + 1) << 30) & 0x80000000));
 }
 
+// (delay_s, phase_rad) of a delay_vals entry whose four fields were loaded with ONE 128-bit instruction.  The two rate
+// fields are folded in as `x | (rate & 0)`: a real instruction that keeps them -- and with them the vector load -- alive;
+// with two fields dead ptxas narrows the load into two 32-bit loads, each of which walks the warp's 512-byte span again.
+__device__ __forceinline__ float2 delay_and_phase(const float4& e) {
+    uint32_t x = __float_as_uint(e.x), z = __float_as_uint(e.z);
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0xF8;" : "+r"(x) : "r"(__float_as_uint(e.y)), "r"(0u));
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0xF8;" : "+r"(z) : "r"(__float_as_uint(e.w)), "r"(0u));
+    return make_float2(__uint_as_float(x), __uint_as_float(z));
+}
+
 // One (beam, antenna) coefficient -> the four 32-bit words of the B operand: rows n = 2m (k = 2a: cos, 2a+1: -sin) and
 // n = 2m+1 (sin, cos), each as fp16 hi and fp16 residual (lo).
 __device__ __forceinline__ void coef_words(float nsn, float cs, uint32_t* hi0, uint32_t* hi1, uint32_t* lo0, uint32_t* lo1) {
@@ -1254,7 +1264,10 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             // delay_vals in flight: the loads of a step are issued kDepth steps ahead, into one of kDepth register sets
             // picked by the step's parity (one copy of the step body per set, so that the set is a compile-time choice).
             constexpr int kDepth = 1;  // (2 was tried: 301 -> 320 us at the C5 share even with 80 registers for this role)
-            Dv nxt[kDepth][kPer];  // static: (delay_s, phase_rad); kTv: all four fields
+            // All four fields of an entry are loaded with one 128-bit instruction and kept until the step consumes them
+            // (delay_and_phase).  Invalid entries load a valid dummy address instead of being predicated (a predicated vector
+            // load is split into scalar loads as well); only the stores are masked.
+            float4 nxt[kDepth][kPer];
             // the cursor's unit, decoded once per unit (the divisions would otherwise sit in every k-block step): this
             // thread's entry (beam wl, antenna lane) of the unit's first k-block, and which of its four beams exist
             const float4* n_ptr = prm.dv;
@@ -1277,12 +1290,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 const float4* p = n_ptr + kKbAnts * nkb;
                 const uint32_t mask = kKbAnts * nkb + lane < A ? n_mask : 0u;
 #pragma unroll
-                for (int u = 0; u < kPer; ++u) {
-                    float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (mask & (1u << u)) t4 = ldg_nc_f4(p + u * u_stride);
-                    if constexpr (kTv) nxt[set][u] = t4;
-                    else nxt[set][u] = make_float2(t4.x, t4.z);
-                }
+                for (int u = 0; u < kPer; ++u) nxt[set][u] = ldg_nc_f4((mask & (1u << u)) ? p + u * u_stride : prm.dv);
             };
             auto advance_cursor = [&]() {
                 if (is_sched) {
@@ -1338,7 +1346,10 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         const uint32_t slot = kstep % kBSlots;
                         Dv v[kPer];
 #pragma unroll
-                        for (int u = 0; u < kPer; ++u) v[u] = nxt[set][u];
+                        for (int u = 0; u < kPer; ++u) {
+                            if constexpr (kTv) v[u] = nxt[set][u];
+                            else v[u] = delay_and_phase(nxt[set][u]);
+                        }
                         advance_cursor();
                         issue_loads(set_c);
                         const int a = kKbAnts * kb + lane;
@@ -1466,7 +1477,10 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         int nw = sched_get(ctl, 0), n_ch = 0, nisb = 0, nisb_last = 0, ne0 = ctid;
         int n_entries = 0;
         const float4* n_src = prm.dv;
-        Dv nxt[kBatch];  // static: (delay_s, phase_rad), the two rate fields are ignored like the reference does
+        // (static: (delay_s, phase_rad), the two rate fields are ignored like the reference does.  The compiler narrows
+        // the 128-bit load to two 32-bit loads then; keeping it whole as the K-streamed step does was measured here too:
+        // C3 262 -> 264.5 us, C4 share 191 -> 194 us -- eight more registers in flight cost more than the LSU passes)
+        Dv nxt[kBatch];
         auto cursor_unit = [&]() {  // the cursor's unit -> channel and its range of (N tile, coefficient set) steps
             if (static_cast<uint32_t>(nw) < n_units) {
                 uint32_t uc;
