@@ -1480,7 +1480,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         // (static: (delay_s, phase_rad), the two rate fields are ignored like the reference does.  The compiler narrows
         // the 128-bit load to two 32-bit loads then; keeping it whole as the K-streamed step does was measured here too:
         // C3 262 -> 264.5 us, C4 share 191 -> 194 us -- eight more registers in flight cost more than the LSU passes)
-        Dv nxt[kBatch];
+        constexpr bool kWhole128 = kQ8 && !kTv;  // (int8 output: this role bounds the kernel there, see the epilogue)
+        using Nx = typename std::conditional<kTv || kWhole128, float4, float2>::type;
+        Nx nxt[kBatch];
         auto cursor_unit = [&]() {  // the cursor's unit -> channel and its range of (N tile, coefficient set) steps
             if (static_cast<uint32_t>(nw) < n_units) {
                 uint32_t uc;
@@ -1500,10 +1502,14 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
                 const int e = ne0 + u * kStride;
-                float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (e < n_entries && !(prm.dbg & 1)) t4 = ldg_nc_f4(n_src + e);
-                if constexpr (kTv) nxt[u] = t4;
-                else nxt[u] = make_float2(t4.x, t4.z);
+                if constexpr (kWhole128) {
+                    nxt[u] = ldg_nc_f4((e < n_entries && !(prm.dbg & 1)) ? n_src + e : prm.dv);  // (a dummy address, not a predicate)
+                } else {
+                    float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e < n_entries && !(prm.dbg & 1)) t4 = ldg_nc_f4(n_src + e);
+                    if constexpr (kTv) nxt[u] = t4;
+                    else nxt[u] = make_float2(t4.x, t4.z);
+                }
             }
         };
         auto advance_cursor = [&]() {
@@ -1627,7 +1633,10 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     const unsigned long long tl0 = kProf && prof_lane ? global_ns() : 0ull;
                     Dv v[kBatch];
 #pragma unroll
-                    for (int u = 0; u < kBatch; ++u) v[u] = nxt[u];
+                    for (int u = 0; u < kBatch; ++u) {
+                        if constexpr (kWhole128) v[u] = delay_and_phase(nxt[u]);
+                        else v[u] = nxt[u];
+                    }
                     if (kProf && prof_lane) {  // developer probe: time spent waiting for this batch's delay_vals to land
                         float sink = 0.f;
 #pragma unroll

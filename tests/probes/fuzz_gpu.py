@@ -26,7 +26,7 @@ def main():
     many_channels = "--many-channels" in sys.argv
     rng = np.random.default_rng(seed)
     dev = torch.device("cuda", 0)
-    worst_f, worst_b, bad = 0.0, 0.0, 0
+    worst_f, worst_b, bad, worst_tag = 0.0, 0.0, 0, ""
     for case in range(n_cases):
         B = int(rng.integers(1, 4))
         A = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 23, 31, 32, 33, 48, 63, 64, 65, 79, 80, 96, 100, 130, 197, 256, 300, 520]))
@@ -88,7 +88,8 @@ def main():
         else:
             got = out.cpu().numpy()
             ratio = float(np.max(np.abs(got - ref) / np.maximum(budget, 1e-30))) if not np.isnan(got).any() else float("inf")
-        worst_f = max(worst_f, ratio)
+        if ratio > worst_f:
+            worst_f, worst_tag = ratio, tag
         # stand-alone ops
         re = torch.empty((B, 2, C, T // 16, 16, A, 2), dtype=torch.uint8, device=dev)
         _capi.reorder(dx, re, B, A, C, T)
@@ -123,7 +124,7 @@ def main():
         if not ok or case % 20 == 0 or A > 512:
             print(tag, f"fused err/budget {ratio:.2e} reorder {'ok' if ok_re else 'BAD'} beamform {eb:.2e} coeffs {ec:.1e} "
                        f"plan {'ok' if ok_plan else 'BAD'} {'ok' if ok else 'FAIL'}", flush=True)
-    print(f"{n_cases} cases, {bad} failed; worst fused err/budget {worst_f:.2e}, worst beamform err/sum|x||w| {worst_b:.2e}")
+    print(f"{n_cases} cases, {bad} failed; worst fused err/budget {worst_f:.2e} ({worst_tag}), worst beamform err/sum|x||w| {worst_b:.2e}")
     sys.exit(1 if bad else 0)
 
 
