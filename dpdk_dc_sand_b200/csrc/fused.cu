@@ -100,6 +100,10 @@ static_assert(kCoeffWarps * DCBF_REGS_COEFF + 4 * (DCBF_REGS_CONVERT + DCBF_REGS
               "register pool of the CTA");
 #define DCBF_STR2(x) #x
 #define DCBF_STR(x) DCBF_STR2(x)
+// sleep between failed probes of the waits that are a whole buffer ahead of their consumer (tc_common.cuh: mbar_wait_slow)
+#ifndef DCBF_BACKOFF_NS
+#define DCBF_BACKOFF_NS 200
+#endif
 constexpr int kTileT = 128;    // samples per MMA tile (UMMA M)
 constexpr int kSlabAnts = 16;  // antennas per raw slab / A stage
 constexpr int kKbAnts = 32;    // antennas per B k-block (128-byte swizzle row of fp16)
@@ -547,7 +551,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         bool ok = true;
         // one raw slab: [16 antennas][128 samples] of (batch b, channel c) -> next ring stage
         auto load_slab = [&](int h, int c, int s, int b) {
-            if (!mbar_wait<kProf>(bar(kRawEmpty + rs), ph ^ 1u, ctl, prm.status, kRoleProducer, kRawEmpty + rs, ps + 0)) return false;
+            if (!mbar_wait<kProf, false, DCBF_BACKOFF_NS>(bar(kRawEmpty + rs), ph ^ 1u, ctl, prm.status, kRoleProducer, kRawEmpty + rs, ps + 0)) return false;
             if (elect_one()) {
                 mbar_arrive_expect_tx(bar(kRawFull + rs), kRawStageBytes);
                 tma_load_4d(raw_addr(rs), &tm_in, bar(kRawFull + rs), h * kTileT, c, s * kSlabAnts, b);
@@ -1354,7 +1358,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         issue_loads(set_c);
                         const int a = kKbAnts * kb + lane;
                         const uint32_t st_mask = a < A ? u_mask : 0u;  // entries of this thread that are stored
-                        ok = mbar_wait<kProf>(bar(kBopEmpty + slot), ((kstep / kBSlots) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + slot, ps + 0);
+                        ok = mbar_wait<kProf, false, DCBF_BACKOFF_NS>(bar(kBopEmpty + slot), ((kstep / kBSlots) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + slot, ps + 0);
                         if (!ok) return;
                         // beam m = wl + 16 u: row 2 m has the same swizzle phase for every u, so the four words of
                         // entry u sit at a constant 4096-byte stride from those of entry 0 (immediate offsets)
@@ -1647,7 +1651,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     advance_cursor();
                     issue_loads();
                     if (!waited) {
-                        ok = mbar_wait<kProf>(bar(kBopEmpty + bb), ((step / kBopBufs) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + bb, ps + 0);
+                        ok = mbar_wait<kProf, false, DCBF_BACKOFF_NS>(bar(kBopEmpty + bb), ((step / kBopBufs) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + bb, ps + 0);
                         waited = true;
                         if (!ok) break;
                     }

@@ -301,25 +301,49 @@ __device__ __forceinline__ int sched_get(Control* ctl, uint32_t k) {
     return ctl->chan_ring[k & 7];
 }
 
+// kSleepNs > 0: sleep between failed probes.  A suspended try_wait is woken by every arrival on ANY barrier of the CTA, so a
+// role that waits long (the coefficient warps for a free B buffer, the producer for a free raw stage) otherwise spins
+// through this loop at full rate: at C3 23 % of all executed warp instructions were the sixteen coefficient warps doing
+// exactly that -- issue slots and power taken from the roles that have work.  Only for waits whose wake-up latency is
+// off the critical path (the waiter is a whole buffer ahead).
+template <int kSleepNs = 0>
 __device__ __forceinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Control* ctl, int* status, int role, int id) {
     const unsigned long long t0 = global_ns();
     for (;;) {
         // up to 64 hardware-suspended probes in a 7-instruction loop, then one look at the abort flag / clock
         uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
-            "mov.u32 n, 0;\n"
-            "DCBF_WAIT_AGAIN:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "@p bra DCBF_WAIT_DONE;\n\t"
-            "add.u32 n, n, 1;\n\t"
-            "setp.lt.u32 q, n, 64;\n\t"
-            "@q bra DCBF_WAIT_AGAIN;\n"
-            "DCBF_WAIT_DONE:\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity), "r"(100000u)
-            : "memory");
+        if constexpr (kSleepNs > 0) {
+            asm volatile(
+                "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
+                "mov.u32 n, 0;\n"
+                "DCBF_WAITS_AGAIN:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "@p bra DCBF_WAITS_DONE;\n\t"
+                "nanosleep.u32 %4;\n\t"
+                "add.u32 n, n, 1;\n\t"
+                "setp.lt.u32 q, n, 64;\n\t"
+                "@q bra DCBF_WAITS_AGAIN;\n"
+                "DCBF_WAITS_DONE:\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(bar), "r"(parity), "r"(100000u), "r"(static_cast<uint32_t>(kSleepNs))
+                : "memory");
+        } else {
+            asm volatile(
+                "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
+                "mov.u32 n, 0;\n"
+                "DCBF_WAIT_AGAIN:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "@p bra DCBF_WAIT_DONE;\n\t"
+                "add.u32 n, n, 1;\n\t"
+                "setp.lt.u32 q, n, 64;\n\t"
+                "@q bra DCBF_WAIT_AGAIN;\n"
+                "DCBF_WAIT_DONE:\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(bar), "r"(parity), "r"(100000u)
+                : "memory");
+        }
         if (ok) return true;
         if (ctl->abort) return false;
         if (global_ns() - t0 > kWatchdogNs) {
@@ -340,14 +364,14 @@ __device__ __forceinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, Co
 // Warp-collective: every lane waits; the result is made warp-uniform.
 // kProf builds only: `slot` >= 0 on exactly one lane of a role makes that lane account its blocked time (the
 // first try_wait may itself suspend the thread, so the whole call is timed).
-template <bool kProf, bool kCluster = false>
+template <bool kProf, bool kCluster = false, int kSleepNs = 0>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, Control* ctl, int* status, int role, int id,
                                           int slot = -1) {
     unsigned long long t0 = 0;
     if (kProf && slot >= 0) t0 = global_ns();
     bool ok = mbar_try_wait<kCluster>(bar, parity) != 0;
     if (!ok) {
-        ok = mbar_wait_slow(bar, parity, ctl, status, role, id);
+        ok = mbar_wait_slow<kSleepNs>(bar, parity, ctl, status, role, id);
         if (kCluster && ok) mbar_try_wait<true>(bar, parity);  // (completed: this probe only adds the cluster-scope acquire)
     }
     if (kProf && slot >= 0) ctl->wait_ns[role][slot] += global_ns() - t0;
