@@ -21,8 +21,10 @@
 // accumulators are double-buffered across items so the epilogue of one overlaps the MMAs of the next.
 //
 // Antenna counts whose sample rows (2A bytes) are not a multiple of 16 bytes are fetched through an [8 samples x 2A]
-// view, eight small boxes per stage.  Odd beam counts (8M bytes per coefficient / output row not a multiple of 16)
-// stay on the float32 CUDA-core kernel in beamform.cu.
+// view, eight small boxes per stage.  Odd beam counts (8M bytes per coefficient / output row not a multiple of 16:
+// no tensor map can describe those rows) run here too: the split warps then read their coefficients straight from
+// global memory (8 consecutive columns per quarter-warp: whole 32-byte sectors) instead of TMA-staged boxes, and the
+// epilogue stores from registers (tcgen05.ld 16x256b -> st.global.v2, as the fused kernel does for odd beam counts).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -85,6 +87,9 @@ struct TcParams {
     int signed_in;
     int x_split;      // 2A is not a multiple of 16 bytes: X rows are fetched as 8 interleaved boxes (see launch_beamform_tc)
     int mma_warps;    // 2: one issuing warp per time tile of a group (narrow tiles are issue-bound); 1: wide tiles
+    int direct;       // odd beam count: coefficients by plain loads, beams by plain stores (rows are only 8-byte aligned)
+    const float* w;   // coefficients [units][K2][N2] (direct mode)
+    float* out;       // beams [units][T][N2] (direct mode)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -205,7 +210,7 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
         // =================================== W producer ===================================
         uint32_t ws = 0, ph = 0;
         const int boxes = nt >> 5;
-        for (long long item = blockIdx.x; item < items && ok; item += stride) {
+        for (long long item = blockIdx.x; item < items && ok && !prm.direct; item += stride) {
             int u, it, hg, hn;
             decode(item, &u, &it, &hg, &hn);
             for (int s = 0; s < kb_count; ++s) {
@@ -283,6 +288,32 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
             for (int h = 0; h < hn; ++h) {
                 const int row0 = (hg * kGroupTiles + h) * kTileT + 32 * q;  // this warp's 32 rows of the tile
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (ab * kGroupTiles + static_cast<uint32_t>(h)) * kNtMax;
+                if (prm.direct) {
+                    // 16 rows x 16 columns per load: lane holds row lane/4 (+8), columns 2 (lane%4) + {0,1} (+8): a quad
+                    // writes 32 contiguous bytes of a row
+                    const int n0 = it * nt;
+                    for (int half = 0; half < 2; ++half) {
+                        const int r_lo = row0 + 16 * half + (lane >> 2);
+                        const uint32_t ta = taddr + (static_cast<uint32_t>(16 * half) << 16);
+                        float* row_lo = prm.out + (static_cast<size_t>(u) * prm.T + r_lo) * prm.N2 + n0 + 2 * (lane & 3);
+                        float* row_hi = row_lo + 8 * static_cast<size_t>(prm.N2);
+                        const bool v_lo = r_lo < prm.T, v_hi = r_lo + 8 < prm.T;
+                        for (int cb = 0; cb < nt; cb += 16) {
+                            uint32_t r[8];
+                            tmem_ld_16x256b_x2(ta + cb, r);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                const int col = cb + 8 * i;
+                                if (n0 + col + 2 * (lane & 3) < prm.N2) {  // (N2 is even: a pair is inside or outside as a whole)
+                                    if (v_lo) st_global_v2(row_lo + col, r[4 * i], r[4 * i + 1]);
+                                    if (v_hi) st_global_v2(row_hi + col, r[4 * i + 2], r[4 * i + 3]);
+                                }
+                            }
+                        }
+                    }
+                    continue;
+                }
                 for (int cb = 0; cb < nt && row0 < prm.T && it * nt + cb < prm.N2; cb += 32, ++box) {
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(taddr + cb, r);
@@ -392,16 +423,32 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
             int u, it, hg, hn;
             decode(item, &u, &it, &hg, &hn);
             for (int s = 0; s < kb_count; ++s) {
-                ok = mbar_wait2<false>(bar(kWFull + ws), wph, kWFull + ws, bar(kBEmpty + bs), bph ^ 1u, kBEmpty + bs, ctl,
-                                       prm.status, kRoleSplit);
+                if (prm.direct)
+                    ok = mbar_wait<false>(bar(kBEmpty + bs), bph ^ 1u, ctl, prm.status, kRoleSplit, kBEmpty + bs);
+                else
+                    ok = mbar_wait2<false>(bar(kWFull + ws), wph, kWFull + ws, bar(kBEmpty + bs), bph ^ 1u, kBEmpty + bs, ctl,
+                                           prm.status, kRoleSplit);
                 if (!ok) break;
                 uint32_t wst = w_base + ws * kWStageBytes, bsl = b_base + bs * kBSlotBytes;
                 for (int r = 0; r < rounds; ++r, wst += kWBoxBytes, bsl += 32 * 64) {
                     float w0[2], w1[2];
+                    if (prm.direct) {
+                        // element (k, n) of the unit's [K2][N2] coefficients; rows / columns past the end are zero like the
+                        // hardware's fill.  A quarter-warp reads 8 consecutive columns of one row: one 32-byte sector.
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        w0[i] = __uint_as_float(ld_shared_u32(wst + src0[i]));
-                        w1[i] = __uint_as_float(ld_shared_u32(wst + src1[i]));
+                        for (int i = 0; i < 2; ++i) {
+                            const int j = warp + i * kSplitWarps;
+                            const int k = s * kKb + (j & 3) * 8 + 2 * kp, n = it * nt + r * 32 + (j >> 2) * 8 + nn;
+                            const float* src = prm.w + (static_cast<size_t>(u) * prm.K2 + k) * prm.N2 + n;
+                            w0[i] = (k < prm.K2 && n < prm.N2) ? __ldg(src) : 0.f;
+                            w1[i] = (k + 1 < prm.K2 && n < prm.N2) ? __ldg(src + prm.N2) : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            w0[i] = __uint_as_float(ld_shared_u32(wst + src0[i]));
+                            w1[i] = __uint_as_float(ld_shared_u32(wst + src1[i]));
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
@@ -420,7 +467,7 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(bar(kBFull + bs));
-                    mbar_arrive(bar(kWEmpty + ws));
+                    if (!prm.direct) mbar_arrive(bar(kWEmpty + ws));
                 }
                 if (++ws == kWStages) ws = 0, wph ^= 1u;
                 if (++bs == kBSlots) bs = 0, bph ^= 1u;
@@ -441,7 +488,8 @@ beamform_tc_kernel(const __grid_constant__ TcParams prm, const __grid_constant__
 
 bool beamform_tc_supported(const void* reordered, const void* coeffs, const void* beams, int A, int M) {
     (void)A;  // any antenna count: rows that TMA cannot address one by one are fetched eight at a time
-    return M % 2 == 0 && aligned16(reordered) && aligned16(coeffs) && aligned16(beams);
+    (void)M;  // any beam count: odd ones read their coefficients and write their beams without tensor maps
+    return aligned16(reordered) && aligned16(coeffs) && aligned16(beams);
 }
 
 int launch_beamform_tc(const uint8_t* reordered, const float* coeffs, float* beams, int B, int C, int T, int A, int M,
@@ -460,6 +508,9 @@ int launch_beamform_tc(const uint8_t* reordered, const float* coeffs, float* bea
     p.signed_in = (flags & DCBF_FLAG_SIGNED_INPUT) ? 1 : 0;
     p.mma_warps = p.nt <= 64 ? 2 : 1;
     p.x_split = (p.K2 % 16) != 0;
+    p.direct = (M % 2) != 0;
+    p.w = coeffs;
+    p.out = beams;
     if (int e = get_status_block(&p.status)) return e;
 
     EncodeTiledFn encode = nullptr;
@@ -487,6 +538,7 @@ int launch_beamform_tc(const uint8_t* reordered, const float* coeffs, float* bea
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return record_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(reordered)");
     }
+    if (!p.direct) {
     {
         // coefficients as float32 [units][2A][2M]; box [1][32][32], 128B swizzle
         const cuuint64_t dims[3] = {static_cast<cuuint64_t>(p.N2), static_cast<cuuint64_t>(p.K2), static_cast<cuuint64_t>(units)};
@@ -506,6 +558,11 @@ int launch_beamform_tc(const uint8_t* reordered, const float* coeffs, float* bea
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return record_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(beams)");
+    }
+
+    } else {
+        tm_w = tm_x;  // never dereferenced in direct mode (odd beam counts: rows are only 8-byte aligned)
+        tm_out = tm_x;
     }
 
     static int n_sms[64] = {};

@@ -99,11 +99,12 @@ int dcbf_coeffs_tv(const float* delay_vals, float* coeffs, int n_batches, int n_
                    const double* batch_dt_s, dcbf_stream_t stream);
 
 /* Stage 3.  out[b,p,c,t,n] = sum_j f32(reordered[b,p,c,t,j]) * coeffs[b,p,c,j,n], fp32 accumulate.
- * The coefficients are arbitrary float32 (this slot is an input of the reference operator).  Even beam counts run
- * on tcgen05: every coefficient is split into three bfloat16 terms (24 significand bits, full float32 exponent
- * range), the 8-bit voltages are exact in bfloat16, accumulation is float32 in TMEM -- the result differs from a
- * float32 evaluation by accumulation order only.  Odd beam counts (and DCBF_FLAG_DEBUG_CUDA_CORES) use a float32
- * CUDA-core kernel that accumulates in the reference's order.  flags: DCBF_FLAG_SIGNED_INPUT. */
+ * The coefficients are arbitrary float32 (this slot is an input of the reference operator).  Runs on tcgen05: every
+ * coefficient is split into three bfloat16 terms (24 significand bits, full float32 exponent range), the 8-bit
+ * voltages are exact in bfloat16, accumulation is float32 in TMEM -- the result differs from a float32 evaluation by
+ * accumulation order only.  (Odd beam counts, whose 8M-byte rows no tensor map can describe, read their coefficients
+ * and write their beams with plain accesses in the same kernel.)  DCBF_FLAG_DEBUG_CUDA_CORES selects the float32
+ * CUDA-core kernel that accumulates in the reference's order (cross-checks).  flags: DCBF_FLAG_SIGNED_INPUT. */
 int dcbf_beamform(const uint8_t* reordered, const float* coeffs, float* beams, int n_batches, int n_chans,
                   int n_samples, int n_ants, int n_beams, unsigned flags, dcbf_stream_t stream);
 

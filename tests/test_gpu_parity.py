@@ -128,13 +128,15 @@ def test_matrix_multiply(dropin, n_ants, n_beams, signed):
     assert np.all(np.abs(got - ref) <= 1e-5 * scale + 1e-6)
 
 
-TC_CASES = [  # B, C, T, A, M, signed: shapes the tcgen05 stand-alone kernel takes (even beam count)
+TC_CASES = [  # B, C, T, A, M, signed: shapes of the tcgen05 stand-alone kernel
     (1, 3, 128, 16, 16, False), (2, 3, 64, 64, 16, False), (1, 5, 256, 64, 64, False), (1, 2, 384, 80, 32, True),
     (1, 2, 256, 8, 2, False), (1, 3, 640, 72, 6, False), (1, 2, 256, 136, 130, False), (1, 2, 48, 24, 70, True),
     (1, 300, 256, 64, 64, False),  # more work items than SMs: the persistent loop wraps and the rings change phase
     # antenna counts whose sample rows are not a multiple of 16 bytes: fetched as eight boxes of an [8 samples x 2A] view
     (1, 3, 256, 197, 256, False), (2, 3, 64, 4, 2, False), (1, 5, 384, 79, 2, True), (1, 2, 48, 23, 4, False),
     (1, 300, 256, 84, 16, False),
+    # odd beam counts (8M-byte coefficient / output rows: no tensor map): coefficients by plain loads, register epilogue
+    (1, 3, 256, 64, 5, False), (2, 2, 48, 23, 3, True), (1, 2, 384, 80, 97, False), (1, 150, 128, 16, 1, False),
 ]
 
 
