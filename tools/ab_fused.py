@@ -1,6 +1,6 @@
 """Developer probe: same-box A/B of dcbf_fused (C3) across several builds of libdcbf.so.
 
-    python tools/ab_fused.py [--q8] lib1.so lib2.so ...      (interleaved rounds, CUDA events, 20 launches each)
+    python tools/ab_fused.py [--q8] [--shape A,C,T,M] lib1.so lib2.so ...      (interleaved rounds, CUDA events, 20 launches each)
 """
 import ctypes as C
 import sys
@@ -14,6 +14,10 @@ LONG = "--long" in sys.argv  # 3000 launches of run-in per measurement: the boar
 if LONG:
     sys.argv.remove("--long")
 A, Cc, T, M, B = 64, 4096, 256, 64, 1
+if "--shape" in sys.argv:
+    i = sys.argv.index("--shape")
+    A, Cc, T, M = (int(v) for v in sys.argv[i + 1].split(","))
+    del sys.argv[i:i + 2]
 dev = torch.device("cuda", 0)
 x = torch.randint(0, 256, (B, A, Cc, T, 2, 2), dtype=torch.uint8, device=dev)
 dv = torch.rand((Cc, M, A, 4), dtype=torch.float32, device=dev) * 1e-8

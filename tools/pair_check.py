@@ -13,7 +13,7 @@ from dpdk_dc_sand_b200 import _capi  # noqa: E402
 
 SHAPES = [  # B, A, C, T, M
     (1, 197, 8, 256, 256), (1, 100, 5, 384, 100), (2, 197, 3, 256, 130), (1, 520, 3, 160, 70), (1, 64, 9, 256, 200),
-    (3, 33, 4, 640, 97),
+    (3, 33, 4, 640, 97), (1, 197, 4, 256, 125), (2, 61, 3, 384, 250), (1, 36, 2, 512, 128),
 ]
 
 

@@ -1,6 +1,6 @@
 """Developer probe: a few dcbf_fused launches of one shape (target for ncu).
 
-    python tools/run_shape_once.py A C T M [B] [q8]
+    python tools/run_shape_once.py A C T M [B] [q8]     (DCBF_FLAGS=0x... adds flags to the fused call)
 """
 import os
 import sys
@@ -15,6 +15,7 @@ q8 = "q8" in sys.argv
 if q8:
     sys.argv.remove("q8")
 B = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+FLAGS = int(os.environ.get("DCBF_FLAGS", "0"), 0)
 dev = torch.device("cuda", 0)
 x = torch.randint(0, 256, (B, A, C, T, 2, 2), dtype=torch.uint8, device=dev)
 dv = torch.rand((C, M, A, 4), dtype=torch.float32, device=dev) * 1e-8
@@ -27,7 +28,7 @@ for _ in range(4):
     if q8:
         _capi.fused_q8(x, dv, gains, out8, B, A, C, C, T, M, 0, 1 / 1712e6, saturated=sat)
     else:
-        _capi.fused(x, dv, out, B, A, C, C, T, M, 0, 1 / 1712e6)
+        _capi.fused(x, dv, out, B, A, C, C, T, M, 0, 1 / 1712e6, FLAGS)
 torch.cuda.synchronize()
 _capi.fused_status()
 print("ok")
