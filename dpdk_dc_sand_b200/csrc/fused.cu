@@ -166,6 +166,12 @@ struct FusedParams {
     // channels is cut into `split` units along its list of tile_count accumulator tiles (N tile, batch, time tile), so
     // that the last round of the persistent CTAs is a fraction of a channel instead of a whole one
     int n_whole, split, tile_count;
+    // bsplit = 2: the pieces of a cut channel come in pairs that take one half of the N tile's beams each (first, because
+    // halves of the beams also halve the coefficient work of a piece; pieces along the tile list repeat it)
+    // (Tried on top: every CTA's FIRST channel as two such halves too, so that the first MMAs of a launch wait for half a
+    // tile set of coefficients -- 41.6 -> 44.0 us at the 512-channel share of C3, 261.5 -> 263.1 us at C3: the second
+    // conversion and the narrower MMAs of that channel cost more than the earlier start gains.)
+    int bsplit;
     int dbg;         // developer experiments: 1 = no delay_vals loads, 2 = no phase / sin-cos arithmetic, 4 = no output stores,
                      // 8 = no L2 prefetches of delay_vals (C3: 268 -> 290 us without them; C5 share: no difference)
     int pdl_wait;    // 1: wait for the preceding kernel of the stream (griddepcontrol.wait) after the prologue
@@ -464,7 +470,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             if (w >= static_cast<uint32_t>(prm.n_whole)) {
                 const uint32_t r_ = w - static_cast<uint32_t>(prm.n_whole), c_ = r_ / static_cast<uint32_t>(prm.split);
                 uc = static_cast<uint32_t>(prm.n_whole) + c_;
-                j0 = static_cast<int>(r_ - c_ * static_cast<uint32_t>(prm.split)) * prm.tile_count / prm.split;
+                j0 = (static_cast<int>(r_ - c_ * static_cast<uint32_t>(prm.split)) / prm.bsplit) * prm.tile_count / (prm.split / prm.bsplit);
             }
             const int bh = prm.B * prm.ht_count;
             m0 = (j0 / bh) * (prm.nt >> 1), b0 = (j0 % bh) / prm.ht_count, h0 = j0 % prm.ht_count;
@@ -519,7 +525,17 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             const uint32_t r_ = w - static_cast<uint32_t>(prm.n_whole), c_ = r_ / static_cast<uint32_t>(prm.split);
             const int s_ = static_cast<int>(r_ - c_ * static_cast<uint32_t>(prm.split));
             *uc = static_cast<uint32_t>(prm.n_whole) + c_;
-            *j0 = s_ * prm.tile_count / prm.split, *j1 = (s_ + 1) * prm.tile_count / prm.split;
+            const int jp = s_ / prm.bsplit, jsplit = prm.split / prm.bsplit;
+            *j0 = jp * prm.tile_count / jsplit, *j1 = (jp + 1) * prm.tile_count / jsplit;
+        }
+    };
+    // beams of the N tile a unit covers: all nt / 2 of them, or (piece of a cut channel, bsplit = 2) one half
+    auto unit_beams = [&](uint32_t w, int* um0, int* umt) {
+        *um0 = 0, *umt = nt >> 1;
+        if (!kStream && prm.bsplit > 1 && w >= static_cast<uint32_t>(prm.n_whole)) {
+            const uint32_t r_ = w - static_cast<uint32_t>(prm.n_whole);
+            *umt = (nt >> 1) / prm.bsplit;
+            *um0 = static_cast<int>((r_ % static_cast<uint32_t>(prm.split)) % static_cast<uint32_t>(prm.bsplit)) * *umt;
         }
     };
     const int bh_count = prm.set_tiles;  // accumulator tiles per coefficient set
@@ -711,6 +727,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             uint32_t uc;
             int j0, j1;
             unit_range(w, &uc, &j0, &j1);
+            int um0, umt;
+            unit_beams(w, &um0, &umt);
+            const uint32_t idesc_u = 2 * umt == nt ? idesc : make_idesc_f16(2 * umt);  // (half of the beams: a narrower MMA)
             for (int j = j0; j < j1 && ok; ++step) {  // one (N tile, coefficient set) and the unit's tiles that use it
                 const int jend = min(j1, (j / bh_count + 1) * bh_count);
                 const uint32_t bb = step % kBopBufs;
@@ -742,7 +761,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                         for (int k = 0; k < 2; ++k) {
                                             if (k < k_steps)
                                                 umma_f16(d_tmem, make_desc(a_lo + p * (kAopTileBytes >> 4) + 2u * k, kDescHiSw64),
-                                                         make_desc(b_lo + part * part_lo + 2u * k, kDescHiSw128), idesc,
+                                                         make_desc(b_lo + part * part_lo + 2u * k, kDescHiSw128), idesc_u,
                                                          (s | part | k) != 0);
                                         }
                                     }
@@ -792,12 +811,12 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         int clipped = 0;
         bool ok = true;
         // One accumulator tile (128 rows x nt columns at TMEM column col0) -> beams[b][p][c][t0 ..][n0 ..], float32.
-        auto store_tile_f32 = [&](uint32_t col0, int b, int p, uint32_t c, int t0, int n0) {
+        auto store_tile_f32 = [&](uint32_t col0, int b, int p, uint32_t c, int t0, int n0, int ncols) {
             if (prm.tma_store) {
                 const int row0 = t0 + 32 * q;  // this warp's 32 rows of the tile
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + col0;
                 const int plane = (b * kPols + p) * C + static_cast<int>(c);
-                for (int cb = 0; cb < nt && row0 < T && n0 + cb < N2; cb += 32, ++box) {
+                for (int cb = 0; cb < ncols && row0 < T && n0 + cb < N2; cb += 32, ++box) {
                     uint32_t r[32];
                     unsigned long long tp0 = 0, tp1 = 0, tp2 = 0;
                     if (kProf && prof_lane) tp0 = global_ns();
@@ -833,7 +852,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     float* row_hi = row_lo + 8 * static_cast<size_t>(N2);
                     const bool v_lo = t0 + r_lo < T, v_hi = t0 + r_lo + 8 < T;
                     int cb = 0;
-                    for (; cb + 64 <= nt; cb += 64) {
+                    for (; cb + 64 <= ncols; cb += 64) {
                         uint32_t r[32];
                         tmem_ld_16x256b_x8(taddr + cb, r);
                         if constexpr (merged) {
@@ -853,7 +872,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                             }
                         }
                     }
-                    for (; cb < nt; cb += 16) {
+                    for (; cb < ncols; cb += 16) {
                         uint32_t r[8];
                         tmem_ld_16x256b_x2(taddr + cb, r);
                         if constexpr (merged) {
@@ -888,7 +907,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     tc_fence_after();
                     for (int p = 0; p < kPols; ++p)
                         store_tile_f32(static_cast<uint32_t>(p) * static_cast<uint32_t>(nt), b, p, c,
-                                       (uh0 + static_cast<int>(cta_rank)) * kTileT, it * nt);
+                                       (uh0 + static_cast<int>(cta_rank)) * kTileT, it * nt, nt);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(bar(kAccEmpty), 0);
@@ -952,7 +971,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                         }
                                     }
                                 } else {
-                                    store_tile_f32(col0, b, p, c, (uh0 + h) * kTileT, it * nt);
+                                    store_tile_f32(col0, b, p, c, (uh0 + h) * kTileT, it * nt, nt);
                                 }
                             }
                         tc_fence_before();
@@ -965,6 +984,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             uint32_t c;
             int j0, j1;
             unit_range(w, &c, &j0, &j1);
+            int um0, umt;
+            unit_beams(w, &um0, &umt);
             int jit = j0 / (B * prm.ht_count), jb = (j0 - jit * B * prm.ht_count) / prm.ht_count, jh = j0 % prm.ht_count;
             {
                 {
@@ -1090,7 +1111,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                 }
                             }
                         } else {
-                            for (int p = 0; p < kPols; ++p) store_tile_f32((ab * kPols + p) * acc_cols, b, p, c, t0, n0);
+                            for (int p = 0; p < kPols; ++p) store_tile_f32((ab * kPols + p) * acc_cols, b, p, c, t0, n0 + 2 * um0, 2 * umt);
                         }
                         tc_fence_before();
                         __syncwarp();
@@ -1479,7 +1500,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         // cursor of the batch whose loads are in flight: (unit sequence index, coefficient set of the unit, entry)
         uint32_t nk = 0;
         int nw = sched_get(ctl, 0), n_ch = 0, nisb = 0, nisb_last = 0, ne0 = ctid;
-        int n_entries = 0;
+        int n_entries = 0, n_um0 = 0, n_umt = mt;
         const float4* n_src = prm.dv;
         // (static: (delay_s, phase_rad), the two rate fields are ignored like the reference does.  The compiler narrows
         // the 128-bit load to two 32-bit loads then; keeping it whole as the K-streamed step does was measured here too:
@@ -1493,11 +1514,12 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 int j0, j1;
                 unit_range(static_cast<uint32_t>(nw), &uc, &j0, &j1);
                 n_ch = static_cast<int>(uc), nisb = j0 / bh_count, nisb_last = (j1 - 1) / bh_count;
+                unit_beams(static_cast<uint32_t>(nw), &n_um0, &n_umt);
             }
         };
         auto cursor_set = [&]() {  // delay_vals of the cursor's (channel, N tile)
-            const int m0 = (nisb / sb_count) * mt;
-            n_entries = min(mt, M - m0) * A;
+            const int m0 = (nisb / sb_count) * mt + n_um0;
+            n_entries = min(n_umt, M - m0) * A;
             n_src = prm.dv + (static_cast<size_t>(n_ch) * M + m0) * A;
         };
         cursor_unit();
@@ -1555,6 +1577,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             uint32_t c;
             int j0, j1;
             unit_range(w, &c, &j0, &j1);
+            int um0, umt;
+            unit_beams(w, &um0, &umt);
             const double scale = (static_cast<double>(c) + prm.chan_centre) * prm.turns_per_delay;  // half-turns per second of delay
             const float s_hi = static_cast<float>(scale), s_lo = static_cast<float>(scale - static_cast<double>(s_hi));
             float dt_hi = 0.f, dt_lo = 0.f;
@@ -1624,8 +1648,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     set_time(prm, sb / sets_per_batch, sb % sets_per_batch, &dt_hi, &dt_lo);
                 }
                 const uint32_t bb = step % kBopBufs;
-                const int m0 = it * mt;
-                const int entries = min(mt, M - m0) * A;
+                const int m0 = it * mt + um0;
+                const int entries = min(umt, M - m0) * A;
                 w_tile = prm.weights ? prm.weights + static_cast<size_t>(m0) * A : nullptr;  // entry e <-> [m0 + e / A][e % A]
                 if (kQ8) g_tile = prm.gains + m0;
                 bool waited = false;
@@ -1972,12 +1996,21 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     p.tile_count = p.nt_count * B * p.ht_count;
     p.n_whole = C;
     p.split = 1;
+    p.bsplit = 1;
     if (!kstream && !(flags & (DCBF_FLAG_DEBUG_WHOLE_CHANNELS | DCBF_FLAG_STREAMING))) {  // (overlapped launches balance themselves)
         const int rem = C % n_sms[dev];
-        const int cut = rem ? std::min(p.tile_count, n_sms[dev] / rem) : 1;
-        if (cut > 1) {
+        // float32 output through TMA stores, one N tile of 128 or 256 columns with beams in both halves: a piece can be one
+        // half of the beams (64-column MMAs; the voltages are converted once per piece either way)
+        const bool by_beams = !q8 && p.tma_store && !p.merged && p.nt_count == 1 && p.nt % 64 == 0 && 4 * M > p.nt &&
+                              !(flags & DCBF_FLAG_DEBUG_NO_BEAM_PIECES);
+        const int room = rem ? n_sms[dev] / rem : 1;  // pieces per cut channel that still keep every CTA at one piece
+        if (by_beams && room >= 2) {
             p.n_whole = C - rem;
-            p.split = cut;
+            p.bsplit = 2;
+            p.split = 2 * std::min(p.tile_count, room / 2);
+        } else if (std::min(p.tile_count, room) > 1) {
+            p.n_whole = C - rem;
+            p.split = std::min(p.tile_count, room);
         }
     }
     const long long units = kstream ? static_cast<long long>(C) * p.nt_count * p.hg_count

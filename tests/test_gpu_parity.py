@@ -455,6 +455,36 @@ def test_cta_pair_mode(dropin, case):
     np.testing.assert_array_equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("case", [(1, 64, 10, 256, 64), (2, 64, 160, 128, 64), (1, 32, 13, 384, 128), (1, 23, 50, 256, 60),
+                                  (1, 64, 75, 256, 40)],
+                         ids=["ten_channels_all_cut", "one_round_plus_12_channels", "256_column_tile", "ragged_second_half",
+                              "ineligible_tile_list_only"])
+def test_last_round_channels_cut_into_beam_halves(dropin, case):
+    """The channels of the last scheduling round are cut into pieces so that all CTAs stay busy: halves of the N tile's
+    beams first (64- or 128-column MMAs, half the coefficient work per piece), then along the tile list.  Inside the budget
+    against the float64 oracle and bit-identical to the uncut schedule and to the tile-list-only cut."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m = case
+    n, xid = 1024, 1
+    x = orc.make_samples(b, a, c, t, seed=81)
+    dv = orc.make_delay_vals_random(c, m, a, seed=82)
+    ref = orc.beamform_pipeline(x, dv, n, xid, TS)
+    dx, ddv = torch.from_numpy(x).cuda(), torch.from_numpy(dv).cuda()
+    outs = []
+    for flags in (0, _capi.FLAG_DEBUG_NO_BEAM_PIECES, _capi.FLAG_DEBUG_WHOLE_CHANNELS):
+        out = torch.full(ref.shape, float("nan"), dtype=torch.float32, device="cuda")
+        _capi.fused(dx, ddv, out, b, a, c, n, t, m, xid, TS, flags)
+        torch.cuda.synchronize()
+        _capi.fused_status()
+        outs.append(out.cpu().numpy())
+    assert np.all(np.abs(outs[0].astype(np.float64) - ref) <= _budget(x))
+    for other in outs[1:]:
+        np.testing.assert_array_equal(outs[0], other)
+
+
 @pytest.mark.parametrize("case", [(2, 64, 3, 512, 6, 4096, 6), (1, 100, 2, 384, 100, 512, 1), (2, 16, 5, 208, 4, 256, 0)],
                          ids=["whole_tile_sets", "k_streamed", "ragged_last_tile"])
 def test_sub_heap_time_varying_steering(dropin, case):
