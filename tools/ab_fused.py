@@ -10,6 +10,9 @@ import torch
 Q8 = "--q8" in sys.argv
 if Q8:
     sys.argv.remove("--q8")
+SAT = "--sat" in sys.argv  # --q8 with the saturation counter (the slower clamp)
+if SAT:
+    sys.argv.remove("--sat")
 LONG = "--long" in sys.argv  # 3000 launches of run-in per measurement: the board is then at its power cap
 if LONG:
     sys.argv.remove("--long")
@@ -38,7 +41,7 @@ for path in sys.argv[1:]:
 def run(lib, n):
     for _ in range(n):
         if Q8:
-            st = lib.dcbf_fused_q8(x.data_ptr(), dv.data_ptr(), gains.data_ptr(), out8.data_ptr(), sat.data_ptr(), B, A, Cc, Cc,
+            st = lib.dcbf_fused_q8(x.data_ptr(), dv.data_ptr(), gains.data_ptr(), out8.data_ptr(), sat.data_ptr() if SAT else None, B, A, Cc, Cc,
                                    T, M, 0, 1 / 1712e6, None, 0, None)
         else:
             st = lib.dcbf_fused(x.data_ptr(), dv.data_ptr(), out.data_ptr(), B, A, Cc, Cc, T, M, 0, 1 / 1712e6, 0, None)

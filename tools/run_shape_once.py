@@ -1,6 +1,6 @@
 """Developer probe: a few dcbf_fused launches of one shape (target for ncu).
 
-    python tools/run_shape_once.py A C T M [B] [q8]     (DCBF_FLAGS=0x... adds flags to the fused call)
+    python tools/run_shape_once.py A C T M [B] [q8 [sat]]     (DCBF_FLAGS=0x... adds flags to the fused call)
 """
 import os
 import sys
@@ -14,6 +14,9 @@ A, C, T, M = (int(v) for v in sys.argv[1:5])
 q8 = "q8" in sys.argv
 if q8:
     sys.argv.remove("q8")
+count = "sat" in sys.argv  # q8 with the saturation counter (the slower clamp)
+if count:
+    sys.argv.remove("sat")
 B = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 FLAGS = int(os.environ.get("DCBF_FLAGS", "0"), 0)
 dev = torch.device("cuda", 0)
@@ -26,7 +29,7 @@ if q8:
     sat = torch.zeros(1, dtype=torch.int64, device=dev)
 for _ in range(4):
     if q8:
-        _capi.fused_q8(x, dv, gains, out8, B, A, C, C, T, M, 0, 1 / 1712e6, saturated=sat)
+        _capi.fused_q8(x, dv, gains, out8, B, A, C, C, T, M, 0, 1 / 1712e6, saturated=sat if count else None)
     else:
         _capi.fused(x, dv, out, B, A, C, C, T, M, 0, 1 / 1712e6, FLAGS)
 torch.cuda.synchronize()
