@@ -518,6 +518,62 @@ def test_sub_heap_time_varying_steering(dropin, case):
         assert np.any(np.abs(got[0.0] - exact) > budget)
 
 
+GUARD_CASES = [(1, 64, 5, 256, 64), (2, 23, 3, 48, 3), (1, 197, 3, 256, 256), (1, 100, 2, 384, 100), (1, 520, 2, 160, 70),
+               (1, 64, 150, 128, 64), (3, 33, 4, 640, 97), (1, 1, 7, 16, 1), (1, 80, 9, 272, 32)]
+
+
+@pytest.mark.parametrize("case", GUARD_CASES, ids=lambda c: "B{}A{}C{}T{}M{}".format(*c))
+def test_outputs_stay_inside_their_buffers(dropin, case):
+    """Bounds check of our own (no memory checker on the GPU boxes): every output of the C-ABI lives in the middle of a
+    larger allocation whose 64 KiB on either side hold a canary pattern; after the fused kernel (float32 and int8, every
+    tiling mode the shapes select: whole tile sets, pieces, K-streamed, CTA pairs), the stand-alone reorder / coefficients /
+    contraction (tcgen05 and CUDA cores) the canaries are intact and the inputs are unchanged."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m = case
+    n, xid, guard = 4 * c, 1, 1 << 16
+    g = torch.Generator(device="cuda").manual_seed(5)
+
+    def guarded(shape, dtype):
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        raw = torch.full((guard + nbytes + guard,), 0xA5, dtype=torch.uint8, device="cuda")
+        return raw, raw[guard:guard + nbytes].view(dtype).view(shape)
+
+    def intact(raw):
+        return bool((raw[:guard] == 0xA5).all()) and bool((raw[-guard:] == 0xA5).all())
+
+    x = torch.randint(0, 256, (b, a, c, t, 2, 2), dtype=torch.uint8, device="cuda", generator=g)
+    dv = torch.rand((c, m, a, 4), dtype=torch.float32, device="cuda", generator=g) * 2e-7
+    gains = torch.full((m,), 0.01, dtype=torch.float32, device="cuda")
+    x0, dv0 = x.clone(), dv.clone()
+    k = t // 16
+    raws = {}
+    raws["fused"], out = guarded((b, 2, c, k, 16, 2 * m), torch.float32)
+    _capi.fused(x, dv, out, b, a, c, n, t, m, xid, TS)
+    raws["fused_q8"], out8 = guarded((b, 2, c, k, 16, 2 * m), torch.int8)
+    _capi.fused_q8(x, dv, gains, out8, b, a, c, n, t, m, xid, TS)
+    raws["reorder"], re = guarded((b, 2, c, k, 16, a, 2), torch.uint8)
+    _capi.reorder(x, re, b, a, c, t)
+    raws["coeffs"], co = guarded((b, 2, c, 2 * a, 2 * m), torch.float32)
+    _capi.coeffs(dv, co, b, 2, c, n, a, m, xid, TS)
+    raws["coeffs_f16"], co16 = guarded((b, 2, c, 2 * a, 2 * m), torch.float16)
+    _capi.coeffs(dv, co16, b, 2, c, n, a, m, xid, TS)
+    raws["beamform"], bf = guarded((b, 2, c, k, 16, 2 * m), torch.float32)
+    _capi.beamform(re, co, bf, b, c, t, a, m)
+    raws["beamform_cuda_cores"], bf2 = guarded((b, 2, c, k, 16, 2 * m), torch.float32)
+    _capi.beamform(re, co, bf2, b, c, t, a, m, _capi.FLAG_DEBUG_CUDA_CORES)
+    torch.cuda.synchronize()
+    _capi.fused_status()
+    for name, raw in raws.items():
+        assert intact(raw), name
+    assert torch.equal(x, x0) and torch.equal(dv, dv0)
+    assert not bool(torch.isnan(out).any()) and not bool(torch.isnan(bf).any())
+    budget = x.to(torch.float32).abs().sum(dim=(1, 5)).amax() * 2.0 ** -10
+    assert float((out - bf).abs().max()) <= 2 * float(budget)  # the two paths agree as well
+
+
 @pytest.mark.parametrize("case", [(1, 64, 7, 256, 16, 1024, 0, False), (2, 23, 3, 48, 3, 256, 1, True),
                                   (1, 80, 4, 256, 32, 32768, 3, False), (1, 4, 9, 128, 8, 64, 0, False),
                                   (1, 1, 21, 128, 15, 21, 0, False), (2, 100, 3, 384, 100, 512, 1, False),
