@@ -30,6 +30,7 @@ FLAG_DEBUG_WHOLE_CHANNELS = 0x800
 FLAG_DEBUG_NO_PDL = 0x1000
 FLAG_DEBUG_NO_PAIR = 0x2000
 FLAG_DEBUG_NO_BEAM_PIECES = 0x4000
+FLAG_DEBUG_TWO_A_STAGES = 0x8000
 
 _ROLE_NAMES = {1: "producer", 2: "mma", 3: "epilogue", 4: "convert", 5: "coeff"}
 

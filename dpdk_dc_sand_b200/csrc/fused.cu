@@ -176,6 +176,7 @@ struct FusedParams {
                      // 8 = no L2 prefetches of delay_vals (C3: 268 -> 290 us without them; C5 share: no difference)
     int pdl_wait;    // 1: wait for the preceding kernel of the stream (griddepcontrol.wait) after the prologue
     int raw_extra_off;  // byte offset of the first extra stage inside each 64 KiB B buffer
+    int aop_extra;      // whole tile sets: 1 = A stages 2 and 3 in the last 16 KiB of the two B buffers
     uint32_t inv_a;     // floor(2^32 / A) + 1: e / A == umulhi(e, inv_a) for every entry index of an N tile (A >= 2)
     double dt_s[DCBF_MAX_TV_BATCHES];  // time-varying steering: time offset (s) of every batch (heap)
     double sample_dt;                  // ... and seconds per sample inside a heap: != 0 gives every 128-sample time tile its
@@ -395,10 +396,15 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     // K-streamed B: every slab is a convert -> MMA -> convert round trip (fence, arrive, wake-up, commit), so the depth of
     // the A ring bounds the slab rate more than the look-ahead of the B ring does (ncu: every role of a two-stage
     // pipeline sat in its barrier waits).  Four A stages, the two extra ones in the fourth slot of the B ring.
-    constexpr uint32_t kAStages = kStream ? kMaxAopStages : kAopStages;
+    // Whole tile sets narrower than their 64 KiB buffers (C2, C4: 16-48 KiB) leave room for the same two extra stages, one
+    // in the last 16 KiB of each buffer (prm.aop_extra): the A ring, not the work, set the slab rate there as well.
+    constexpr uint32_t kAStages = kStream ? kMaxAopStages : kAopStages;  // (K-streamed builds: a compile-time constant)
+    const uint32_t a_shift = kStream ? 2u : (prm.aop_extra ? 2u : 1u), a_mask = (1u << a_shift) - 1u;
     constexpr uint32_t kBSlots = kStream ? 3 : kBopSlots;
     auto aop_addr = [&](uint32_t as) {
-        return as < kAopStages ? aop_base + as * kAopStageBytes : bop_base + 3u * kBopSlotBytes + (as - kAopStages) * kAopStageBytes;
+        if (as < kAopStages) return aop_base + as * kAopStageBytes;
+        return kStream ? bop_base + 3u * kBopSlotBytes + (as - kAopStages) * kAopStageBytes
+                       : bop_base + (as - kAopStages) * kBopBufBytes + (kBopBufBytes - kAopStageBytes);
     };
     static_assert(320 + sizeof(Control) <= kCtlBytes, "control area");
     // raw stage s: its own 8 KiB for s < kRawStages, else alternately behind the tiles of B buffer 0 / 1
@@ -741,8 +747,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     tc_fence_after();
                     const uint32_t d_tmem0 = tmem_base + ab * kPols * acc_cols;
                     for (int s = 0; s < prm.slab_count; ++s, ++slab) {
-                        const uint32_t as = slab % kAStages;
-                        ok = mbar_wait<kProf>(bar(kAopFull + as), (slab / kAStages) & 1u, ctl, prm.status, kRoleMma, kAopFull + as, ps + 2);
+                        const uint32_t as = slab & a_mask;
+                        ok = mbar_wait<kProf>(bar(kAopFull + as), (slab >> a_shift) & 1u, ctl, prm.status, kRoleMma, kAopFull + as, ps + 2);
                         if (!ok) break;
                         tc_fence_after();
                         const int n_ants = min(kSlabAnts, A - s * kSlabAnts);
@@ -1153,9 +1159,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             {
                 for (int bh = 0; bh < tiles && ok; ++bh)
                     for (int s = 0; s < prm.slab_count; ++s, ++slab) {
-                        const uint32_t as = slab % kAStages;
+                        const uint32_t as = slab & a_mask;
                         ok = mbar_wait2<kProf>(bar(kRawFull + rs), rph, kRawFull + rs, bar(kAopEmpty + as),
-                                               ((slab / kAStages) & 1u) ^ 1u, kAopEmpty + as, ctl, prm.status, kRoleConvert, ps + 0);
+                                               ((slab >> a_shift) & 1u) ^ 1u, kAopEmpty + as, ctl, prm.status, kRoleConvert, ps + 0);
                         if (!ok) break;
                         // antennas beyond A were zero-filled by the TMA box: byte 0 -> value 0 (u8), and
                         // 0 ^ 0x80 - 128 -> 0 (i8), so the K padding of the operand needs no special case
@@ -1913,7 +1919,11 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
     p.raw_stages = kRawStages;
     if (!kstream) {
         const int used = p.kb_count * p.parts * p.nt * 128;
-        const int spare = (kBopBufBytes - used) / kRawStageBytes;
+        // (the raw ring comes first: at C4, where 16 KiB per buffer are spare, two more A stages instead of four more raw
+        // stages cost 3 %; with both -- C2, 32 beams -- the extra A stages are worth 3-4 %)
+        p.aop_extra = kBopBufBytes - used >= kAopStageBytes + ((kMaxRawStages - kRawStages) / 2) * kRawStageBytes &&
+                      !(flags & DCBF_FLAG_DEBUG_TWO_A_STAGES);
+        const int spare = (kBopBufBytes - used - (p.aop_extra ? kAopStageBytes : 0)) / kRawStageBytes;
         p.raw_extra_off = used;
         p.raw_stages = kRawStages + 2 * std::min(spare, (kMaxRawStages - kRawStages) / 2);
     }

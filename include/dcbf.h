@@ -73,6 +73,7 @@ typedef enum dcbf_status {
 #define DCBF_FLAG_DEBUG_NO_PDL 0x1000u /* dcbf_fused: plain stream-ordered launch (no programmatic dependent launch attribute) */
 #define DCBF_FLAG_DEBUG_NO_PAIR 0x2000u /* dcbf_fused: many antennas x beams on single CTAs instead of cta_group::2 CTA pairs (cross-check) */
 #define DCBF_FLAG_DEBUG_NO_BEAM_PIECES 0x4000u /* dcbf_fused: the channels of the last scheduling round are only cut along their tile list, not into halves of the beams (cross-check) */
+#define DCBF_FLAG_DEBUG_TWO_A_STAGES 0x8000u /* dcbf_fused: narrow whole tile sets keep the two-stage converted-voltage ring (cross-check / A-B) */
 
 int dcbf_version(void);
 const char* dcbf_strerror(int status);
