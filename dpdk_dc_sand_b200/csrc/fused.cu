@@ -76,10 +76,15 @@ constexpr int kThreads = (kCoeffWarps + 12) * 32;  // the last warp only keeps t
 // int8 output: a second epilogue warpgroup, warps 28..31, one group per pol.  Quantising costs ~3 ALU instructions per
 // value on top of the float32 epilogue, and the four epilogue warps share their schedulers with the coefficient role:
 // they were busy 275 of 290 us at C3 while every other role waited for them.  The kernel then starts from 64 registers
-// per thread (32 warps) and splits 72 (coefficients) / 72 (epilogue) / 40 / 40.
+// per thread (32 warps) and splits 72 (coefficients) / 72 (epilogue) / 40 / 40 -- or, in the build for whole tile sets of
+// more than 64 columns (kQ8Wide: C3), 80 / 56 / 40 / 40: the coefficient role bounds that kernel, and its spills go
+// to L2 (all of L1 is carved out for shared memory): an `ncu` capture had 20 % of its stall samples on local-memory
+// reloads.  C3: 242.6 -> 220.4 us on the same box.  The merged-tile (<= 64 columns) and K-streamed builds keep 72 / 72:
+// their epilogues need the registers (+9 ... +12 % with 56).
 constexpr int kEpilogue2Warp0 = kCoeffWarps + 12;
 constexpr int kThreadsQ8 = kThreads + 128;
-static_assert(kThreadsQ8 * 64 <= 65536 && kCoeffWarps * 72 + 8 * 72 + 4 * 40 + 4 * 40 <= (kCoeffWarps + 16) * 64, "register pool, int8 output");
+static_assert(kThreadsQ8 * 64 <= 65536 && kCoeffWarps * 72 + 8 * 72 + 4 * 40 + 4 * 40 <= (kCoeffWarps + 16) * 64 &&
+              kCoeffWarps * 80 + 8 * 56 + 4 * 40 + 4 * 40 <= (kCoeffWarps + 16) * 64, "register pool, int8 output");
 // registers per thread at launch (the __launch_bounds__ cap) and per role after setmaxnreg; the roles' sum must fit the
 // CTA's pool of kThreads * kRegsLaunch
 #if DCBF_COEFF_WARPS == 16
@@ -416,6 +421,11 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     auto bar = [&](int id) { return bar_base + 8u * static_cast<uint32_t>(id); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr bool kQ8Wide = kQ8 && !kMerged && !kStream;  // register split 80 / 56 instead of 72 / 72 (see kThreadsQ8)
+    // Time-varying steering, float32 output: the coefficient role carries the four fields of every entry and the time
+    // pair and spills at 72 registers (to L2, see kThreadsQ8) -- it gets 80; convert 48, epilogue 96, issue warps 40.
+    constexpr bool kTvSplit = kTv && !kQ8 && DCBF_COEFF_WARPS == 16;
+    static_assert(kCoeffWarps * 80 + 4 * (48 + 96 + 40) <= (kCoeffWarps + 12) * DCBF_REGS_LAUNCH || DCBF_COEFF_WARPS != 16, "register pool, time-varying steering");
 
     // ---- one-time setup ----
     if (threadIdx.x == 0) {
@@ -564,7 +574,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     const unsigned long long role_t0_cta = (kProf && threadIdx.x < 24) ? global_ns() : 0ull;
 
     if (warp >= kProducerWarp && warp < kProducerWarp + 4) {
-        if constexpr (kQ8) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if constexpr (kQ8 || kTvSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 " DCBF_STR(DCBF_REGS_ISSUE) ";");
     }
     if (warp == kProducerWarp) {
@@ -786,7 +796,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         }
     } else if ((warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + 4) || (kQ8 && warp >= kEpilogue2Warp0)) {
         // =================================== epilogue ===================================
-        if constexpr (kQ8) asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
+        if constexpr (kQ8Wide) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        else if constexpr (kQ8) asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
+        else if constexpr (kTvSplit) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 " DCBF_STR(DCBF_REGS_EPILOGUE) ";");
         const int q = warp & 3;  // TMEM lane quarter this warp may read
         // int8 output: two warpgroups, group g quantises pol g; every warp then has 4 KiB of staging (one wide box or
@@ -1134,6 +1146,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     } else if (warp >= kConvertWarp0 && warp < kConvertWarp0 + 4) {
         // =================================== convert ===================================
         if constexpr (kQ8) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        else if constexpr (kTvSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 " DCBF_STR(DCBF_REGS_CONVERT) ";");
         // thread = one sample row t; per 4-antenna chunk: 4 conflict-free LDS.32, 8 PRMT + 8 HSUB2, 2 STS.128
         // (quarter-warps write 8 distinct 16-byte chunks of the 64B-swizzled rows: conflict-free)
@@ -1201,7 +1214,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         }
     } else if (warp < kCoeffWarp0 + kCoeffWarps) {
         // =================================== steering coefficients ===================================
-        if constexpr (kQ8) asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");  // (from 64 at launch)
+        if constexpr (kQ8Wide) asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");  // (from 64 at launch)
+        else if constexpr (kQ8) asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
+        else if constexpr (kTvSplit) asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 " DCBF_STR(DCBF_REGS_COEFF) ";");
         // delay_vals[c][m0 .. m0+mt) is one contiguous run of (beam, antenna) entries: the 256 threads walk it
         // with lane <-> consecutive entry, so every warp load is 512 contiguous bytes.  Each entry becomes four
@@ -1624,6 +1639,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     nsn *= w;
                 }
                 if constexpr (kQ8) {  // requantisation gain of this entry's beam, relative to the largest one
+                    // (loading the batch's gains ahead of the wait and the phase arithmetic was measured: four more live
+                    // registers, more spills, 220 -> 238 us)
                     if (valid) {
                         const float g = __ldg(g_tile + (A == 1 ? static_cast<uint32_t>(e) : __umulhi(static_cast<uint32_t>(e), prm.inv_a))) * q8_inv_gmax;
                         cs *= g;
