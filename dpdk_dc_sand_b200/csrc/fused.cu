@@ -424,7 +424,8 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     constexpr bool kQ8Wide = kQ8 && !kMerged && !kStream;  // register split 80 / 56 instead of 72 / 72 (see kThreadsQ8)
     // Time-varying steering, float32 output: the coefficient role carries the four fields of every entry and the time
     // pair and spills at 72 registers (to L2, see kThreadsQ8) -- it gets 80; convert 48, epilogue 96, issue warps 40.
-    constexpr bool kTvSplit = kTv && !kQ8 && DCBF_COEFF_WARPS == 16;
+    // The CTA-pair build as well (its per-unit counters came back from local memory: C5 on one GPU 2463 -> 2370 us).
+    constexpr bool kTvSplit = (kTv || kPair) && !kQ8 && DCBF_COEFF_WARPS == 16;
     static_assert(kCoeffWarps * 80 + 4 * (48 + 96 + 40) <= (kCoeffWarps + 12) * DCBF_REGS_LAUNCH || DCBF_COEFF_WARPS != 16, "register pool, time-varying steering");
 
     // ---- one-time setup ----
