@@ -422,10 +422,13 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr bool kQ8Wide = kQ8 && !kMerged && !kStream;  // register split 80 / 56 instead of 72 / 72 (see kThreadsQ8)
-    // Time-varying steering, float32 output: the coefficient role carries the four fields of every entry and the time
-    // pair and spills at 72 registers (to L2, see kThreadsQ8) -- it gets 80; convert 48, epilogue 96, issue warps 40.
-    // The CTA-pair build as well (its per-unit counters came back from local memory: C5 on one GPU 2463 -> 2370 us).
-    constexpr bool kTvSplit = (kTv || kPair) && !kQ8 && DCBF_COEFF_WARPS == 16;
+    // Float32 output: the coefficient role gets 80 registers, convert 48, the epilogue 96, the issue warps 40 (the launch
+    // bound of 72 per thread is what the 28 warps share).  At 72 the time-varying builds -- four fields per entry and the
+    // time pair -- spilled in this role, to L2 (see kThreadsQ8): C3 with per-heap times 313 -> 287 us; the CTA-pair build
+    // reloaded its per-unit counters from local memory (C5 on one GPU 2463 -> 2370 us); and the static builds can then
+    // afford whole 128-bit delay_vals loads (kWhole128 below): C3 at the power cap 304 -> 290 us, C4-shaped 4096 channels
+    // 198 -> 194 us, the 512-channel share of C3 40.8 -> 39.6 us (same box, interleaved).
+    constexpr bool kTvSplit = !kQ8 && DCBF_COEFF_WARPS == 16;
     static_assert(kCoeffWarps * 80 + 4 * (48 + 96 + 40) <= (kCoeffWarps + 12) * DCBF_REGS_LAUNCH || DCBF_COEFF_WARPS != 16, "register pool, time-varying steering");
 
     // ---- one-time setup ----
@@ -1524,10 +1527,11 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         int nw = sched_get(ctl, 0), n_ch = 0, nisb = 0, nisb_last = 0, ne0 = ctid;
         int n_entries = 0, n_um0 = 0, n_umt = mt;
         const float4* n_src = prm.dv;
-        // (static: (delay_s, phase_rad), the two rate fields are ignored like the reference does.  The compiler narrows
-        // the 128-bit load to two 32-bit loads then; keeping it whole as the K-streamed step does was measured here too:
-        // C3 262 -> 264.5 us, C4 share 191 -> 194 us -- eight more registers in flight cost more than the LSU passes)
-        constexpr bool kWhole128 = kQ8 && !kTv;  // (int8 output: this role bounds the kernel there, see the epilogue)
+        // (static: (delay_s, phase_rad), the two rate fields are ignored like the reference does.  The compiler would narrow
+        // the 128-bit load to two 32-bit loads then, each walking the warp's 512-byte span again; it is kept whole as in
+        // the K-streamed step (delay_and_phase).  With 72 registers for this role the eight more registers in flight cost
+        // more than the LSU passes saved -- C3 262 -> 264.5 us; with 80 it is a gain everywhere, see kTvSplit)
+        constexpr bool kWhole128 = !kTv;
         using Nx = typename std::conditional<kTv || kWhole128, float4, float2>::type;
         Nx nxt[kBatch];
         auto cursor_unit = [&]() {  // the cursor's unit -> channel and its range of (N tile, coefficient set) steps
