@@ -178,7 +178,9 @@ struct FusedParams {
     // conversion and the narrower MMAs of that channel cost more than the earlier start gains.)
     int bsplit;
     int dbg;         // developer experiments: 1 = no delay_vals loads, 2 = no phase / sin-cos arithmetic, 4 = no output stores,
-                     // 8 = no L2 prefetches of delay_vals (C3: 268 -> 290 us without them; C5 share: no difference)
+                     // 8 = no L2 prefetches of delay_vals (C3: 268 -> 290 us without them; C5 share: no difference),
+                     // 16 = half of the u8 -> fp16 conversion work, 32 = no epilogue staging stores / proxy fence,
+                     // 64 = one MMA per tile (the last three on top of 4: which role carries the SM-side time)
     int pdl_wait;    // 1: wait for the preceding kernel of the stream (griddepcontrol.wait) after the prologue
     int raw_extra_off;  // byte offset of the first extra stage inside each 64 KiB B buffer
     int aop_extra;      // whole tile sets: 1 = A stages 2 and 3 in the last 16 KiB of the two B buffers
@@ -779,7 +781,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                                     if (part < mma_parts) {
 #pragma unroll
                                         for (int k = 0; k < 2; ++k) {
-                                            if (k < k_steps)
+                                            if (k < k_steps && !((prm.dbg & 64) && (s | part | k) != 0))  // (ablation: one MMA per tile)
                                                 umma_f16(d_tmem, make_desc(a_lo + p * (kAopTileBytes >> 4) + 2u * k, kDescHiSw64),
                                                          make_desc(b_lo + part * part_lo + 2u * k, kDescHiSw128), idesc_u,
                                                          (s | part | k) != 0);
@@ -850,10 +852,12 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                     tmem_wait_ld();
                     if (kProf && prof_lane) tp2 = global_ns();
                     const uint32_t dst = sb + lane * 128;
+                    if (!(prm.dbg & 32)) {  // (ablation: no staging stores, no proxy fence)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        st_shared_v4(dst + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-                    fence_proxy_async_smem();
+                        for (int j = 0; j < 8; ++j)
+                            st_shared_v4(dst + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                        fence_proxy_async_smem();
+                    }
                     __syncwarp();
                     if (kProf && prof_lane) {  // slot 1: bulk-store read wait, slot 2: TMEM read + fence + stores
                         ctl->wait_ns[kRoleEpilogue][1] += tp1 - tp0;
@@ -1190,9 +1194,10 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         // interleaving them with the stores would expose the load latency once per chunk)
                         uint32_t w[kSlabAnts];
 #pragma unroll
-                        for (int i = 0; i < kSlabAnts; ++i) w[i] = ld_shared_u32(src + i * (kTileT * 4));
+                        for (int i = 0; i < kSlabAnts; ++i) w[i] = ((prm.dbg & 16) && i >= 8) ? 0u : ld_shared_u32(src + i * (kTileT * 4));
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
+                            if ((prm.dbg & 16) && j >= 2) continue;  // (ablation: half of the conversion work)
 #pragma unroll
                             for (int i = 0; i < 4; ++i) w[4 * j + i] ^= flip;
                             const uint32_t off = (static_cast<uint32_t>(j) ^ sw) << 4;
@@ -2088,7 +2093,7 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
         ++cfg.numAttrs;
     }
     p.pdl_wait = (flags & DCBF_FLAG_STREAMING) ? 0 : 1;
-    p.dbg = (flags >> 16) & 15;  // developer experiments
+    p.dbg = (flags >> 16) & 127;  // developer experiments
     // (int8 output, variant, merged) specialisation; variant: 0 plain, 1 profiling, 2 time-varying steering (the
     // profiler has no time-varying build)
     const int variant = batch_dt_s ? 2 : p.prof ? 1 : 0;
