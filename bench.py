@@ -364,6 +364,10 @@ def measure_share(A, C, T, M, B, n_total, xeng_id, steps, dev, peak, desc=None):
     sec_graph = run_graph(steps, 0)
     time.sleep(0.25)
     sec_graph_stream = run_graph(steps, _capi.FLAG_STREAMING)
+    time.sleep(0.25)
+    # the optional single fp16 rounding of the coefficients (one MMA pass, inside the 2^-10 sum|x| budget) with streaming
+    run(sets, _capi.FLAG_STREAMING | _capi.FLAG_FP16_COEFF)
+    sec_h_stream, _ = run(steps, _capi.FLAG_STREAMING | _capi.FLAG_FP16_COEFF)
     _capi.fused_status()
     out = {"ms_per_step": sec * 1e3, "input_GBps": xs[0].numel() / sec / 1e9,
            "beam_gsamples_per_s": B * 2 * C * T * M / sec / 1e9, "algorithmic_bytes_per_launch": alg,
@@ -373,6 +377,8 @@ def measure_share(A, C, T, M, B, n_total, xeng_id, steps, dev, peak, desc=None):
            "graph_ms_per_step": sec_graph * 1e3, "graph_roofline_frac": alg / sec_graph / 1e9 / peak,
            "graph_streaming_ms_per_step": sec_graph_stream * 1e3,
            "graph_streaming_roofline_frac": alg / sec_graph_stream / 1e9 / peak,
+           "fp16_coeff_streaming_ms_per_step": sec_h_stream * 1e3,
+           "fp16_coeff_streaming_roofline_frac": alg / sec_h_stream / 1e9 / peak,
            "l2": f"{sets} rotating input/output sets",
            "geometry": {"n_ants": A, "n_chans_per_gpu": C, "n_chans_total": n_total, "n_samples": T, "n_beams": M,
                         "n_batches": B, "xeng_id": xeng_id}}
@@ -389,13 +395,15 @@ BANDS = {
     "c4": ("MeerKAT+ 32k mode: 80 antennas x 32768 channels x 256 samples, 32 beams", 80, 32768, 256, 32, (8,)),
     "c5": ("SKA-Mid scale: 197 antennas x 4096 channels x 256 samples, 256 beams", 197, 4096, 256, 256, (8,)),
 }
-_MODES = ("ms_per_step", "streaming_ms_per_step", "graph_ms_per_step", "graph_streaming_ms_per_step")
+_MODES = ("ms_per_step", "streaming_ms_per_step", "graph_ms_per_step", "graph_streaming_ms_per_step",
+          "fp16_coeff_streaming_ms_per_step")
 
 
 def strong_scaling(world, rank, dev, peak, steps, dist=None, emulate=(2, 4, 8)):
     """STRONG scaling: a fixed band cut over `world` GPUs (n_chans_per_gpu = n_chans / world, xeng_id = rank), the
     partitioning BASELINE.json configs[2..4] name.  Every rank times its own share (one heap and 8 heaps per launch;
-    default launches, DCBF_FLAG_STREAMING, and both replayed from a CUDA graph); the slowest rank's time is reported.
+    default launches, DCBF_FLAG_STREAMING, both replayed from a CUDA graph, and streaming with the optional single fp16
+    rounding of the coefficients, DCBF_FLAG_FP16_COEFF); the slowest rank's time is reported.
     `efficiency_vs_n1` = t(whole band on one GPU) / (world * t(share)), the whole band being timed in the same run.
     With one GPU the per-GPU shares of 2, 4 and 8 GPUs are timed on it instead (`emulated_shares`: the shards exchange
     nothing, so a share's kernel time does not depend on the other GPUs)."""

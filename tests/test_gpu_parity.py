@@ -1098,6 +1098,33 @@ def test_full_size_configs_against_the_oracle(dropin, name):
     assert worst < 2.0 ** -10
 
 
+@pytest.mark.parametrize("name", ["c3", "c3_share_of_8", "c5_share_of_8"])
+def test_full_size_single_rounding_option_stays_inside_the_budget(dropin, name):
+    """DCBF_FLAG_FP16_COEFF (one fp16 rounding per coefficient, one MMA pass: the option that holds 0.9 of the roofline
+    at the board's power cap) with DCBF_FLAG_STREAMING at full size: sampled channels against the float64 oracle.
+    The north_star budget is 2^-10 * sum|x|; a rounding of 2^-12 per coefficient must stay well inside it."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    a, c, t, m, n_total, xid = FULL_SIZE[name]
+    x, dv = _full_size_inputs(a, c, t, m, seed=51)
+    outs = [torch.empty((1, 2, c, t // 16, 16, 2 * m), dtype=torch.float32, device=x.device) for _ in range(2)]
+    for i in range(2):  # two overlapping launches into distinct buffers, as the streaming flag requires
+        _capi.fused(x, dv, outs[i], 1, a, c, n_total, t, m, xid, TS, _capi.FLAG_FP16_COEFF | _capi.FLAG_STREAMING)
+    torch.cuda.synchronize()
+    _capi.fused_status()
+    assert torch.equal(outs[0], outs[1])
+    worst = 0.0
+    for ch in _sampled_channels(c, seed=52):
+        xs = x[:, :, ch:ch + 1].cpu().numpy()
+        dvs = np.ascontiguousarray(dv[ch:ch + 1].cpu().numpy())
+        ref = orc.beamform_pipeline(xs, dvs, n_total, c * xid + ch, TS)
+        err = np.abs(outs[1][:, :, ch:ch + 1].cpu().numpy().astype(np.float64) - ref)
+        worst = max(worst, float(np.max(err / _budget(xs))))
+    assert worst < 0.25, worst  # (measured: under a tenth of the budget)
+
+
 def test_full_size_q8_against_the_oracle(dropin):
     """int8 requantised output at the size the metric is quoted on (C3): sampled channels against the oracle's
     requantisation of its float64 beams (at most one quantisation step away, practically always equal)."""

@@ -51,7 +51,8 @@ def main():
             print(f"{name:6s} B={B}: {r['ms_per_step'] * 1e3:8.1f} us {r['roofline_frac']:.3f} | streaming "
                   f"{r['streaming_ms_per_step'] * 1e3:8.1f} us {r['streaming_roofline_frac']:.3f} | graph "
                   f"{r['graph_ms_per_step'] * 1e3:8.1f} us {r['graph_roofline_frac']:.3f} | graph+streaming "
-                  f"{r['graph_streaming_ms_per_step'] * 1e3:8.1f} us {r['graph_streaming_roofline_frac']:.3f} | host "
+                  f"{r['graph_streaming_ms_per_step'] * 1e3:8.1f} us {r['graph_streaming_roofline_frac']:.3f} | fp16 coeff + streaming "
+                  f"{r['fp16_coeff_streaming_ms_per_step'] * 1e3:8.1f} us {r['fp16_coeff_streaming_roofline_frac']:.3f} | host "
                   f"{r['host_us_per_launch']:6.1f} us/launch | ideal {r['algorithmic_bytes_per_launch'] / peak / 1e3:8.1f} us",
                   flush=True)
     print(json.dumps(rows))
