@@ -177,7 +177,7 @@ struct FusedParams {
     // tile set of coefficients -- 41.6 -> 44.0 us at the 512-channel share of C3, 261.5 -> 263.1 us at C3: the second
     // conversion and the narrower MMAs of that channel cost more than the earlier start gains.)
     int bsplit;
-    int dbg;         // developer experiments: 1 = no delay_vals loads, 2 = no phase / sin-cos arithmetic, 4 = no output stores,
+    int dbg;         // developer experiments: 1 = no delay_vals loads, 2 = no phase / sin-cos arithmetic (and no B stores), 4 = no output stores,
                      // 8 = no L2 prefetches of delay_vals (C3: 268 -> 290 us without them; C5 share: no difference),
                      // 16 = half of the u8 -> fp16 conversion work, 32 = no epilogue staging stores / proxy fence,
                      // 64 = one MMA per tile (the last three on top of 4: which role carries the SM-side time)
@@ -1732,23 +1732,37 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                         }
                     }
                     const bool whole = (e0 - ctid) + kStride * kBatch <= entries;  // batch inside the tile (uniform over the role)
-#pragma unroll
-                    for (int g = 0; g < kBatch; g += kIlp) {
-                        float ph_t[kIlp];
-                        int ph_q[kIlp];
+                    // entries of the tile from this batch on (uniform over the role).  A batch that reaches past the end of
+                    // a narrow tile (C2: 1024 entries for the 2048 of a batch; C4: 2560, so its second batch holds 512)
+                    // evaluates only the pair that exists (the arithmetic is branch-free per entry): C2 40.1 -> 39.2 us, the
+                    // C4 share 193.5 -> 192.7 us, C3 unchanged (same box, interleaved)
+                    const int left = entries - (e0 - ctid);
+                    auto evaluate = [&](auto n_c, int g) {
+                        constexpr int n = decltype(n_c)::value;
+                        float ph_t[n];
+                        int ph_q[n];
                         bool in_range = true;
 #pragma unroll
-                        for (int u = 0; u < kIlp; ++u) in_range &= phase_fast(v[g + u], &ph_t[u], &ph_q[u]);
+                        for (int u = 0; u < n; ++u) in_range &= phase_fast(v[g + u], &ph_t[u], &ph_q[u]);
                         if (!in_range) {
 #pragma unroll
-                            for (int u = 0; u < kIlp; ++u) {
+                            for (int u = 0; u < n; ++u) {
                                 const Tq r = phase_f64(v[g + u]);
                                 ph_t[u] = r.t, ph_q[u] = r.q;
                             }
                         }
 #pragma unroll
-                        for (int u = 0; u < kIlp; ++u)
+                        for (int u = 0; u < n; ++u)
                             finish(ph_t[u], ph_q[u], d0[g + u], e0 + (g + u) * kStride, whole || e0 + (g + u) * kStride < entries);
+                    };
+                    if (prm.dbg & 2) {  // (ablation: no phase / sin-cos arithmetic, no B stores)
+                    } else if constexpr (kIlp == 4 && kBatch == 4) {
+                        if (left <= 2 * kStride) evaluate(std::integral_constant<int, 2>{}, 0);
+                        else evaluate(std::integral_constant<int, 4>{}, 0);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < kBatch; g += kIlp)
+                            if (g == 0 || g * kStride < left) evaluate(std::integral_constant<int, kIlp>{}, g);
                     }
                 }
                 if (!ok) break;
