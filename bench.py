@@ -707,7 +707,8 @@ def run_ours(args, wl) -> None:
         q_sec = q_ms / 1e3 / args.steps
         q8 = {"ms_per_step": q_sec * 1e3, "value": world * in_bytes / q_sec / 1e9, "unit": UNIT,
               "algorithmic_bytes_per_launch": q8_bytes, "algorithmic_GBps_per_gpu": q8_bytes / q_sec / 1e9,
-              "note": "int8 beams = clip(rint(beam*gain)); output bytes / 4"}
+              "note": "int8 beams = clip(rint(beam*gain)); output bytes / 4",
+              "parity": "unpinned: the reference has no requantising path; checked against this repo's own oracle.requantise of the float64 beams"}
         del out8
 
     # ---- end to end through the host-buffer C-ABI call (pinned host arrays, H2D + kernel + D2H timed) ----
