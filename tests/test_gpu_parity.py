@@ -1125,6 +1125,41 @@ def test_full_size_single_rounding_option_stays_inside_the_budget(dropin, name):
     assert worst < 0.25, worst  # (measured: under a tenth of the budget)
 
 
+@pytest.mark.parametrize("shape", [(64, 1024, 256, 16), (64, 512, 256, 64), (80, 600, 256, 32), (197, 64, 256, 256)],
+                         ids=["c2", "c3_share", "c4_like", "c5_like"])
+def test_repeated_launches_are_bit_identical(dropin, shape):
+    """200 launches queued back to back over rotating input / output sets (programmatic dependent launch lets each start
+    while its predecessor drains) must all reproduce the first result of their input set bit for bit: a tile overwritten
+    before its last reader is done would show here and not in a test that launches once (tools/stress_determinism.py is
+    the long version)."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    a, c, t, m = shape
+    dev = torch.device("cuda", 0)
+    sets, reps = 3, 200
+    inputs = [_full_size_inputs(a, c, t, m, seed=61 + j) for j in range(sets)]
+    out_shape = (1, 2, c, t // 16, 16, 2 * m)
+    stream = torch.cuda.Stream()
+    refs = []
+    for x, dv in inputs:
+        o = torch.empty(out_shape, dtype=torch.float32, device=dev)
+        _capi.fused(x, dv, o, 1, a, c, c, t, m, 0, TS, 0, stream)
+        stream.synchronize()
+        refs.append(o)
+    ring = [torch.full(out_shape, float("nan"), dtype=torch.float32, device=dev) for _ in range(8)]
+    bad = 0
+    for start in range(0, reps, len(ring)):
+        for i in range(len(ring)):
+            x, dv = inputs[(start + i) % sets]
+            _capi.fused(x, dv, ring[i], 1, a, c, c, t, m, 0, TS, 0, stream)
+        stream.synchronize()
+        bad += sum(not torch.equal(ring[i], refs[(start + i) % sets]) for i in range(len(ring)))
+    _capi.fused_status()
+    assert bad == 0
+
+
 def test_full_size_q8_against_the_oracle(dropin):
     """int8 requantised output at the size the metric is quoted on (C3): sampled channels against the oracle's
     requantisation of its float64 beams (at most one quantisation step away, practically always equal)."""
