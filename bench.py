@@ -314,6 +314,7 @@ def measure_share(A, C, T, M, B, n_total, xeng_id, steps, dev, peak, desc=None):
         dvs.append(d)
     outs = [torch.empty((B, 2, C, T // 16, 16, 2 * M), dtype=torch.float32, device=dev) for _ in range(sets)]
     stream = torch.cuda.Stream()
+    torch.cuda.synchronize()  # the inputs were generated on the default stream, the launches go to `stream`
 
     def enqueue(n, flags, st):
         for i in range(n):
@@ -503,6 +504,7 @@ def run_ours(args, wl) -> None:
     dv[..., 2] = (torch.rand((C, M, A), device=dev, generator=gen) * 2 - 1) * 3.14159265
     beams = torch.empty((B, 2, C, T // 16, 16, 2 * M), dtype=torch.float32, device=dev)
     stream = torch.cuda.Stream()
+    torch.cuda.synchronize()  # the inputs were generated on the default stream, the launches go to `stream`
     alg_bytes = _capi.fused_bytes(B, A, C, T, M)
     in_bytes = samples.numel()
 

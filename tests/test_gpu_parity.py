@@ -788,6 +788,7 @@ def test_concurrent_launches_on_several_streams_do_not_share_the_channel_queue(d
         want.append(o)
     streams = [torch.cuda.Stream() for _ in range(3)]
     outs = [[torch.full_like(want[0], float("nan")) for _ in range(4)] for _ in range(3)]
+    torch.cuda.synchronize()  # (the fills ran on the default stream, the launches go to side streams)
     for rep in range(4):
         for i, st in enumerate(streams):
             flags = _capi.FLAG_STREAMING if rep else 0
@@ -1142,6 +1143,7 @@ def test_repeated_launches_are_bit_identical(dropin, shape):
     inputs = [_full_size_inputs(a, c, t, m, seed=61 + j) for j in range(sets)]
     out_shape = (1, 2, c, t // 16, 16, 2 * m)
     stream = torch.cuda.Stream()
+    torch.cuda.synchronize()  # the inputs were generated on the default stream, the launches go to `stream`
     refs = []
     for x, dv in inputs:
         o = torch.empty(out_shape, dtype=torch.float32, device=dev)
@@ -1149,15 +1151,26 @@ def test_repeated_launches_are_bit_identical(dropin, shape):
         stream.synchronize()
         refs.append(o)
     ring = [torch.full(out_shape, float("nan"), dtype=torch.float32, device=dev) for _ in range(8)]
-    bad = 0
+    torch.cuda.synchronize()
+    bad, detail = 0, ""
     for start in range(0, reps, len(ring)):
         for i in range(len(ring)):
             x, dv = inputs[(start + i) % sets]
             _capi.fused(x, dv, ring[i], 1, a, c, c, t, m, 0, TS, 0, stream)
         stream.synchronize()
-        bad += sum(not torch.equal(ring[i], refs[(start + i) % sets]) for i in range(len(ring)))
+        for i in range(len(ring)):
+            ref = refs[(start + i) % sets]
+            if not torch.equal(ring[i], ref):
+                bad += 1
+                if not detail:
+                    diff = (ring[i] != ref) | torch.isnan(ring[i])
+                    idx = diff.nonzero()
+                    detail = (f"launch {start + i}: {int(diff.sum())} values differ, nan {int(torch.isnan(ring[i]).sum())}, "
+                              f"max |d| {float((ring[i] - ref).abs().nan_to_num().max()):.3g}, first {idx[0].tolist()}, last {idx[-1].tolist()}, "
+                              f"channels {sorted(set(idx[:, 2].tolist()))[:12]}, pols {sorted(set(idx[:, 1].tolist()))}, "
+                              f"columns {sorted(set(idx[:, 5].tolist()))[:8]}...")
     _capi.fused_status()
-    assert bad == 0
+    assert bad == 0, f"{bad} of {reps} launches differ; {detail}"
 
 
 def test_full_size_q8_against_the_oracle(dropin):

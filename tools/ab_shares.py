@@ -69,6 +69,7 @@ def main():
                                         flags, stream.cuda_stream)
                 assert st == 0, st
 
+        torch.cuda.synchronize()  # the inputs were generated on the default stream, the launches go to `stream`
         results = {}
         ref = None
         for name, lib in libs:  # warm-up + identity of results across builds

@@ -47,6 +47,7 @@ def main():
             d[..., 2] = (torch.rand((Cc, M, A), device=dev) * 2 - 1) * 3.14159265
             dvs.append(d)
         shape = (B, 2, Cc, T // 16, 16, 2 * M)
+        torch.cuda.synchronize()  # the inputs were generated on the default stream, the launches go to `stream`
         refs = []
         for j in range(sets):
             o = torch.empty(shape, dtype=torch.float32, device=dev)
@@ -54,6 +55,7 @@ def main():
             stream.synchronize()
             refs.append(o)
         outs = [torch.full(shape, float("nan"), dtype=torch.float32, device=dev) for _ in range(reps)]
+        torch.cuda.synchronize()
         with torch.cuda.stream(stream):
             for i in range(reps):
                 _capi.fused(xs[i % sets], dvs[i % sets], outs[i], B, A, Cc, Cc, T, M, 0, TS, flags, stream)
