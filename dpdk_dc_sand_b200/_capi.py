@@ -54,6 +54,11 @@ SIGNATURES = {
                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_uint,
                                 C.c_void_p]),
     "dcbf_fused_q8_bytes": (C.c_ulonglong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dcbf_fused_packed_bytes": (C.c_ulonglong, [C.c_int, C.c_int, C.c_int, C.c_uint]),
+    "dcbf_fused_pack_coeffs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                         C.c_void_p, C.c_uint, C.c_void_p]),
+    "dcbf_fused_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_double, C.c_uint, C.c_void_p]),
     "dcbf_fused_status": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dcbf_fused_status_poll": (C.c_int, []),
     "dcbf_debug_set_profile_buffer": (None, [C.c_void_p]),
@@ -273,6 +278,27 @@ def fused_tiling(n_ants, n_beams, flags=0):
     kb, nt, ntc = C.c_int(0), C.c_int(0), C.c_int(0)
     load().dcbf_fused_tiling(n_ants, n_beams, flags, C.byref(kb), C.byref(nt), C.byref(ntc))
     return kb.value, nt.value, ntc.value
+
+
+def fused_packed_bytes(n_ants, n_chans, n_beams, flags=0) -> int:
+    """Bytes of the packed steering-coefficient tile sets of n_chans channels (0: the shape keeps no whole tile set)."""
+    return int(load().dcbf_fused_packed_bytes(n_ants, n_chans, n_beams, flags))
+
+
+def fused_pack_coeffs(delay_vals, packed, n_ants, n_chans, n_chans_total, n_beams, xeng_id, sample_period, flags=0,
+                      stream=None, weights=None) -> None:
+    """dcbf_fused_pack_coeffs: one delay model -> tile sets in the tensor cores' layout (device uint8 tensor `packed`)."""
+    check(load().dcbf_fused_pack_coeffs(_ptr(delay_vals), _ptr(packed), n_ants, n_chans, n_chans_total, n_beams, xeng_id,
+                                        float(sample_period), _ptr(weights) if weights is not None else None, flags,
+                                        _stream_handle(stream)), "dcbf_fused_pack_coeffs")
+
+
+def fused_packed(samples, packed, beams, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams, xeng_id,
+                 sample_period, flags=0, stream=None) -> None:
+    """dcbf_fused_packed: dcbf_fused with the coefficients read from `packed` instead of being evaluated per heap."""
+    check(load().dcbf_fused_packed(_ptr(samples), _ptr(packed), _ptr(beams), n_batches, n_ants, n_chans, n_chans_total,
+                                   n_samples, n_beams, xeng_id, float(sample_period), flags, _stream_handle(stream)),
+          "dcbf_fused_packed")
 
 
 def fused_bytes(n_batches, n_ants, n_chans, n_samples, n_beams) -> int:

@@ -83,6 +83,7 @@ class OpSequence(accel.OperationSequence):
         self.batch_times = None
         self.sample_dt = 0.0
         self.beam_weights = None
+        self._packed = None  # steering coefficients of the bound delay model in the tensor cores' layout (pack_coefficients)
         # The fused path never needs the reordered voltages or the coefficients in HBM, so ensure_all_bound() leaves
         # them out; code written against the reference may still ask for them (its own test reads
         # op.beamform_mult.buffer("inData").shape, beamform_op_sequence_test.py:182): they are then allocated on the
@@ -114,6 +115,34 @@ class OpSequence(accel.OperationSequence):
     def flags(self) -> int:
         return (_capi.FLAG_SIGNED_INPUT if self.signed_input else 0) | (_capi.FLAG_FP16_COEFF if self.fp16_coeff else 0)
 
+    # -- packed steering coefficients (extension) -----------------------------------------------------
+    def pack_coefficients(self) -> bool:
+        """Evaluate the steering coefficients of the delay model now bound to ``bufin_delay_vals`` ONCE
+        (``dcbf_fused_pack_coeffs``): until ``release_coefficients()`` every call of the sequence loads them instead of
+        regenerating them per heap -- bit-identical beams, a fraction of the SM-side work.  The delay model changes at
+        control-plane cadence; call this again after writing a new one.  Returns False (and changes nothing) for shapes
+        that keep no whole tile set (many antennas x beams) and for weights that need a scale, which stay on the
+        per-call path; time-varying steering (``batch_times``) always regenerates."""
+        import torch
+
+        r = self.template.preBeamformReorder_template
+        c = self.template.beamform_coeff_template
+        flags = _capi.FLAG_FP16_COEFF if self.fp16_coeff else 0
+        nbytes = _capi.fused_packed_bytes(r.n_ants, r.n_channels_per_stream, c.n_beams, flags)
+        weights = _device_weights(self)
+        if not nbytes or (weights is not None and weights_log2(self) != 0):
+            self._packed = None
+            return False
+        dv = self.buffer("bufin_delay_vals").buffer
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=dv.device)
+        _capi.fused_pack_coeffs(dv, packed, r.n_ants, r.n_channels_per_stream, c.n_channels, c.n_beams, c.xeng_id,
+                                c.sample_period, flags, self.command_queue.stream, weights=weights)
+        self._packed = (packed, flags)
+        return True
+
+    def release_coefficients(self) -> None:
+        self._packed = None
+
     # -- execution --------------------------------------------------------------------------------
     def _run(self) -> None:
         self.beamform_coeff.batch_times = self.batch_times
@@ -125,6 +154,17 @@ class OpSequence(accel.OperationSequence):
             return
         r = self.template.preBeamformReorder_template
         c = self.template.beamform_coeff_template
+        if self._packed is not None and self.batch_times is None and self._packed[1] == (self.flags() & _capi.FLAG_FP16_COEFF):
+            _capi.fused_packed(
+                self.buffer("bufin_reorder").buffer, self._packed[0], self.buffer("bufout_mult").buffer, r.n_batches,
+                r.n_ants, r.n_channels_per_stream, c.n_channels, r.n_samples_per_channel, c.n_beams, c.xeng_id,
+                c.sample_period, self.flags(), self.command_queue.stream,
+            )
+            if self.slots["bufint_data"].is_bound:
+                self.prebeamform_reorder()
+            if self.slots["bufint_coeff"].is_bound:
+                self.beamform_coeff()
+            return
         _capi.fused(
             self.buffer("bufin_reorder").buffer, self.buffer("bufin_delay_vals").buffer,
             self.buffer("bufout_mult").buffer, r.n_batches, r.n_ants, r.n_channels_per_stream, c.n_channels,

@@ -202,6 +202,43 @@ int dcbf_fused_ex(const uint8_t* samples, const float* delay_vals, float* beams,
                         o.batch_dt_s ? o.sample_dt_s : 0.0, o.beam_weights ? o.beam_weights_log2 : 0);
 }
 
+unsigned long long dcbf_fused_packed_bytes(int A, int C, int M, unsigned flags) {
+    if (A <= 0 || C <= 0 || M <= 0) return 0;
+    int kb = 0, nt = 0, ntc = 0;
+    fused_tiling(A, M, flags, &kb, &nt, &ntc);
+    if (ntc != 1 || nt < 16) return 0;  // K-streamed shapes keep no whole tile set
+    const int parts = (flags & DCBF_FLAG_FP16_COEFF) ? 1 : 2;
+    return 1ull * C * kb * parts * nt * 128;
+}
+
+int dcbf_fused_pack_coeffs(const float* delay_vals, void* packed, int A, int C, int N, int M, int xeng_id,
+                           double sample_period, const float* beam_weights, unsigned flags, dcbf_stream_t stream) {
+    if (!delay_vals || !packed || A <= 0 || C <= 0 || N <= 0 || M <= 0 || xeng_id < 0 || !(sample_period > 0.0))
+        return DCBF_ERR_INVALID_ARG;
+    if (!aligned16(delay_vals) || !aligned16(packed)) return DCBF_ERR_INVALID_ARG;
+    if (!dcbf_fused_packed_bytes(A, C, M, flags)) return DCBF_ERR_UNSUPPORTED;
+    if (int e = check_device()) return e;
+    // (the kernel of the hot path with its voltage and beam roles idle: the tile sets are bit for bit what dcbf_fused
+    // builds in shared memory; the voltage / beam pointers only have to be valid addresses)
+    uint8_t* img = static_cast<uint8_t*>(packed);
+    return launch_fused(img, delay_vals, reinterpret_cast<float*>(img), 1, A, C, N, 128, M, static_cast<long long>(C) * xeng_id,
+                        sample_period, nullptr, flags & (DCBF_FLAG_FP16_COEFF | DCBF_FLAG_SIGNED_INPUT), static_cast<cudaStream_t>(stream),
+                        nullptr, beam_weights, 0.0, 0, 1, img);
+}
+
+int dcbf_fused_packed(const uint8_t* samples, const void* packed, float* beams, int B, int A, int C, int N, int T, int M,
+                      int xeng_id, double sample_period, unsigned flags, dcbf_stream_t stream) {
+    if (!samples || !packed || !beams || B <= 0 || A <= 0 || C <= 0 || N <= 0 || M <= 0 || xeng_id < 0 || bad_t(T) ||
+        !(sample_period > 0.0))
+        return DCBF_ERR_INVALID_ARG;
+    if (!aligned16(samples) || !aligned16(packed) || !aligned16(beams)) return DCBF_ERR_INVALID_ARG;
+    if (!dcbf_fused_packed_bytes(A, C, M, flags)) return DCBF_ERR_UNSUPPORTED;
+    if (int e = check_device()) return e;
+    return launch_fused(samples, nullptr, beams, B, A, C, N, T, M, static_cast<long long>(C) * xeng_id, sample_period, nullptr,
+                        flags, static_cast<cudaStream_t>(stream), nullptr, nullptr, 0.0, 0, 2,
+                        const_cast<uint8_t*>(static_cast<const uint8_t*>(packed)));
+}
+
 int dcbf_fused_status(int* role, int* barrier, int* block) {
     if (int e = check_device()) return e;
     return fused_status(role, barrier, block);

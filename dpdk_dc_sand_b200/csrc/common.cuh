@@ -56,7 +56,7 @@ struct QuantisedOut {
 int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T,
                  int M, long long first_chan, double sample_period, const double* batch_dt_s, unsigned flags,
                  cudaStream_t s, const QuantisedOut* q8 = nullptr, const float* beam_weights = nullptr,
-                 double sample_dt_s = 0.0, int weights_log2 = 0);
+                 double sample_dt_s = 0.0, int weights_log2 = 0, int packed_mode = 0, uint8_t* packed = nullptr);
 int fused_status(int* role, int* barrier, int* block);
 int fused_status_poll();
 void fused_set_profile_buffer(unsigned long long* dev_ptr);

@@ -182,6 +182,13 @@ struct FusedParams {
                      // 16 = half of the u8 -> fp16 conversion work, 32 = no epilogue staging stores / proxy fence,
                      // 64 = one MMA per tile (the last three on top of 4: which role carries the SM-side time)
     int pdl_wait;    // 1: wait for the preceding kernel of the stream (griddepcontrol.wait) after the prologue
+    // Packed steering coefficients (whole-tile-set mode, static steering): the B tile set of a channel -- exactly the bytes
+    // the coefficient role leaves in a B buffer -- kept in HBM between delay-model updates.  1: generate and write them
+    // (no voltages are read, no beams written); 2: the hot path loads them with one bulk copy per channel instead of
+    // evaluating 4096 phases and sin/cos pairs per channel and heap.
+    int packed_mode;
+    int packed_bytes;       // bytes of one channel's tile set (kb_count * parts * nt * 128)
+    uint8_t* packed;        // [C][packed_bytes]
     int raw_extra_off;  // byte offset of the first extra stage inside each 64 KiB B buffer
     int aop_extra;      // whole tile sets: 1 = A stages 2 and 3 in the last 16 KiB of the two B buffers
     uint32_t inv_a;     // floor(2^32 / A) + 1: e / A == umulhi(e, inv_a) for every entry index of an N tile (A >= 2)
@@ -444,7 +451,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             mbar_init(bar(kAopEmpty + s), 2);  // one tcgen05.commit per MMA warp
         }
         for (int s = 0; s < kBopSlots; ++s) {
-            mbar_init(bar(kBopFull + s), kPair ? 2 * kCoeffWarps : kCoeffWarps);
+            mbar_init(bar(kBopFull + s), prm.packed_mode == 2 ? 1 : kPair ? 2 * kCoeffWarps : kCoeffWarps);  // (packed: one bulk copy)
             mbar_init(bar(kBopEmpty + s), 2);
         }
         for (int s = 0; s < kAccBufs; ++s) {
@@ -473,7 +480,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     }
     if (warp == kProducerWarp && lane == 0) prefetch_tensormap(&tm_in);
     if (warp == kEpilogueWarp0 && lane == 0) prefetch_tensormap(&tm_out);
-    if (!kPair && warp == kCoeffWarp0 + 1 && prm.pdl_wait && !(prm.dbg & 8)) {
+    if (!kPair && warp == kCoeffWarp0 + 1 && prm.pdl_wait && !(prm.dbg & 8) && prm.packed_mode != 1) {
         // The first unit's inputs -> L2 before anything else asks for memory (and, with programmatic dependent launch,
         // while the preceding kernel still drains: a prefetch returns no data, and L2 is the coherence point of global
         // memory, so this is safe ahead of the dependency wait).  The launch is otherwise serial until the first B tile
@@ -497,8 +504,12 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
             const int bh = prm.B * prm.ht_count;
             m0 = (j0 / bh) * (prm.nt >> 1), b0 = (j0 % bh) / prm.ht_count, h0 = j0 % prm.ht_count;
         }
-        const size_t dv_bytes = static_cast<size_t>(min(prm.nt >> 1, prm.M - m0)) * prm.A * 16;
+        size_t dv_bytes = static_cast<size_t>(min(prm.nt >> 1, prm.M - m0)) * prm.A * 16;
         const char* dv_p = reinterpret_cast<const char*>(prm.dv + (static_cast<size_t>(uc) * prm.M + m0) * prm.A);
+        if (prm.packed_mode == 2) {  // the channel's packed tile set instead of its delay_vals
+            dv_bytes = static_cast<size_t>(prm.packed_bytes);
+            dv_p = reinterpret_cast<const char*>(prm.packed) + static_cast<size_t>(uc) * dv_bytes;
+        }
         for (size_t o = static_cast<size_t>(lane) * 8192; o < dv_bytes; o += 32 * 8192)
             bulk_prefetch_l2(dv_p + o, static_cast<uint32_t>(min(dv_bytes - o, static_cast<size_t>(8192))));
         const uint32_t row_bytes = static_cast<uint32_t>(min(hn * kTileT, prm.T - h0 * kTileT)) * 4u;
@@ -586,7 +597,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
     if (warp == kProducerWarp) {
         // =================================== TMA producer ===================================
         uint32_t rs = 0, ph = 0;
-        bool ok = true;
+        bool ok = prm.packed_mode != 1;  // (packing the coefficients: no voltages are read)
         // one raw slab: [16 antennas][128 samples] of (batch b, channel c) -> next ring stage
         auto load_slab = [&](int h, int c, int s, int b) {
             if (!mbar_wait<kProf, false, DCBF_BACKOFF_NS>(bar(kRawEmpty + rs), ph ^ 1u, ctl, prm.status, kRoleProducer, kRawEmpty + rs, ps + 0)) return false;
@@ -756,6 +767,21 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                 const int jend = min(j1, (j / bh_count + 1) * bh_count);
                 const uint32_t bb = step % kBopBufs;
                 ok = mbar_wait<kProf>(bar(kBopFull + bb), (step / kBopBufs) & 1u, ctl, prm.status, kRoleMma, kBopFull + bb, ps + 0);
+                if (prm.packed_mode == 1) {
+                    // packing: the finished tile set goes to HBM as it lies in shared memory (the writers have fenced it for
+                    // the async proxy); the buffer is handed back once the copy has read it.  One arrival per MMA warp,
+                    // like the two commits of the normal path.
+                    if (ok && warp == kMmaWarp && elect_one()) {
+                        bulk_store(prm.packed + static_cast<size_t>(uc) * prm.packed_bytes, bop_base + bb * kBopBufBytes,
+                                   static_cast<uint32_t>(prm.packed_bytes));
+                        bulk_commit_group();
+                        bulk_wait_group_read<0>();
+                    }
+                    __syncwarp();
+                    if (ok && lane == 0) mbar_arrive(bar(kBopEmpty + bb));
+                    j = jend;
+                    continue;
+                }
                 for (; j < jend && ok; ++j, ++unit) {
                     const uint32_t ab = unit % kAccBufs;
                     ok = mbar_wait<kProf>(bar(kAccEmpty + ab), ((unit / kAccBufs) & 1u) ^ 1u, ctl, prm.status, kRoleMma, kAccEmpty + ab, ps + 1);
@@ -833,7 +859,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         };
         uint32_t unit = 0, box = 0;
         int clipped = 0;
-        bool ok = true;
+        bool ok = prm.packed_mode != 1;  // (packing the coefficients: no beams are formed)
         // One accumulator tile (128 rows x nt columns at TMEM column col0) -> beams[b][p][c][t0 ..][n0 ..], float32.
         auto store_tile_f32 = [&](uint32_t col0, int b, int p, uint32_t c, int t0, int n0, int ncols) {
             if (prm.tma_store) {
@@ -1163,7 +1189,7 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         const uint32_t flip = prm.signed_in ? 0x80808080u : 0u;
         const uint32_t sw = static_cast<uint32_t>((t >> 1) & 3);
         uint32_t slab = 0, rs = 0, rph = 0;
-        bool ok = true;
+        bool ok = prm.packed_mode != 1;
         for (uint32_t k = 0, w; ok && (w = sched_get(ctl, k)) < n_units; ++k) {
             int tiles;  // (batch, time tile) pairs of the unit, each with slab_count slabs
             if (kStream) {
@@ -1259,6 +1285,9 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
         int sch_n = 0, sch_raw = 0;  // sch_raw: counter value still in flight (not touched until it is published)
         bool sch_end = false, sch_pending = false;
         auto warm_l2 = [&](int ch, int m0) {  // delay_vals of one (channel, N tile) step -> L2
+            // (packed tile sets: the bulk copy itself is issued a whole buffer ahead of its use; warming L2 two units ahead
+            // on top of that cost 10 % at C3 -- 283 vs 257 us -- the lines are evicted by the output stream and fetched twice)
+            if (prm.packed_mode == 2) return;
             m0 += m_cta0;
             if (m0 >= M) return;
             const size_t bytes = static_cast<size_t>(min(mt_cta, M - m0)) * A * 16;
@@ -1523,6 +1552,38 @@ fused_beamform_kernel(const __grid_constant__ FusedParams prm, const __grid_cons
                       };
                       if (kDepth > 1 && (kstep & 1u)) do_step(std::integral_constant<int, kDepth - 1>{});
                       else do_step(std::integral_constant<int, 0>{});
+                    }
+                }
+            }
+        } else if (prm.packed_mode == 2) {
+            // packed tile sets: one bulk copy per unit into the free B buffer (asynchronous proxy to asynchronous proxy: no
+            // fence), issued by the scheduler's warp a whole buffer ahead of the MMAs; the other coefficient warps have
+            // nothing to do in this mode
+            if (warp == kCoeffWarp0) {
+                uint32_t step = 0;
+                bool ok = true;
+                for (uint32_t k = 0;; ++k) {
+                    if (is_sched) {  // keep the sequence published one unit beyond this one
+                        while (!sch_end && sch_n <= static_cast<int>(k) + 1) {
+                            sch_request();
+                            sch_flush();
+                        }
+                    }
+                    __syncwarp();
+                    const uint32_t w = static_cast<uint32_t>(sched_get(ctl, k));
+                    if (!ok || w >= n_units) break;
+                    uint32_t c;
+                    int j0, j1;
+                    unit_range(w, &c, &j0, &j1);
+                    for (int isb = j0 / bh_count, isb_last = (j1 - 1) / bh_count; isb <= isb_last && ok; ++isb, ++step) {
+                        const uint32_t bb = step % kBopBufs;
+                        ok = mbar_wait<kProf, false, DCBF_BACKOFF_NS>(bar(kBopEmpty + bb), ((step / kBopBufs) & 1u) ^ 1u, ctl, prm.status, kRoleCoeff, kBopEmpty + bb, ps + 0);
+                        if (ok && lane == 0) {
+                            mbar_arrive_expect_tx(bar(kBopFull + bb), static_cast<uint32_t>(prm.packed_bytes));
+                            bulk_load(bop_base + bb * kBopBufBytes, prm.packed + static_cast<size_t>(c) * prm.packed_bytes,
+                                      static_cast<uint32_t>(prm.packed_bytes), bar(kBopFull + bb));
+                        }
+                        __syncwarp();
                     }
                 }
             }
@@ -1897,8 +1958,11 @@ int get_encode_fn(EncodeTiledFn* out) {
 
 int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, int B, int A, int C, int N, int T,
                  int M, long long first_chan, double sample_period, const double* batch_dt_s, unsigned flags,
-                 cudaStream_t s, const QuantisedOut* q8, const float* beam_weights, double sample_dt_s, int weights_log2) {
+                 cudaStream_t s, const QuantisedOut* q8, const float* beam_weights, double sample_dt_s, int weights_log2,
+                 int packed_mode, uint8_t* packed) {
     FusedParams p{};
+    p.packed_mode = packed_mode;
+    p.packed = packed;
     p.dv = reinterpret_cast<const float4*>(delay_vals);
     p.samples = samples;
     p.out = beams;
@@ -1967,6 +2031,12 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
         const int spare = (kBopBufBytes - used - (p.aop_extra ? kAopStageBytes : 0)) / kRawStageBytes;
         p.raw_extra_off = used;
         p.raw_stages = kRawStages + 2 * std::min(spare, (kMaxRawStages - kRawStages) / 2);
+    }
+    if (packed_mode) {  // whole tile sets, static steering, float32 beams only (the shapes packed_bytes() answers for)
+        if (kstream || batch_dt_s || q8 || !packed) return DCBF_ERR_UNSUPPORTED;
+        p.packed_bytes = p.kb_count * p.parts * p.nt * 128;
+        if (packed_mode == 1) flags |= DCBF_FLAG_DEBUG_WHOLE_CHANNELS;  // every channel is generated (and written) once
+        else flags |= DCBF_FLAG_DEBUG_NO_BEAM_PIECES;                   // a piece of a cut channel loads the whole tile set
     }
     p.tma_store = !(flags & DCBF_FLAG_DEBUG_DIRECT_EPILOGUE) && (M % (q8 ? 8 : 2) == 0) && (p.nt_count == 1 || p.nt % 32 == 0);
     if (static_cast<long long>(B) * kPols * C > 0x7fffffffLL) return DCBF_ERR_UNSUPPORTED;

@@ -205,6 +205,30 @@ int dcbf_fused_status(int* role, int* barrier, int* block);
  * cudaStreamSynchronize / an event wait); dcbf_host_plan_run* check it themselves and return the error. */
 int dcbf_fused_status_poll(void);
 
+/* Packed steering coefficients: the delay model changes at control-plane cadence (the reference rebuilds its
+ * coefficient array on every call of the sequence, beamformer/beamforming/beamform_op_sequence.py:117-157; its native
+ * precursor has stand-alone generators that leave a coefficient array in device memory for a later beamformer,
+ * beamformer_coefficient_generator/BeamformerKernels.cu:7-54, 56-119), the heaps arrive every fraction of a
+ * millisecond.  dcbf_fused_pack_coeffs evaluates the steering coefficients of one
+ * delay model ONCE and stores them in the layout the tensor cores read (fp16 hi + lo rows, 128-byte swizzle: the very
+ * bytes dcbf_fused builds per channel in shared memory); dcbf_fused_packed is dcbf_fused with those tile sets loaded by
+ * one bulk copy per channel instead of 4096 phase / sin-cos evaluations per channel and heap.  Same HBM traffic
+ * (a tile set is as large as the channel's delay_vals for the hi+lo pair), bit-identical beams, a fraction of the
+ * SM-side work -- which is what a power-capped board runs out of first.
+ * Static steering, float32 beams, shapes whose tile set fits one shared-memory buffer (dcbf_fused_tiling nt_count == 1:
+ * up to 64 antennas x 64 beams, 128 x 32, 256 x 16 ...); otherwise dcbf_fused_packed_bytes returns 0 and the two calls
+ * DCBF_ERR_UNSUPPORTED.  flags: DCBF_FLAG_FP16_COEFF must be the same in all three calls; DCBF_FLAG_SIGNED_INPUT and
+ * DCBF_FLAG_STREAMING as for dcbf_fused (a streaming launch must not directly follow the pack it reads on the stream:
+ * it would not wait for it).  beam_weights: optional [n_beams][n_ants] real weights folded into the
+ * coefficients (as dcbf_fused_ex with beam_weights_log2 = 0), or NULL. */
+unsigned long long dcbf_fused_packed_bytes(int n_ants, int n_chans, int n_beams, unsigned flags);
+int dcbf_fused_pack_coeffs(const float* delay_vals, void* packed, int n_ants, int n_chans, int n_chans_total, int n_beams,
+                           int xeng_id, double sample_period, const float* beam_weights, unsigned flags,
+                           dcbf_stream_t stream);
+int dcbf_fused_packed(const uint8_t* samples, const void* packed, float* beams, int n_batches, int n_ants, int n_chans,
+                      int n_chans_total, int n_samples, int n_beams, int xeng_id, double sample_period, unsigned flags,
+                      dcbf_stream_t stream);
+
 /* Developer aid: when non-NULL, every dcbf_fused CTA writes 24 uint64 to dev_ptr[blockIdx*24 + role*4 + slot]:
  * nanoseconds each warp role spent blocked per barrier class (slot 0..2) and the role's span (slot 3).
  * The buffer must hold 24 * (number of SMs) entries. */

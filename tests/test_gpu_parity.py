@@ -1126,6 +1126,106 @@ def test_full_size_single_rounding_option_stays_inside_the_budget(dropin, name):
     assert worst < 0.25, worst  # (measured: under a tenth of the budget)
 
 
+PACKED_CASES = [
+    # B, A, C, T, M, N, xeng_id, flags
+    (1, 64, 300, 256, 64, 4096, 3, 0),                         # C3 geometry, more channels than SMs (cut last round)
+    (1, 64, 170, 256, 16, 1024, 0, 0),                         # C2 geometry (merged hi|lo tiles, extra ring stages)
+    (2, 80, 40, 256, 32, 32768, 7, 0),                         # C4 geometry, two heaps per launch
+    (1, 4, 64, 256, 4, 64, 0, 0),                              # BASELINE configs[0]
+    (2, 5, 3, 32, 3, 256, 1, 0),                               # odd everything (register epilogue), partial time tile
+    (1, 64, 149, 16, 4, 4096, 3, 1),                           # signed input, 16-sample heaps
+    (3, 33, 200, 144, 9, 4096, 2, 2),                          # single-rounding coefficients (half-size tile sets)
+    (1, 256, 6, 256, 16, 1024, 0, 4),                          # 8 k-blocks, streaming launches
+]
+
+
+@pytest.mark.parametrize("case", PACKED_CASES, ids=lambda c: "B{}A{}C{}T{}M{}N{}x{}f{}".format(*c))
+def test_packed_coefficients_give_the_same_beams(dropin, case):
+    """dcbf_fused_pack_coeffs + dcbf_fused_packed (the delay model evaluated once, its tile sets loaded per heap) against
+    dcbf_fused: bit-identical -- the packed bytes ARE what the kernel builds in shared memory -- and against the float64
+    oracle; a second delay model packed into the same buffer replaces the first."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m, n, xid, flags = case
+    dev = torch.device("cuda", 0)
+    x = orc.make_samples(b, a, c, t, seed=300 + a)
+    dvs = [orc.make_delay_vals_random(c, m, a, seed=400 + m + i) for i in range(2)]
+    dx = torch.from_numpy(x).to(dev)
+    nbytes = _capi.fused_packed_bytes(a, c, m, flags)
+    assert nbytes == c * _capi.fused_tiling(a, m, flags)[0] * (1 if flags & 2 else 2) * _capi.fused_tiling(a, m, flags)[1] * 128
+    packed = torch.full((nbytes + 256,), 0x5A, dtype=torch.uint8, device=dev)  # (a canary tail)
+    shape = (b, 2, c, t // 16, 16, 2 * m)
+    for i, dv in enumerate(dvs):
+        ddv = torch.from_numpy(dv).to(dev)
+        want = torch.full(shape, float("nan"), dtype=torch.float32, device=dev)
+        got = torch.full(shape, float("nan"), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        _capi.fused(dx, ddv, want, b, a, c, n, t, m, xid, TS, flags)
+        _capi.fused_pack_coeffs(ddv, packed, a, c, n, m, xid, TS, flags & _capi.FLAG_FP16_COEFF)
+        if flags & _capi.FLAG_STREAMING:  # a streaming launch promises independence of the kernel queued before it:
+            torch.cuda.synchronize()      # the first one after a pack is not (dcbf.h), so the pack is waited for here
+        n0 = _capi.launch_count()
+        _capi.fused_packed(dx, packed, got, b, a, c, n, t, m, xid, TS, flags)
+        torch.cuda.synchronize()
+        _capi.fused_status()
+        assert _capi.launch_count() - n0 == 1
+        assert torch.equal(got, want), (i, int((got != want).sum()))
+        assert bool((packed[nbytes:] == 0x5A).all())
+        if i == 0:
+            ref = orc.beamform_pipeline(x, dv, n, xid, TS, signed_input=bool(flags & 1))
+            assert np.all(np.abs(got.cpu().numpy().astype(np.float64) - ref) <= _budget(x, bool(flags & 1)))
+
+
+def test_packed_coefficients_through_the_operator_and_unsupported_shapes(dropin):
+    """OpSequence.pack_coefficients(): the calls after it load the packed tile sets (one launch each, same beams as
+    before); a new delay model needs a new pack; shapes without a whole tile set stay on the per-call path."""
+    import torch
+
+    from beamforming.beamform_op_sequence import OpSequenceTemplate
+    from dpdk_dc_sand_b200 import _capi
+
+    ctx, queue = dropin
+    b, a, c, t, m, n, xid = 1, 64, 40, 256, 64, 4096, 2
+    op = OpSequenceTemplate(ctx, b, 2, c, n, t // 16, 16, a, m, xid, TS, t).instantiate(queue)
+    op.ensure_all_bound()
+    x = orc.make_samples(b, a, c, t, seed=5)
+    dv = orc.make_delay_vals_random(c, m, a, seed=6)
+    op.buffer("bufin_reorder").set(queue, x)
+    op.buffer("bufin_delay_vals").set(queue, dv)
+    op()
+    want = op.buffer("bufout_mult").get(queue).copy()
+    assert op.pack_coefficients()
+    op.buffer("bufout_mult").zero(queue)
+    n0 = _capi.launch_count()
+    op()
+    got = op.buffer("bufout_mult").get(queue)
+    assert _capi.launch_count() - n0 == 1
+    assert np.array_equal(got, want)
+    dv2 = orc.make_delay_vals_random(c, m, a, seed=7)
+    op.buffer("bufin_delay_vals").set(queue, dv2)
+    op()  # still the packed (old) model: the delay model is only read when it is packed
+    assert np.array_equal(op.buffer("bufout_mult").get(queue), want)
+    op.pack_coefficients()
+    op()
+    ref = orc.beamform_pipeline(x, dv2, n, xid, TS)
+    assert np.all(np.abs(op.buffer("bufout_mult").get(queue).astype(np.float64) - ref) <= _budget(x))
+    op.release_coefficients()
+    op()
+    assert np.all(np.abs(op.buffer("bufout_mult").get(queue).astype(np.float64) - ref) <= _budget(x))
+    _capi.fused_status()
+    # many antennas x beams: K-streamed, no whole tile set
+    assert _capi.fused_packed_bytes(197, 8, 256) == 0
+    dev = torch.device("cuda", 0)
+    dummy = torch.zeros(1 << 20, dtype=torch.uint8, device=dev)
+    with pytest.raises(Exception):
+        _capi.fused_pack_coeffs(torch.zeros((8, 256, 197, 4), device=dev), dummy, 197, 8, 8, 256, 0, TS)
+    big = OpSequenceTemplate(ctx, 1, 2, 2, 64, 8, 16, 197, 256, 0, TS, 128).instantiate(queue)
+    big.ensure_all_bound()
+    assert big.pack_coefficients() is False
+
+
 @pytest.mark.parametrize("shape", [(64, 1024, 256, 16), (64, 512, 256, 64), (80, 600, 256, 32), (197, 64, 256, 256)],
                          ids=["c2", "c3_share", "c4_like", "c5_like"])
 def test_repeated_launches_are_bit_identical(dropin, shape):

@@ -1,6 +1,6 @@
 """Developer probe: dcbf_fused across flag words (debug bits included) at the board's power cap.
 
-    python tools/time_flags_sustained.py A C T M flags [flags ...]
+    python tools/time_flags_sustained.py [--packed] A C T M flags [flags ...]
 
 Per flag word: 0.6 s of back-to-back launches, then 200 launches between two CUDA events, SM clock and power sampled
 through NVML meanwhile (the kernel follows the SM clock once the cap has lowered it).
@@ -17,6 +17,9 @@ from dpdk_dc_sand_b200 import _capi  # noqa: E402
 
 import pynvml  # noqa: E402
 
+PACKED = "--packed" in sys.argv  # dcbf_fused_packed (coefficients packed once) instead of dcbf_fused
+if PACKED:
+    sys.argv.remove("--packed")
 A, C, T, M = (int(v) for v in sys.argv[1:5])
 FLAGS = [int(v, 0) for v in sys.argv[5:]] or [0]
 dev = torch.device("cuda", 0)
@@ -28,7 +31,18 @@ pynvml.nvmlInit()
 h = pynvml.nvmlDeviceGetHandleByIndex(0)
 
 
+packed = {}
+
+
 def launch(f, n):
+    if PACKED:
+        key = f & _capi.FLAG_FP16_COEFF
+        if key not in packed:
+            packed[key] = torch.empty(_capi.fused_packed_bytes(A, C, M, key), dtype=torch.uint8, device=dev)
+            _capi.fused_pack_coeffs(dv, packed[key], A, C, C, M, 0, 1 / 1712e6, key)
+        for _ in range(n):
+            _capi.fused_packed(x, packed[key], out, 1, A, C, C, T, M, 0, 1 / 1712e6, f)
+        return
     for _ in range(n):
         _capi.fused(x, dv, out, 1, A, C, C, T, M, 0, 1 / 1712e6, f)
 
