@@ -321,7 +321,21 @@ def measure_share(A, C, T, M, B, n_total, xeng_id, steps, dev, peak, desc=None):
             j = i % sets
             _capi.fused(xs[j], dvs[j], outs[j], B, A, C, n_total, T, M, xeng_id, SAMPLE_PERIOD, flags, st)
 
-    def run(n, flags):
+    # packed steering coefficients (dcbf_fused_pack_coeffs once per delay model, dcbf_fused_packed per heap); shapes that
+    # keep no whole tile set (C5) have no such path
+    packs = None
+    if _capi.fused_packed_bytes(A, C, M, 0):
+        packs = [torch.empty(_capi.fused_packed_bytes(A, C, M, 0), dtype=torch.uint8, device=dev) for _ in range(sets)]
+        for j in range(sets):
+            _capi.fused_pack_coeffs(dvs[j], packs[j], A, C, n_total, M, xeng_id, SAMPLE_PERIOD, 0, stream)
+        stream.synchronize()
+
+    def enqueue_packed(n, flags, st):
+        for i in range(n):
+            j = i % sets
+            _capi.fused_packed(xs[j], packs[j], outs[j], B, A, C, n_total, T, M, xeng_id, SAMPLE_PERIOD, flags, st)
+
+    def run(n, flags, enqueue=enqueue):
         """(device seconds per launch, host seconds spent issuing one launch) of n launches from the host."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
@@ -369,6 +383,14 @@ def measure_share(A, C, T, M, B, n_total, xeng_id, steps, dev, peak, desc=None):
     # the optional single fp16 rounding of the coefficients (one MMA pass, inside the 2^-10 sum|x| budget) with streaming
     run(sets, _capi.FLAG_STREAMING | _capi.FLAG_FP16_COEFF)
     sec_h_stream, _ = run(steps, _capi.FLAG_STREAMING | _capi.FLAG_FP16_COEFF)
+    sec_p = sec_p_stream = 0.0
+    if packs is not None:
+        time.sleep(0.25)
+        run(sets, 0, enqueue_packed)
+        sec_p, _ = run(steps, 0, enqueue_packed)
+        time.sleep(0.25)
+        run(sets, _capi.FLAG_STREAMING, enqueue_packed)
+        sec_p_stream, _ = run(steps, _capi.FLAG_STREAMING, enqueue_packed)
     _capi.fused_status()
     out = {"ms_per_step": sec * 1e3, "input_GBps": xs[0].numel() / sec / 1e9,
            "beam_gsamples_per_s": B * 2 * C * T * M / sec / 1e9, "algorithmic_bytes_per_launch": alg,
@@ -380,6 +402,9 @@ def measure_share(A, C, T, M, B, n_total, xeng_id, steps, dev, peak, desc=None):
            "graph_streaming_roofline_frac": alg / sec_graph_stream / 1e9 / peak,
            "fp16_coeff_streaming_ms_per_step": sec_h_stream * 1e3,
            "fp16_coeff_streaming_roofline_frac": alg / sec_h_stream / 1e9 / peak,
+           "packed_ms_per_step": sec_p * 1e3, "packed_roofline_frac": alg / sec_p / 1e9 / peak if sec_p else None,
+           "packed_streaming_ms_per_step": sec_p_stream * 1e3,
+           "packed_streaming_roofline_frac": alg / sec_p_stream / 1e9 / peak if sec_p_stream else None,
            "l2": f"{sets} rotating input/output sets",
            "geometry": {"n_ants": A, "n_chans_per_gpu": C, "n_chans_total": n_total, "n_samples": T, "n_beams": M,
                         "n_batches": B, "xeng_id": xeng_id}}
@@ -397,14 +422,15 @@ BANDS = {
     "c5": ("SKA-Mid scale: 197 antennas x 4096 channels x 256 samples, 256 beams", 197, 4096, 256, 256, (8,)),
 }
 _MODES = ("ms_per_step", "streaming_ms_per_step", "graph_ms_per_step", "graph_streaming_ms_per_step",
-          "fp16_coeff_streaming_ms_per_step")
+          "fp16_coeff_streaming_ms_per_step", "packed_ms_per_step", "packed_streaming_ms_per_step")
 
 
 def strong_scaling(world, rank, dev, peak, steps, dist=None, emulate=(2, 4, 8)):
     """STRONG scaling: a fixed band cut over `world` GPUs (n_chans_per_gpu = n_chans / world, xeng_id = rank), the
     partitioning BASELINE.json configs[2..4] name.  Every rank times its own share (one heap and 8 heaps per launch;
-    default launches, DCBF_FLAG_STREAMING, both replayed from a CUDA graph, and streaming with the optional single fp16
-    rounding of the coefficients, DCBF_FLAG_FP16_COEFF); the slowest rank's time is reported.
+    default launches, DCBF_FLAG_STREAMING, both replayed from a CUDA graph, streaming with the optional single fp16
+    rounding of the coefficients, DCBF_FLAG_FP16_COEFF, and -- same beams bit for bit -- dcbf_fused_packed on coefficients
+    packed once per delay model, default and streaming); the slowest rank's time is reported.
     `efficiency_vs_n1` = t(whole band on one GPU) / (world * t(share)), the whole band being timed in the same run.
     With one GPU the per-GPU shares of 2, 4 and 8 GPUs are timed on it instead (`emulated_shares`: the shards exchange
     nothing, so a share's kernel time does not depend on the other GPUs)."""
@@ -418,8 +444,8 @@ def strong_scaling(world, rank, dev, peak, steps, dist=None, emulate=(2, 4, 8)):
             for k, v in zip(_MODES, t.tolist()):
                 r[k] = v
         alg = r["algorithmic_bytes_per_launch"]
-        for k in _MODES:
-            r[k.replace("ms_per_step", "roofline_frac")] = alg / (r[k] / 1e3) / 1e9 / peak
+        for k in _MODES:  # (0: the mode does not exist for this shape -- packed coefficients at C5)
+            r[k.replace("ms_per_step", "roofline_frac")] = alg / (r[k] / 1e3) / 1e9 / peak if r[k] else None
         r.pop("input_GBps", None)
         r.pop("beam_gsamples_per_s", None)
         return r
@@ -439,7 +465,7 @@ def strong_scaling(world, rank, dev, peak, steps, dist=None, emulate=(2, 4, 8)):
                 share = timed(A, C // world, T, M, B, C, rank)
                 if whole is not None:
                     for k in _MODES:
-                        share[k.replace("ms_per_step", "efficiency_vs_n1")] = whole[k] / (world * share[k])
+                        share[k.replace("ms_per_step", "efficiency_vs_n1")] = whole[k] / (world * share[k]) if share[k] else None
                 band[key]["share"] = share
             else:
                 band[key]["emulated_shares"] = {}
@@ -449,7 +475,7 @@ def strong_scaling(world, rank, dev, peak, steps, dist=None, emulate=(2, 4, 8)):
                     share = timed(A, C // n, T, M, B, C, n - 1)
                     if whole is not None:
                         for k in _MODES:
-                            share[k.replace("ms_per_step", "efficiency_vs_n1")] = whole[k] / (n * share[k])
+                            share[k.replace("ms_per_step", "efficiency_vs_n1")] = whole[k] / (n * share[k]) if share[k] else None
                     band[key]["emulated_shares"][f"n{n}"] = share
         out["bands"][name] = band
     return out
@@ -683,6 +709,74 @@ def run_ours(args, wl) -> None:
         del beams_h
         barrier()
 
+    # ---- packed steering coefficients: the delay model evaluated once (dcbf_fused_pack_coeffs), every heap loads the
+    # tile sets (dcbf_fused_packed).  Same beams bit for bit, same HBM bytes, a fraction of the SM-side work: the
+    # full-precision figure of a deployment whose delay model changes at control-plane cadence.  Reported beside the
+    # headline, which regenerates the coefficients per heap like the reference's sequence does. ----
+    packed_blk = None
+    n_packed = _capi.fused_packed_bytes(A, C, M, flags) if not args.no_packed else 0
+    if n_packed:
+        packed = torch.empty(n_packed, dtype=torch.uint8, device=dev)
+        outs_p = (torch.empty_like(beams), torch.empty_like(beams))
+        torch.cuda.synchronize()
+        pk0, pk1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            _capi.fused_pack_coeffs(dv, packed, A, C, n_total, M, rank, SAMPLE_PERIOD, flags, stream)
+            pk0.record(stream)
+            for _ in range(5):
+                _capi.fused_pack_coeffs(dv, packed, A, C, n_total, M, rank, SAMPLE_PERIOD, flags, stream)
+            pk1.record(stream)
+        stream.synchronize()
+
+        def pstep(i=0, f=flags):
+            _capi.fused_packed(samples, packed, outs_p[i & 1], B, A, C, n_total, T, M, rank, SAMPLE_PERIOD, f, stream)
+
+        def timed_p(n, f, alternate):
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                q0.record(stream)
+                for i in range(n):
+                    pstep(i if alternate else 0, f)
+                q1.record(stream)
+            stream.synchronize()
+            return q0.elapsed_time(q1) / 1e3 / n
+
+        for _ in range(3):
+            pstep()
+        stream.synchronize()
+        time.sleep(0.3)
+        p_sec = timed_p(args.steps, flags, False)
+        same_p = bool(torch.equal(outs_p[0], beams))
+        time.sleep(0.3)
+        timed_p(3, flags | _capi.FLAG_STREAMING, True)
+        ps_sec = timed_p(args.steps, flags | _capi.FLAG_STREAMING, True)
+        _capi.fused_status()
+        packed_blk = {"ms_per_step": p_sec * 1e3, "value": world * in_bytes / p_sec / 1e9, "unit": UNIT,
+                      "algorithmic_GBps_per_gpu": alg_bytes / p_sec / 1e9, "same_result_bit_for_bit": same_p,
+                      "streaming_ms_per_step": ps_sec * 1e3, "streaming_algorithmic_GBps_per_gpu": alg_bytes / ps_sec / 1e9,
+                      "pack_ms": pk0.elapsed_time(pk1) / 5, "packed_bytes": int(n_packed),
+                      "api": "dcbf_fused_pack_coeffs once per delay model, dcbf_fused_packed per heap",
+                      "note": "tile sets in the tensor cores' layout, as large as delay_vals: same HBM traffic, no phase / sin-cos "
+                              "work per heap; every rank runs it, rank 0's numbers"}
+        if not args.no_sustained:
+            sampler3 = ClockSampler(local)
+            sampler3.start()
+            t_s0 = time.time()
+            while time.time() - t_s0 < 0.5:
+                for _ in range(100):
+                    pstep()
+                stream.synchronize()
+            t_u0 = time.time()
+            ps_sus = timed_p(200, flags, False)
+            t_u1 = time.time()
+            packed_blk["sustained"] = {"ms_per_step": ps_sus * 1e3, "algorithmic_GBps_per_gpu": alg_bytes / ps_sus / 1e9,
+                                       "clocks": sampler3.window(t_u0, t_u1),
+                                       "note": "200 steps timed after 0.5 s of continuous launches, like roofline.sustained"}
+            sampler3.stop()
+            time.sleep(0.3)
+        del outs_p, packed
+        barrier()
+
     # ---- requantised int8 output (dcbf_fused_q8): the SURVEY 8f-2 extension, reported beside the headline ----
     q8 = None
     if not args.no_q8:
@@ -857,6 +951,11 @@ def run_ours(args, wl) -> None:
     achieved = alg_bytes / mean_launch_s / 1e9
     if q8 is not None:
         q8["roofline_frac"] = q8["algorithmic_GBps_per_gpu"] / peak
+    if packed_blk is not None:
+        packed_blk["roofline_frac"] = packed_blk["algorithmic_GBps_per_gpu"] / peak
+        packed_blk["streaming_roofline_frac"] = packed_blk["streaming_algorithmic_GBps_per_gpu"] / peak
+        if "sustained" in packed_blk:
+            packed_blk["sustained"]["roofline_frac"] = packed_blk["sustained"]["algorithmic_GBps_per_gpu"] / peak
     if fp16c is not None:
         fp16c["roofline_frac"] = fp16c["algorithmic_GBps_per_gpu"] / peak
         if "sustained" in fp16c:
@@ -892,7 +991,7 @@ def run_ours(args, wl) -> None:
         "beam_gsamples_per_s": world * B * 2 * C * T * M / sec_per_step / 1e9,
         "algorithmic_GBps": world * alg_bytes / sec_per_step / 1e9,
         "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_verbatim": _verbatim_cpu(), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "sustained": sustained, "streaming": streaming, "fp16_coeff": fp16c, "q8_output": q8, "other_workloads": secondary, "gather": gather,
+        "sustained": sustained, "streaming": streaming, "fp16_coeff": fp16c, "packed_coeffs": packed_blk, "q8_output": q8, "other_workloads": secondary, "gather": gather,
         "strong_scaling": strong,
         "pcie": {"note": "e2e is bounded by the host link: pinned copies measured on this pool (tools/bench_standalone.py) "
                          "reach 55.5 GB/s H2D, 57.3 GB/s D2H alone and 49.9 GB/s each way when both directions run "
@@ -916,6 +1015,7 @@ def main() -> None:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=["c1", "c2", "c3"], default="c3")
     ap.add_argument("--fp16-coeff", action="store_true", help="single fp16 coefficient rounding (DCBF_FLAG_FP16_COEFF)")
+    ap.add_argument("--no-packed", action="store_true", help="skip the packed_coeffs block (dcbf_fused_pack_coeffs / dcbf_fused_packed)")
     ap.add_argument("--no-fp16-coeff", action="store_true", help="skip the fp16_coeff block (the optional single-rounding mode beside the default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-streaming", action="store_true")

@@ -52,7 +52,9 @@ def main():
                   f"{r['streaming_ms_per_step'] * 1e3:8.1f} us {r['streaming_roofline_frac']:.3f} | graph "
                   f"{r['graph_ms_per_step'] * 1e3:8.1f} us {r['graph_roofline_frac']:.3f} | graph+streaming "
                   f"{r['graph_streaming_ms_per_step'] * 1e3:8.1f} us {r['graph_streaming_roofline_frac']:.3f} | fp16 coeff + streaming "
-                  f"{r['fp16_coeff_streaming_ms_per_step'] * 1e3:8.1f} us {r['fp16_coeff_streaming_roofline_frac']:.3f} | host "
+                  f"{r['fp16_coeff_streaming_ms_per_step'] * 1e3:8.1f} us {r['fp16_coeff_streaming_roofline_frac']:.3f} | packed "
+                  f"{r['packed_ms_per_step'] * 1e3:8.1f} us {r['packed_roofline_frac'] or 0:.3f} | packed + streaming "
+                  f"{r['packed_streaming_ms_per_step'] * 1e3:8.1f} us {r['packed_streaming_roofline_frac'] or 0:.3f} | host "
                   f"{r['host_us_per_launch']:6.1f} us/launch | ideal {r['algorithmic_bytes_per_launch'] / peak / 1e3:8.1f} us",
                   flush=True)
     print(json.dumps(rows))
