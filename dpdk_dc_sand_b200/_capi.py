@@ -59,6 +59,10 @@ SIGNATURES = {
                                          C.c_void_p, C.c_uint, C.c_void_p]),
     "dcbf_fused_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_double, C.c_uint, C.c_void_p]),
+    "dcbf_fused_pack_coeffs_q8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_double, C.c_uint, C.c_void_p]),
+    "dcbf_fused_packed_q8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint, C.c_void_p]),
     "dcbf_fused_status": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dcbf_fused_status_poll": (C.c_int, []),
     "dcbf_debug_set_profile_buffer": (None, [C.c_void_p]),
@@ -299,6 +303,23 @@ def fused_packed(samples, packed, beams, n_batches, n_ants, n_chans, n_chans_tot
     check(load().dcbf_fused_packed(_ptr(samples), _ptr(packed), _ptr(beams), n_batches, n_ants, n_chans, n_chans_total,
                                    n_samples, n_beams, xeng_id, float(sample_period), flags, _stream_handle(stream)),
           "dcbf_fused_packed")
+
+
+def fused_pack_coeffs_q8(delay_vals, gains, packed, n_ants, n_chans, n_chans_total, n_beams, xeng_id, sample_period,
+                         flags=0, stream=None) -> None:
+    """dcbf_fused_pack_coeffs_q8: tile sets for fused_packed_q8 (the quantisation gains are folded in)."""
+    check(load().dcbf_fused_pack_coeffs_q8(_ptr(delay_vals), _ptr(gains), _ptr(packed), n_ants, n_chans, n_chans_total,
+                                           n_beams, xeng_id, float(sample_period), flags, _stream_handle(stream)),
+          "dcbf_fused_pack_coeffs_q8")
+
+
+def fused_packed_q8(samples, packed, gains, beams_q8, n_batches, n_ants, n_chans, n_chans_total, n_samples, n_beams,
+                    xeng_id, sample_period, flags=0, stream=None, saturated=None) -> None:
+    """dcbf_fused_packed_q8: fused_q8 on packed coefficients."""
+    check(load().dcbf_fused_packed_q8(_ptr(samples), _ptr(packed), _ptr(gains), _ptr(beams_q8),
+                                      _ptr(saturated) if saturated is not None else None, n_batches, n_ants, n_chans,
+                                      n_chans_total, n_samples, n_beams, xeng_id, float(sample_period), flags,
+                                      _stream_handle(stream)), "dcbf_fused_packed_q8")
 
 
 def fused_bytes(n_batches, n_ants, n_chans, n_samples, n_beams) -> int:

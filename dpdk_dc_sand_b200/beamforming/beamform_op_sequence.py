@@ -216,6 +216,29 @@ class QuantisedOpSequence(accel.Operation):
         self.fp16_coeff = False
         self.batch_times = None
         self._saturated = None
+        self._packed = None
+
+    def pack_coefficients(self) -> bool:
+        """As ``OpSequence.pack_coefficients``: the bound delay model AND gains evaluated once
+        (``dcbf_fused_pack_coeffs_q8``); pack again after writing either.  False for shapes without a whole tile set."""
+        import torch
+
+        r = self.template.preBeamformReorder_template
+        c = self.template.beamform_coeff_template
+        flags = _capi.FLAG_FP16_COEFF if self.fp16_coeff else 0
+        nbytes = _capi.fused_packed_bytes(r.n_ants, r.n_channels_per_stream, c.n_beams, flags)
+        if not nbytes:
+            self._packed = None
+            return False
+        dv = self.buffer("bufin_delay_vals").buffer
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=dv.device)
+        _capi.fused_pack_coeffs_q8(dv, self.buffer("bufin_gains").buffer, packed, r.n_ants, r.n_channels_per_stream,
+                                   c.n_channels, c.n_beams, c.xeng_id, c.sample_period, flags, self.command_queue.stream)
+        self._packed = (packed, flags)
+        return True
+
+    def release_coefficients(self) -> None:
+        self._packed = None
 
     @property
     def saturated(self) -> int:
@@ -232,6 +255,13 @@ class QuantisedOpSequence(accel.Operation):
         with torch.cuda.stream(self.command_queue.stream):
             self._saturated.zero_()
         flags = (_capi.FLAG_SIGNED_INPUT if self.signed_input else 0) | (_capi.FLAG_FP16_COEFF if self.fp16_coeff else 0)
+        if self._packed is not None and self.batch_times is None and self._packed[1] == (flags & _capi.FLAG_FP16_COEFF):
+            _capi.fused_packed_q8(
+                self.buffer("bufin_reorder").buffer, self._packed[0], gains, self.buffer("bufout_q8").buffer, r.n_batches,
+                r.n_ants, r.n_channels_per_stream, c.n_channels, r.n_samples_per_channel, c.n_beams, c.xeng_id,
+                c.sample_period, flags, self.command_queue.stream, saturated=self._saturated,
+            )
+            return
         _capi.fused_q8(
             self.buffer("bufin_reorder").buffer, self.buffer("bufin_delay_vals").buffer, gains,
             self.buffer("bufout_q8").buffer, r.n_batches, r.n_ants, r.n_channels_per_stream, c.n_channels,

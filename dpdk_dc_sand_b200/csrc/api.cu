@@ -239,6 +239,35 @@ int dcbf_fused_packed(const uint8_t* samples, const void* packed, float* beams, 
                         const_cast<uint8_t*>(static_cast<const uint8_t*>(packed)));
 }
 
+int dcbf_fused_pack_coeffs_q8(const float* delay_vals, const float* beam_gains, void* packed, int A, int C, int N, int M,
+                              int xeng_id, double sample_period, unsigned flags, dcbf_stream_t stream) {
+    if (!delay_vals || !beam_gains || !packed || A <= 0 || C <= 0 || N <= 0 || M <= 0 || xeng_id < 0 || !(sample_period > 0.0))
+        return DCBF_ERR_INVALID_ARG;
+    if (!aligned16(delay_vals) || !aligned16(packed)) return DCBF_ERR_INVALID_ARG;
+    if (!dcbf_fused_packed_bytes(A, C, M, flags)) return DCBF_ERR_UNSUPPORTED;
+    if (int e = check_device()) return e;
+    uint8_t* img = static_cast<uint8_t*>(packed);
+    const QuantisedOut q8{reinterpret_cast<int8_t*>(img), beam_gains, nullptr};  // (the int8 kernel: its coefficients carry gain / max|gain|)
+    return launch_fused(img, delay_vals, nullptr, 1, A, C, N, 128, M, static_cast<long long>(C) * xeng_id, sample_period, nullptr,
+                        flags & (DCBF_FLAG_FP16_COEFF | DCBF_FLAG_SIGNED_INPUT), static_cast<cudaStream_t>(stream), &q8, nullptr,
+                        0.0, 0, 1, img);
+}
+
+int dcbf_fused_packed_q8(const uint8_t* samples, const void* packed, const float* beam_gains, int8_t* beams_q8,
+                         unsigned long long* saturated, int B, int A, int C, int N, int T, int M, int xeng_id,
+                         double sample_period, unsigned flags, dcbf_stream_t stream) {
+    if (!samples || !packed || !beam_gains || !beams_q8 || B <= 0 || A <= 0 || C <= 0 || N <= 0 || M <= 0 || xeng_id < 0 ||
+        bad_t(T) || !(sample_period > 0.0))
+        return DCBF_ERR_INVALID_ARG;
+    if (!aligned16(samples) || !aligned16(packed) || !aligned16(beams_q8)) return DCBF_ERR_INVALID_ARG;
+    if (!dcbf_fused_packed_bytes(A, C, M, flags)) return DCBF_ERR_UNSUPPORTED;
+    if (int e = check_device()) return e;
+    const QuantisedOut q8{beams_q8, beam_gains, saturated};
+    return launch_fused(samples, nullptr, nullptr, B, A, C, N, T, M, static_cast<long long>(C) * xeng_id, sample_period, nullptr,
+                        flags, static_cast<cudaStream_t>(stream), &q8, nullptr, 0.0, 0, 2,
+                        const_cast<uint8_t*>(static_cast<const uint8_t*>(packed)));
+}
+
 int dcbf_fused_status(int* role, int* barrier, int* block) {
     if (int e = check_device()) return e;
     return fused_status(role, barrier, block);

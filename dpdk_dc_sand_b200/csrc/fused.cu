@@ -2032,8 +2032,8 @@ int launch_fused(const uint8_t* samples, const float* delay_vals, float* beams, 
         p.raw_extra_off = used;
         p.raw_stages = kRawStages + 2 * std::min(spare, (kMaxRawStages - kRawStages) / 2);
     }
-    if (packed_mode) {  // whole tile sets, static steering, float32 beams only (the shapes packed_bytes() answers for)
-        if (kstream || batch_dt_s || q8 || !packed) return DCBF_ERR_UNSUPPORTED;
+    if (packed_mode) {  // whole tile sets, static steering (the shapes packed_bytes() answers for)
+        if (kstream || batch_dt_s || !packed) return DCBF_ERR_UNSUPPORTED;
         p.packed_bytes = p.kb_count * p.parts * p.nt * 128;
         if (packed_mode == 1) flags |= DCBF_FLAG_DEBUG_WHOLE_CHANNELS;  // every channel is generated (and written) once
         else flags |= DCBF_FLAG_DEBUG_NO_BEAM_PIECES;                   // a piece of a cut channel loads the whole tile set

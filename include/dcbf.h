@@ -215,7 +215,7 @@ int dcbf_fused_status_poll(void);
  * one bulk copy per channel instead of 4096 phase / sin-cos evaluations per channel and heap.  Same HBM traffic
  * (a tile set is as large as the channel's delay_vals for the hi+lo pair), bit-identical beams, a fraction of the
  * SM-side work -- which is what a power-capped board runs out of first.
- * Static steering, float32 beams, shapes whose tile set fits one shared-memory buffer (dcbf_fused_tiling nt_count == 1:
+ * Static steering, shapes whose tile set fits one shared-memory buffer (dcbf_fused_tiling nt_count == 1:
  * up to 64 antennas x 64 beams, 128 x 32, 256 x 16 ...); otherwise dcbf_fused_packed_bytes returns 0 and the two calls
  * DCBF_ERR_UNSUPPORTED.  flags: DCBF_FLAG_FP16_COEFF must be the same in all three calls; DCBF_FLAG_SIGNED_INPUT and
  * DCBF_FLAG_STREAMING as for dcbf_fused (a streaming launch must not directly follow the pack it reads on the stream:
@@ -228,6 +228,17 @@ int dcbf_fused_pack_coeffs(const float* delay_vals, void* packed, int n_ants, in
 int dcbf_fused_packed(const uint8_t* samples, const void* packed, float* beams, int n_batches, int n_ants, int n_chans,
                       int n_chans_total, int n_samples, int n_beams, int xeng_id, double sample_period, unsigned flags,
                       dcbf_stream_t stream);
+
+/* The same for the int8 requantised output (dcbf_fused_q8): the per-beam gains ride on the coefficients (relative to
+ * max|gain|), so they are part of the packed tile sets -- pack again when the gains change -- and are passed to the hot
+ * call as well (its epilogue scales by max|gain|).  Bit-identical to dcbf_fused_q8 with the same arguments. */
+int dcbf_fused_pack_coeffs_q8(const float* delay_vals, const float* beam_gains, void* packed, int n_ants, int n_chans,
+                              int n_chans_total, int n_beams, int xeng_id, double sample_period, unsigned flags,
+                              dcbf_stream_t stream);
+int dcbf_fused_packed_q8(const uint8_t* samples, const void* packed, const float* beam_gains, int8_t* beams_q8,
+                         unsigned long long* saturated, int n_batches, int n_ants, int n_chans, int n_chans_total,
+                         int n_samples, int n_beams, int xeng_id, double sample_period, unsigned flags,
+                         dcbf_stream_t stream);
 
 /* Developer aid: when non-NULL, every dcbf_fused CTA writes 24 uint64 to dev_ptr[blockIdx*24 + role*4 + slot]:
  * nanoseconds each warp role spent blocked per barrier class (slot 0..2) and the role's span (slot 3).

@@ -1178,6 +1178,59 @@ def test_packed_coefficients_give_the_same_beams(dropin, case):
             assert np.all(np.abs(got.cpu().numpy().astype(np.float64) - ref) <= _budget(x, bool(flags & 1)))
 
 
+@pytest.mark.parametrize("case", [(1, 64, 300, 256, 64, 0), (2, 64, 170, 256, 16, 0), (1, 80, 40, 256, 32, 0), (2, 5, 7, 48, 3, 0),
+                                  (1, 33, 200, 144, 8, 2), (1, 1, 20, 64, 16, 1)],
+                         ids=lambda c: "B{}A{}C{}T{}M{}f{}".format(*c))
+def test_packed_coefficients_int8_output(dropin, case):
+    """dcbf_fused_pack_coeffs_q8 + dcbf_fused_packed_q8 against dcbf_fused_q8: the same int8 beams and the same
+    saturation count (the gains ride on the packed coefficients), and the oracle's requantisation within one step."""
+    import torch
+
+    from dpdk_dc_sand_b200 import _capi
+
+    b, a, c, t, m, flags = case
+    dev = torch.device("cuda", 0)
+    n, xid = 2 * c, 1
+    x = orc.make_samples(b, a, c, t, seed=500 + a)
+    dv = orc.make_delay_vals_random(c, m, a, seed=600 + m)
+    gains = np.linspace(0.004, 0.03, m).astype(np.float32)
+    dx, ddv, dg = (torch.from_numpy(v).to(dev) for v in (x, dv, gains))
+    want = torch.zeros((b, 2, c, t // 16, 16, 2 * m), dtype=torch.int8, device=dev)
+    got = torch.full_like(want, 77)
+    sat_w, sat_g = (torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(2))
+    packed = torch.empty(_capi.fused_packed_bytes(a, c, m, flags), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    _capi.fused_q8(dx, ddv, dg, want, b, a, c, n, t, m, xid, TS, flags, saturated=sat_w)
+    _capi.fused_pack_coeffs_q8(ddv, dg, packed, a, c, n, m, xid, TS, flags & _capi.FLAG_FP16_COEFF)
+    _capi.fused_packed_q8(dx, packed, dg, got, b, a, c, n, t, m, xid, TS, flags, saturated=sat_g)
+    torch.cuda.synchronize()
+    _capi.fused_status()
+    assert torch.equal(got, want)
+    assert int(sat_g.item()) == int(sat_w.item())
+    ref, _ = orc.requantise(orc.beamform_pipeline(x, dv, n, xid, TS, signed_input=bool(flags & 1)), gains)
+    assert np.abs(got.cpu().numpy().astype(np.int32) - ref.astype(np.int32)).max() <= 1
+
+
+def test_packed_coefficients_int8_operator(dropin):
+    """QuantisedOpSequence.pack_coefficients(): same int8 beams and saturation count as the per-call path."""
+    from beamforming.beamform_op_sequence import QuantisedOpSequenceTemplate
+
+    ctx, queue = dropin
+    b, a, c, t, m, n, xid = 1, 64, 20, 256, 64, 4096, 1
+    op = QuantisedOpSequenceTemplate(ctx, b, 2, c, n, t // 16, 16, a, m, xid, TS, t).instantiate(queue)
+    op.ensure_all_bound()
+    op.buffer("bufin_reorder").set(queue, orc.make_samples(b, a, c, t, seed=9))
+    op.buffer("bufin_delay_vals").set(queue, orc.make_delay_vals_random(c, m, a, seed=10))
+    op.buffer("bufin_gains").set(queue, np.full(m, 0.03, np.float32))
+    op()
+    want, sat = op.buffer("bufout_q8").get(queue).copy(), op.saturated
+    assert op.pack_coefficients()
+    op.buffer("bufout_q8").zero(queue)
+    op()
+    assert np.array_equal(op.buffer("bufout_q8").get(queue), want)
+    assert op.saturated == sat and sat > 0
+
+
 def test_packed_coefficients_through_the_operator_and_unsupported_shapes(dropin):
     """OpSequence.pack_coefficients(): the calls after it load the packed tile sets (one launch each, same beams as
     before); a new delay model needs a new pack; shapes without a whole tile set stay on the per-call path."""
