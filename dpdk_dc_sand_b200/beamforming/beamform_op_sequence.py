@@ -134,7 +134,8 @@ class OpSequence(accel.OperationSequence):
             self._packed = None
             return False
         dv = self.buffer("bufin_delay_vals").buffer
-        packed = torch.empty(nbytes, dtype=torch.uint8, device=dv.device)
+        with torch.cuda.stream(self.command_queue.stream):  # (the block belongs to the stream whose launches read it: a
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=dv.device)  # replaced pack is reused in stream order)
         _capi.fused_pack_coeffs(dv, packed, r.n_ants, r.n_channels_per_stream, c.n_channels, c.n_beams, c.xeng_id,
                                 c.sample_period, flags, self.command_queue.stream, weights=weights)
         self._packed = (packed, flags)
@@ -231,7 +232,8 @@ class QuantisedOpSequence(accel.Operation):
             self._packed = None
             return False
         dv = self.buffer("bufin_delay_vals").buffer
-        packed = torch.empty(nbytes, dtype=torch.uint8, device=dv.device)
+        with torch.cuda.stream(self.command_queue.stream):  # (the block belongs to the stream whose launches read it: a
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=dv.device)  # replaced pack is reused in stream order)
         _capi.fused_pack_coeffs_q8(dv, self.buffer("bufin_gains").buffer, packed, r.n_ants, r.n_channels_per_stream,
                                    c.n_channels, c.n_beams, c.xeng_id, c.sample_period, flags, self.command_queue.stream)
         self._packed = (packed, flags)

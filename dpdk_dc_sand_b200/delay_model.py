@@ -79,4 +79,8 @@ class DelayModelUpdater:
         if w_dev is not None:
             self.op.beam_weights = w_dev
         self._active, self._pending = idx, None
+        # an operation that runs on packed steering coefficients gets the new model packed here, on the compute stream
+        # behind the upload: launches already queued keep the old tile sets, later ones read the new ones
+        if getattr(self.op, "_packed", None) is not None:
+            self.op.pack_coefficients()
         return True

@@ -741,6 +741,39 @@ def test_delay_model_updater_switches_at_a_heap_boundary(dropin):
     assert np.all(np.abs(out2 - orc.beamform_pipeline(x, dv0, n, xid, TS, weights=w1)) <= 1.5 * _budget(x))
 
 
+def test_delay_model_updater_repacks_the_coefficients(dropin):
+    """The same hook on an operation that runs on packed steering coefficients: activate() packs the new model on the
+    compute stream, heaps queued before it still get the old tile sets."""
+    from beamforming.beamform_op_sequence import OpSequenceTemplate
+    from dpdk_dc_sand_b200 import _capi
+    from dpdk_dc_sand_b200.delay_model import DelayModelUpdater
+
+    ctx, queue = dropin
+    b, a, c, t, m, n, xid = 1, 64, 30, 256, 16, 1024, 0
+    x = orc.make_samples(b, a, c, t, seed=181)
+    dv0 = orc.make_delay_vals_random(c, m, a, seed=182)
+    dv1 = orc.make_delay_vals_random(c, m, a, seed=183)
+    op = OpSequenceTemplate(ctx, b, 2, c, n, t // 16, 16, a, m, xid, TS, t).instantiate(queue)
+    op.ensure_all_bound()
+    op.buffer("bufin_reorder").set(queue, x)
+    op.buffer("bufin_delay_vals").set(queue, dv0)
+    assert op.pack_coefficients()
+    upd = DelayModelUpdater(op)
+    upd.update(dv1)
+    op()
+    out0 = op.buffer("bufout_mult").get(queue).astype(np.float64)
+    first_pack = op._packed[0]
+    assert upd.activate()
+    assert op._packed is not None and op._packed[0] is not first_pack
+    n0 = _capi.launch_count()
+    op()
+    assert _capi.launch_count() - n0 == 1
+    out1 = op.buffer("bufout_mult").get(queue).astype(np.float64)
+    _capi.fused_status()
+    assert np.all(np.abs(out0 - orc.beamform_pipeline(x, dv0, n, xid, TS)) <= _budget(x))
+    assert np.all(np.abs(out1 - orc.beamform_pipeline(x, dv1, n, xid, TS)) <= _budget(x))
+
+
 def test_ingest_ring_feeds_the_host_plan(dropin):
     """SURVEY 8f-3 end to end: heaps -> page-locked chunk (dcbf_ingest_*) -> dcbf_host_plan_run -> beams."""
     from dpdk_dc_sand_b200 import _capi
