@@ -20,6 +20,11 @@ from oracle import beamform_oracle as orc  # noqa: E402
 TS = orc.SAMPLE_PERIOD
 
 
+def _capi_weights_log2(weights) -> int:
+    """The power-of-two scale fused_ex would put on these weights (0: none, the only case the packed path takes)."""
+    return 0  # the sweep's weights are in [0, 1.5]: fused_ex is called here without weights_log2
+
+
 def main():
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
@@ -119,11 +124,33 @@ def main():
             plan.run(x, dv, h_out)
             plan.close()
             ok_plan = bool(np.array_equal(h_out, out.cpu().numpy()))
-        ok = ratio <= 1.0 and ok_re and eb < 4e-6 and ec <= 2.5e-6 and ok_plan
+        # packed steering coefficients (shapes with a whole tile set): bit-equal to the per-call result, weights included
+        ok_packed = True
+        if mode in ("plain", "weights", "q8") and _capi.fused_packed_bytes(A, C, M, flags):
+            pk = torch.full((_capi.fused_packed_bytes(A, C, M, flags),), 0xEE, dtype=torch.uint8, device=dev)
+            if mode == "q8":
+                dg = torch.from_numpy(gains).to(dev)
+                o2 = torch.full(out.shape, 55, dtype=torch.int8, device=dev)
+                sat2 = torch.zeros(1, dtype=torch.int64, device=dev)
+                torch.cuda.synchronize()
+                _capi.fused_pack_coeffs_q8(ddv, dg, pk, A, C, n_total, M, xid, TS, flags & _capi.FLAG_FP16_COEFF)
+                _capi.fused_packed_q8(dx, pk, dg, o2, B, A, C, n_total, T, M, xid, TS, flags, saturated=sat2)
+                torch.cuda.synchronize()
+                ok_packed = bool(torch.equal(o2, out8)) and int(sat2.item()) == int(sat.item())
+            elif weights is None or _capi_weights_log2(weights) == 0:
+                o2 = torch.full_like(out, float("nan"))
+                torch.cuda.synchronize()
+                _capi.fused_pack_coeffs(ddv, pk, A, C, n_total, M, xid, TS, flags & _capi.FLAG_FP16_COEFF,
+                                        weights=None if weights is None else torch.from_numpy(weights).to(dev))
+                _capi.fused_packed(dx, pk, o2, B, A, C, n_total, T, M, xid, TS, flags)
+                torch.cuda.synchronize()
+                ok_packed = bool(torch.equal(o2, out))
+            _capi.fused_status()
+        ok = ratio <= 1.0 and ok_re and eb < 4e-6 and ec <= 2.5e-6 and ok_plan and ok_packed
         bad += not ok
         if not ok or case % 20 == 0 or A > 512:
             print(tag, f"fused err/budget {ratio:.2e} reorder {'ok' if ok_re else 'BAD'} beamform {eb:.2e} coeffs {ec:.1e} "
-                       f"plan {'ok' if ok_plan else 'BAD'} {'ok' if ok else 'FAIL'}", flush=True)
+                       f"plan {'ok' if ok_plan else 'BAD'} packed {'ok' if ok_packed else 'BAD'} {'ok' if ok else 'FAIL'}", flush=True)
     print(f"{n_cases} cases, {bad} failed; worst fused err/budget {worst_f:.2e} ({worst_tag}), worst beamform err/sum|x||w| {worst_b:.2e}")
     sys.exit(1 if bad else 0)
 
