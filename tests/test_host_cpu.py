@@ -71,6 +71,13 @@ def test_algorithmic_bytes_and_tiling():
             parts = 1 if flags else 2
             assert kb == -(-a // 32) and nt % 16 == 0 and 16 <= nt <= 128
             assert nt * ntc >= 2 * m and kb * parts * nt * 128 <= 64 * 1024
+            # packed steering coefficients: one tile set per channel where a whole one exists, none for K-streamed shapes
+            want = 7 * kb * parts * nt * 128 if ntc == 1 else 0
+            assert _capi.fused_packed_bytes(a, 7, m, flags) == want
+    # at C3 a channel's tile set is exactly as large as its delay_vals (64 KiB): the hot path's HBM traffic is unchanged
+    assert _capi.fused_packed_bytes(64, 4096, 64) == 4096 * 64 * 64 * 16 == 4096 * 65536
+    assert _capi.fused_packed_bytes(64, 4096, 64, _capi.FLAG_FP16_COEFF) == 4096 * 32768
+    assert _capi.fused_packed_bytes(197, 512, 256) == 0 and _capi.fused_packed_bytes(0, 1, 1) == 0
 
 
 def test_templates_reproduce_reference_shape_algebra():
